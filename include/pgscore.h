@@ -1,0 +1,132 @@
+/*
+ * pgscore.h — C ABI of libpgscore.so, the B200 (sm_100a) scorer for ProteinGym's PLM log-likelihood hot path.
+ *
+ * ProteinGym has no FFI/plugin API; its "operator interface" for this path is the Python call sequence in
+ * proteingym/baselines/esm/compute_fitness.py (reference root: OATML-Markslab/ProteinGym). Each entry point below
+ * names the reference code it replaces. All buffers are plain device pointers owned by the caller (PyTorch
+ * allocations in our host code); the library never frees caller memory and keeps its own workspace inside the handle.
+ * Calls are asynchronous on the given stream; the caller synchronises. Errors: non-zero return code + pg_last_error().
+ * No C++ exceptions cross this boundary. A handle is bound to one device and is not thread-safe.
+ */
+#ifndef PGSCORE_H
+#define PGSCORE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pg_handle_s* pg_handle;
+typedef void* pg_stream; /* cudaStream_t */
+
+enum pg_status { PG_OK = 0, PG_ERR_ARG = 1, PG_ERR_CUDA = 2, PG_ERR_STATE = 3, PG_ERR_UNSUPPORTED = 4 };
+
+enum pg_arch {
+  PG_ARCH_ESM1B = 0, /* ESM-1b / ESM-1v: learned positions (esm/model/esm1.py:83-102) */
+  PG_ARCH_ESM2 = 1   /* ESM2: rotary (esm/model/esm2.py:40-74) */
+};
+
+/* Tensor-core operand precision. The reference is strict fp32.
+ *  PG_PREC_F16X3: every GEMM/attention operand is split into fp16 hi+lo and three tcgen05 passes (hi*hi + lo*hi + hi*lo)
+ *                 accumulate in fp32 — ~22-bit operands; meets the 1e-3 abs per-mutant parity target.
+ *  PG_PREC_F16  : single fp16 pass, fp32 accumulate; ~3x faster, |error| ~1e-2 on scores of std ~6 (Spearman > 0.999). */
+enum pg_precision { PG_PREC_F16 = 0, PG_PREC_F16X3 = 1 };
+
+typedef struct {
+  int32_t arch;            /* pg_arch */
+  int32_t layers;          /* args.layers / cfg.encoder_layers */
+  int32_t embed_dim;       /* args.embed_dim */
+  int32_t heads;           /* args.attention_heads; head_dim must be 64 */
+  int32_t ffn_dim;         /* args.ffn_embed_dim (ESM2: 4*embed_dim, esm2.py:52) */
+  int32_t vocab;           /* 33 */
+  int32_t max_positions;   /* learned-position table rows - 2 (ESM-1b: 1024) */
+  int32_t token_dropout;   /* esm1.py:125 / esm2.py:85 */
+  int32_t emb_ln_before;   /* esm1.py:135-136; decided by key presence in the checkpoint (pretrained.py:80-82) */
+  int32_t precision;       /* pg_precision */
+  int32_t device;          /* CUDA device ordinal */
+  int32_t max_rows;        /* workspace capacity in token rows (sequences x window length) per pass; 0 = default */
+} pg_model_desc;
+
+typedef struct {
+  const char* name;   /* reference state_dict key after prefix stripping, e.g. "layers.0.self_attn.q_proj.weight" */
+  const void* data;   /* device pointer, fp32, contiguous */
+  int64_t shape[2];   /* [rows, cols]; 1-D tensors use shape[1] = 1 */
+} pg_tensor;
+
+/* Replaces pretrained.load_model_and_alphabet + model.cuda() (compute_fitness.py:349-353; esm/pretrained.py:24-218):
+ * create a model instance, then hand it the (already key-normalised) fp32 state dict; the library repacks into its own
+ * fp16 hi/lo buffers (q scaling folded in, multihead_attention.py:261), so the caller may free its tensors. */
+int pg_create(const pg_model_desc* desc, pg_handle* out);
+int pg_load_weights(pg_handle h, const pg_tensor* tensors, int32_t n);
+int pg_destroy(pg_handle h);
+const char* pg_last_error(pg_handle h); /* h may be NULL: returns the last creation error */
+
+/* Replaces the masked-marginals loop (compute_fitness.py:486-504) — L+2 batch-1 forwards of
+ * ProteinBertModel/ESM2.forward (esm1.py:116-193 / esm2.py:76-143) + log_softmax + row pick — by one batched pass.
+ *   tokens     [n_tokens] int32 (device): <cls> seq <eos> of the FULL sequence
+ *   positions  [P] int32 (device): token index i to mask for row p; -1 = no mask (wt-marginals row)
+ *   win_start  [P] int32 (device) or NULL (= all 0): first token of row p's window (get_optimal_window, utils/scoring_utils.py:43-52)
+ *   out_row    [P] int32 (device) or NULL: which token index of the window to emit for row p, relative to the full
+ *              sequence; NULL = positions[p]
+ *   T          window length (<= 1024 for ESM-1b; tokens per row)
+ *   out_logprobs [P, vocab] fp32 (device): log_softmax(logits)[out_row - win_start]
+ * All rows share T (no padding exists on this path). */
+int pg_masked_marginals(pg_handle h, const int32_t* tokens, int32_t n_tokens, const int32_t* positions,
+                        const int32_t* win_start, const int32_t* out_row, int32_t P, int32_t T, float* out_logprobs,
+                        pg_stream stream);
+
+/* Full-table variant used by wt-marginals (compute_fitness.py:475): one unmasked (or arbitrarily masked) forward of
+ * `T` tokens starting at `win_start`, emitting log_softmax for every token: out [T, vocab]. mask_pos = -1 for none. */
+int pg_forward_logprobs(pg_handle h, const int32_t* tokens, int32_t n_tokens, int32_t win_start, int32_t T,
+                        int32_t mask_pos, float* out_logprobs, pg_stream stream);
+
+/* Replaces label_row over the whole DMS frame (compute_fitness.py:240-250, :505-514):
+ *   score[m] = sum_{s in [row_offsets[m], row_offsets[m+1])} table[site_row[s], site_mt[s]] - table[site_row[s], site_wt[s]]
+ * table [n_rows, vocab] fp32; site_* int32 CSR arrays (device); out_scores [M] fp32. Fixed summation order per mutant. */
+int pg_score_mutants(const float* table, int32_t n_rows, int32_t vocab, const int32_t* site_row, const int32_t* site_wt,
+                     const int32_t* site_mt, const int32_t* row_offsets, int32_t M, float* out_scores,
+                     pg_stream stream);
+
+/* ---- kernel-level entry points (used by the parity tests and bench roofline legs; same kernels as above) ---- */
+
+/* C = epilogue(A[M,K] * W[N,K]^T + bias). fp16 operands in [hi | lo] column blocks when nseg == 3.
+ *   a: [M, lda] fp16 (lda >= K, or >= 2K with lo at column offset K when nseg == 3); w: [N, ldw] likewise.
+ *   epi 0: out_h[M, ldo] = fp16(acc + bias) (lo part at column offset out_lo_off if > 0)
+ *   epi 1: same with exact-erf GELU (esm/modules.py:17-24)
+ *   epi 2: resid[M, ldr] (fp32) += acc + bias
+ *   epi 3: as 0, with rotary applied to the first 2*rot_dim columns ([q | k], heads of 64; esm/rotary_embedding.py:11-20),
+ *          token index = row % rot_T, cos/sin tables [rot_T, 32] fp32 in rot_cos/rot_sin. */
+typedef struct {
+  const void* a; int64_t lda;
+  const void* w; int64_t ldw;
+  const float* bias;
+  int32_t M, N, K, nseg, epi;
+  void* out_h; int64_t ldo; int64_t out_lo_off;
+  float* resid; int64_t ldr;
+  const float* rot_cos; const float* rot_sin; int32_t rot_T; int32_t rot_dim;
+} pg_gemm_args;
+int pg_gemm(const pg_gemm_args* args, pg_stream stream);
+
+/* LayerNorm (eps 1e-5, esm/modules.py:68-81) of fp32 rows -> fp16 hi (and lo at column offset lo_off if > 0). */
+int pg_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int32_t rows, int32_t d,
+                     void* out, int64_t ldo, int64_t lo_off, pg_stream stream);
+
+/* Multi-head self-attention over equal-length sequences (multihead_attention.py:357-394), head_dim 64, q pre-scaled.
+ *   qkv [B*T, ld] fp16 with q at column 0, k at column d, v at 2d (d = heads*64); lo parts at +lo_off when nseg == 3.
+ *   out [B*T, ldo] fp16 (lo at +out_lo_off). causal/alibi are for the Tranception path (model_pytorch.py:155-183). */
+typedef struct {
+  const void* qkv; int64_t ld; int64_t lo_off;
+  void* out; int64_t ldo; int64_t out_lo_off;
+  int32_t B, T, heads, nseg;
+  int32_t causal; const float* alibi_slopes; /* NULL = none */
+} pg_attn_args;
+int pg_attention(const pg_attn_args* args, pg_stream stream);
+
+/* Build/version probe (also what the CPU-only test suite calls to check the library loads). */
+int pg_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGSCORE_H */

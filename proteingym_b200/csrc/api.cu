@@ -1,0 +1,407 @@
+// C-ABI of libpgscore.so (include/pgscore.h): model handle, weight repacking, and the batched masked-marginal forward.
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace pg {
+
+std::string& tls_error() {
+  static thread_local std::string e;
+  return e;
+}
+int set_error(int code, const std::string& msg) {
+  tls_error() = msg;
+  return code;
+}
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+namespace {
+
+// fp32 [N, K] -> fp16 hi at [n, 0:K] and (np == 2) lo at [n, K:2K]; rows scaled by `scale` (q scaling fold).
+__global__ void pack_weight_kernel(const float* __restrict__ w, int N, int K, float scale, __half* __restrict__ out, int np) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(N) * K) return;
+  const int n = static_cast<int>(i / K), k = static_cast<int>(i % K);
+  const float v = w[i] * scale;
+  __half hi, lo;
+  split_hi_lo(v, hi, lo);
+  out[static_cast<long long>(n) * K * np + k] = hi;
+  if (np == 2) out[static_cast<long long>(n) * K * np + K + k] = lo;
+}
+__global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * scale;
+}
+
+struct Layer {
+  __half *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+  float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+  float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+};
+
+}  // namespace
+}  // namespace pg
+
+struct pg_handle_s {
+  pg_model_desc desc{};
+  int np = 1;  // operand planes: 1 (fp16) or 2 (hi|lo)
+  bool loaded = false;
+  std::string err;
+  std::vector<void*> allocs;
+  std::vector<pg::Layer> layers;
+  float *embed = nullptr, *pos = nullptr, *lnbg = nullptr, *lnbb = nullptr, *lnag = nullptr, *lnab = nullptr;
+  float *hdw = nullptr, *hdb = nullptr, *hlng = nullptr, *hlnb = nullptr, *hbias = nullptr;
+  float *rot_cos = nullptr, *rot_sin = nullptr;
+  int rot_rows = 0;
+  // workspace
+  long long max_rows = 0;
+  int head_cap = 0;
+  float* x = nullptr;
+  __half *abuf = nullptr, *qkv = nullptr, *fbuf = nullptr;
+  float *hs_a = nullptr, *hs_b = nullptr;
+  int32_t* row_sel = nullptr;  // [head_cap] token index within the window to emit
+};
+
+namespace pg {
+namespace {
+
+int fail(pg_handle h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return set_error(code, msg);
+}
+
+template <typename T>
+int dev_alloc(pg_handle h, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+  if (e != cudaSuccess) return fail(h, PG_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return PG_OK;
+}
+
+__global__ void row_select_kernel(const int32_t* positions, const int32_t* win_start, const int32_t* out_row, int p_offset, int n,
+                                  int32_t* sel) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int gp = p_offset + i;
+  const int tok = out_row ? out_row[gp] : positions[gp];
+  sel[i] = tok - (win_start ? win_start[gp] : 0);
+}
+
+int forward_rows(pg_handle h, const int32_t* tokens, int n_tokens, const int32_t* positions, const int32_t* win_start,
+                 int p_offset, int Bc, int T, cudaStream_t s) {
+  const pg_model_desc& D = h->desc;
+  const int d = D.embed_dim, f = D.ffn_dim, np = h->np, nseg = (np == 2) ? 3 : 1;
+  const int rows = Bc * T;
+  EmbedLaunch e{};
+  e.tokens = tokens; e.n_tokens = n_tokens; e.positions = positions; e.win_start = win_start;
+  e.P = Bc; e.T = T; e.d = d; e.embed = h->embed; e.pos_table = (D.arch == PG_ARCH_ESM1B) ? h->pos : nullptr;
+  e.lnb_gamma = D.emb_ln_before ? h->lnbg : nullptr; e.lnb_beta = D.emb_ln_before ? h->lnbb : nullptr;
+  e.token_dropout = D.token_dropout; e.mask_idx = 32; e.p_offset = p_offset; e.x = h->x;
+  int rc = launch_embed(e, s);
+  if (rc) return rc;
+  const bool rotary = (D.arch == PG_ARCH_ESM2);
+  for (int l = 0; l < D.layers; ++l) {
+    const Layer& L = h->layers[l];
+    rc = launch_layernorm_f16(h->x, d, L.ln1g, L.ln1b, rows, d, h->abuf, static_cast<int64_t>(d) * np, np == 2 ? d : 0, s);
+    if (rc) return rc;
+    GemmLaunch g{};
+    g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.wqkv; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.bqkv;
+    g.M = rows; g.N = 3 * d; g.K = d; g.nseg = nseg; g.epi = rotary ? 3 : 0;
+    g.out = h->qkv; g.ldo = static_cast<int64_t>(3 * d) * np; g.out_lo_off = np == 2 ? 3 * d : 0;
+    g.rot_cos = h->rot_cos; g.rot_sin = h->rot_sin; g.rot_T = T; g.rot_dim = d;
+    rc = launch_gemm(g, s);
+    if (rc) return rc;
+    AttnLaunch a{};
+    a.qkv = h->qkv; a.ld = static_cast<int64_t>(3 * d) * np; a.lo_off = np == 2 ? 3 * d : 0;
+    a.out = h->abuf; a.ldo = static_cast<int64_t>(d) * np; a.out_lo_off = np == 2 ? d : 0;
+    a.B = Bc; a.T = T; a.heads = D.heads; a.nseg = nseg; a.causal = 0; a.alibi_slopes = nullptr;
+    rc = launch_attention(a, s);
+    if (rc) return rc;
+    g = GemmLaunch{};
+    g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.wo; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.bo;
+    g.M = rows; g.N = d; g.K = d; g.nseg = nseg; g.epi = 2; g.resid = h->x; g.ldr = d;
+    rc = launch_gemm(g, s);
+    if (rc) return rc;
+    rc = launch_layernorm_f16(h->x, d, L.ln2g, L.ln2b, rows, d, h->abuf, static_cast<int64_t>(d) * np, np == 2 ? d : 0, s);
+    if (rc) return rc;
+    g = GemmLaunch{};
+    g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.w1; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.b1;
+    g.M = rows; g.N = f; g.K = d; g.nseg = nseg; g.epi = 1;
+    g.out = h->fbuf; g.ldo = static_cast<int64_t>(f) * np; g.out_lo_off = np == 2 ? f : 0;
+    rc = launch_gemm(g, s);
+    if (rc) return rc;
+    g = GemmLaunch{};
+    g.a = h->fbuf; g.lda = static_cast<int64_t>(f) * np; g.w = L.w2; g.ldw = static_cast<int64_t>(f) * np; g.bias = L.b2;
+    g.M = rows; g.N = d; g.K = f; g.nseg = nseg; g.epi = 2; g.resid = h->x; g.ldr = d;
+    rc = launch_gemm(g, s);
+    if (rc) return rc;
+  }
+  return PG_OK;
+}
+
+HeadLaunch head_args(pg_handle h, int T) {
+  HeadLaunch hl{};
+  hl.x = h->x; hl.d = h->desc.embed_dim; hl.T = T;
+  hl.lna_g = h->lnag; hl.lna_b = h->lnab; hl.dense_w = h->hdw; hl.dense_b = h->hdb;
+  hl.ln_g = h->hlng; hl.ln_b = h->hlnb; hl.out_w = h->embed; hl.out_b = h->hbias; hl.vocab = h->desc.vocab;
+  hl.scratch_a = h->hs_a; hl.scratch_b = h->hs_b;
+  return hl;
+}
+
+}  // namespace
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" {
+
+int pg_abi_version(void) { return 1; }
+
+const char* pg_last_error(pg_handle h) {
+  if (h && !h->err.empty()) return h->err.c_str();
+  return tls_error().c_str();
+}
+
+int pg_create(const pg_model_desc* desc, pg_handle* out) {
+  if (!desc || !out) return set_error(PG_ERR_ARG, "pg_create: null argument");
+  const pg_model_desc& D = *desc;
+  if (D.layers <= 0 || D.embed_dim <= 0 || D.heads <= 0 || D.ffn_dim <= 0 || D.vocab <= 0)
+    return set_error(PG_ERR_ARG, "pg_create: non-positive model dimension");
+  if (D.embed_dim != D.heads * 64) return set_error(PG_ERR_UNSUPPORTED, "pg_create: head_dim must be 64");
+  if (D.embed_dim % 64 || D.ffn_dim % 64) return set_error(PG_ERR_UNSUPPORTED, "pg_create: embed_dim and ffn_dim must be multiples of 64");
+  if (D.arch != PG_ARCH_ESM1B && D.arch != PG_ARCH_ESM2) return set_error(PG_ERR_UNSUPPORTED, "pg_create: unknown arch");
+  if (D.precision != PG_PREC_F16 && D.precision != PG_PREC_F16X3) return set_error(PG_ERR_ARG, "pg_create: unknown precision");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return set_error(PG_ERR_CUDA, "pg_create: no CUDA device (the B200 path has no CPU fallback)");
+  if (D.device < 0 || D.device >= ndev) return set_error(PG_ERR_ARG, "pg_create: bad device ordinal");
+  PG_CUDA_OK(cudaSetDevice(D.device));
+  cudaDeviceProp prop;
+  PG_CUDA_OK(cudaGetDeviceProperties(&prop, D.device));
+  if (prop.major != 10) return set_error(PG_ERR_UNSUPPORTED, "pg_create: device is not sm_100 (tcgen05/TMEM required)");
+  pg_handle h = new pg_handle_s();
+  h->desc = D;
+  h->np = (D.precision == PG_PREC_F16X3) ? 2 : 1;
+  h->max_rows = D.max_rows > 0 ? D.max_rows : 131072;
+  h->head_cap = 8192;
+  const int d = D.embed_dim, f = D.ffn_dim, np = h->np;
+  int rc = PG_OK;
+  auto A = [&](auto** p, size_t n) { if (!rc) rc = dev_alloc(h, p, n); };
+  h->layers.resize(D.layers);
+  for (auto& L : h->layers) {
+    A(&L.wqkv, static_cast<size_t>(3) * d * d * np); A(&L.wo, static_cast<size_t>(d) * d * np);
+    A(&L.w1, static_cast<size_t>(f) * d * np); A(&L.w2, static_cast<size_t>(d) * f * np);
+    A(&L.bqkv, 3 * d); A(&L.bo, d); A(&L.b1, f); A(&L.b2, d);
+    A(&L.ln1g, d); A(&L.ln1b, d); A(&L.ln2g, d); A(&L.ln2b, d);
+  }
+  A(&h->embed, static_cast<size_t>(D.vocab) * d);
+  if (D.arch == PG_ARCH_ESM1B) A(&h->pos, static_cast<size_t>(D.max_positions + 2) * d);
+  A(&h->lnbg, d); A(&h->lnbb, d); A(&h->lnag, d); A(&h->lnab, d);
+  A(&h->hdw, static_cast<size_t>(d) * d); A(&h->hdb, d); A(&h->hlng, d); A(&h->hlnb, d); A(&h->hbias, D.vocab);
+  A(&h->x, static_cast<size_t>(h->max_rows) * d);
+  A(&h->abuf, static_cast<size_t>(h->max_rows) * d * np);
+  A(&h->qkv, static_cast<size_t>(h->max_rows) * 3 * d * np);
+  A(&h->fbuf, static_cast<size_t>(h->max_rows) * f * np);
+  A(&h->hs_a, static_cast<size_t>(h->head_cap) * d);
+  A(&h->hs_b, static_cast<size_t>(h->head_cap) * d);
+  A(&h->row_sel, h->head_cap);
+  if (rc) {
+    std::string m = h->err;
+    pg_destroy(h);
+    return set_error(rc, m);
+  }
+  *out = h;
+  return PG_OK;
+}
+
+int pg_destroy(pg_handle h) {
+  if (!h) return PG_OK;
+  cudaSetDevice(h->desc.device);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+  return PG_OK;
+}
+
+int pg_load_weights(pg_handle h, const pg_tensor* tensors, int32_t n) {
+  if (!h || !tensors) return set_error(PG_ERR_ARG, "pg_load_weights: null argument");
+  PG_CUDA_OK(cudaSetDevice(h->desc.device));
+  const pg_model_desc& D = h->desc;
+  const int d = D.embed_dim, f = D.ffn_dim, np = h->np;
+  std::map<std::string, const pg_tensor*> by_name;
+  for (int i = 0; i < n; ++i) by_name[tensors[i].name] = &tensors[i];
+  std::string missing;
+  auto get = [&](const std::string& name, int64_t r, int64_t c) -> const float* {
+    auto it = by_name.find(name);
+    if (it == by_name.end()) { missing += name + " "; return nullptr; }
+    if (it->second->shape[0] != r || it->second->shape[1] != c) { missing += name + "(shape) "; return nullptr; }
+    return static_cast<const float*>(it->second->data);
+  };
+  auto copy = [&](float* dst, const float* src, size_t cnt, float scale = 1.f) {
+    if (!src) return;
+    scale_copy_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256>>>(src, dst, static_cast<int>(cnt), scale);
+  };
+  auto pack = [&](__half* dst, const float* src, int N, int K, float scale = 1.f) {
+    if (!src) return;
+    const long long tot = static_cast<long long>(N) * K;
+    pack_weight_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256>>>(src, N, K, scale, dst, np);
+  };
+  const float qscale = 0.125f;  // head_dim^-1/2 with head_dim == 64 (multihead_attention.py:103,261); exact power of two
+  for (int l = 0; l < D.layers; ++l) {
+    Layer& L = h->layers[l];
+    const std::string p = "layers." + std::to_string(l) + ".";
+    const size_t dd = static_cast<size_t>(d) * d * np;
+    pack(L.wqkv, get(p + "self_attn.q_proj.weight", d, d), d, d, qscale);
+    pack(L.wqkv + dd, get(p + "self_attn.k_proj.weight", d, d), d, d);
+    pack(L.wqkv + 2 * dd, get(p + "self_attn.v_proj.weight", d, d), d, d);
+    copy(L.bqkv, get(p + "self_attn.q_proj.bias", d, 1), d, qscale);
+    copy(L.bqkv + d, get(p + "self_attn.k_proj.bias", d, 1), d);
+    copy(L.bqkv + 2 * d, get(p + "self_attn.v_proj.bias", d, 1), d);
+    pack(L.wo, get(p + "self_attn.out_proj.weight", d, d), d, d);
+    copy(L.bo, get(p + "self_attn.out_proj.bias", d, 1), d);
+    pack(L.w1, get(p + "fc1.weight", f, d), f, d);
+    copy(L.b1, get(p + "fc1.bias", f, 1), f);
+    pack(L.w2, get(p + "fc2.weight", d, f), d, f);
+    copy(L.b2, get(p + "fc2.bias", d, 1), d);
+    copy(L.ln1g, get(p + "self_attn_layer_norm.weight", d, 1), d);
+    copy(L.ln1b, get(p + "self_attn_layer_norm.bias", d, 1), d);
+    copy(L.ln2g, get(p + "final_layer_norm.weight", d, 1), d);
+    copy(L.ln2b, get(p + "final_layer_norm.bias", d, 1), d);
+  }
+  copy(h->embed, get("embed_tokens.weight", D.vocab, d), static_cast<size_t>(D.vocab) * d);
+  if (D.arch == PG_ARCH_ESM1B)
+    copy(h->pos, get("embed_positions.weight", D.max_positions + 2, d), static_cast<size_t>(D.max_positions + 2) * d);
+  if (D.emb_ln_before) {
+    copy(h->lnbg, get("emb_layer_norm_before.weight", d, 1), d);
+    copy(h->lnbb, get("emb_layer_norm_before.bias", d, 1), d);
+  }
+  copy(h->lnag, get("emb_layer_norm_after.weight", d, 1), d);
+  copy(h->lnab, get("emb_layer_norm_after.bias", d, 1), d);
+  copy(h->hdw, get("lm_head.dense.weight", d, d), static_cast<size_t>(d) * d);
+  copy(h->hdb, get("lm_head.dense.bias", d, 1), d);
+  copy(h->hlng, get("lm_head.layer_norm.weight", d, 1), d);
+  copy(h->hlnb, get("lm_head.layer_norm.bias", d, 1), d);
+  copy(h->hbias, get("lm_head.bias", D.vocab, 1), D.vocab);
+  if (D.arch == PG_ARCH_ESM2) {
+    auto it = by_name.find("rotary.cos");
+    auto is = by_name.find("rotary.sin");
+    if (it == by_name.end() || is == by_name.end() || it->second->shape[1] != 32 || is->second->shape[0] != it->second->shape[0]) {
+      missing += "rotary.cos/rotary.sin[T,32] ";
+    } else {
+      h->rot_rows = static_cast<int>(it->second->shape[0]);
+      int rc = dev_alloc(h, &h->rot_cos, static_cast<size_t>(h->rot_rows) * 32);
+      if (!rc) rc = dev_alloc(h, &h->rot_sin, static_cast<size_t>(h->rot_rows) * 32);
+      if (rc) return rc;
+      copy(h->rot_cos, static_cast<const float*>(it->second->data), static_cast<size_t>(h->rot_rows) * 32);
+      copy(h->rot_sin, static_cast<const float*>(is->second->data), static_cast<size_t>(h->rot_rows) * 32);
+    }
+  }
+  if (!missing.empty()) return fail(h, PG_ERR_ARG, "pg_load_weights: missing or mis-shaped tensors: " + missing);
+  PG_CUDA_OK(cudaGetLastError());
+  PG_CUDA_OK(cudaDeviceSynchronize());  // caller may free its tensors on return
+  h->loaded = true;
+  return PG_OK;
+}
+
+int pg_masked_marginals(pg_handle h, const int32_t* tokens, int32_t n_tokens, const int32_t* positions, const int32_t* win_start,
+                        const int32_t* out_row, int32_t P, int32_t T, float* out_logprobs, pg_stream stream) {
+  if (!h) return set_error(PG_ERR_ARG, "pg_masked_marginals: null handle");
+  if (!h->loaded) return fail(h, PG_ERR_STATE, "pg_masked_marginals: weights not loaded");
+  if (!tokens || !positions || !out_logprobs) return fail(h, PG_ERR_ARG, "pg_masked_marginals: null buffer");
+  if (P < 0 || T <= 0 || T > n_tokens) return fail(h, PG_ERR_ARG, "pg_masked_marginals: bad P/T");
+  if (h->desc.arch == PG_ARCH_ESM1B && T > h->desc.max_positions)
+    return fail(h, PG_ERR_ARG, "pg_masked_marginals: window longer than the learned position table (modules.py:256-260)");
+  if (h->desc.arch == PG_ARCH_ESM2 && T > h->rot_rows) return fail(h, PG_ERR_ARG, "pg_masked_marginals: window longer than rotary tables");
+  if (T > h->max_rows) return fail(h, PG_ERR_ARG, "pg_masked_marginals: window longer than workspace (raise max_rows)");
+  PG_CUDA_OK(cudaSetDevice(h->desc.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  long long per = h->max_rows / T;
+  if (per > h->head_cap) per = h->head_cap;
+  for (int p0 = 0; p0 < P; p0 += static_cast<int>(per)) {
+    const int Bc = (P - p0) < per ? (P - p0) : static_cast<int>(per);
+    int rc = forward_rows(h, tokens, n_tokens, positions, win_start, p0, Bc, T, s);
+    if (rc) return fail(h, rc, tls_error());
+    row_select_kernel<<<(Bc + 255) / 256, 256, 0, s>>>(positions, win_start, out_row, p0, Bc, h->row_sel);
+    HeadLaunch hl = head_args(h, T);
+    hl.row_in_seq = h->row_sel; hl.P = Bc; hl.all_rows = 0;
+    hl.out = out_logprobs + static_cast<long long>(p0) * h->desc.vocab;
+    rc = launch_head(hl, s);
+    if (rc) return fail(h, rc, tls_error());
+  }
+  return PG_OK;
+}
+
+int pg_forward_logprobs(pg_handle h, const int32_t* tokens, int32_t n_tokens, int32_t win_start, int32_t T, int32_t mask_pos,
+                        float* out_logprobs, pg_stream stream) {
+  if (!h) return set_error(PG_ERR_ARG, "pg_forward_logprobs: null handle");
+  if (!h->loaded) return fail(h, PG_ERR_STATE, "pg_forward_logprobs: weights not loaded");
+  if (!tokens || !out_logprobs || T <= 0 || win_start < 0 || win_start + T > n_tokens) return fail(h, PG_ERR_ARG, "pg_forward_logprobs: bad arguments");
+  if (h->desc.arch == PG_ARCH_ESM1B && T > h->desc.max_positions) return fail(h, PG_ERR_ARG, "pg_forward_logprobs: sequence longer than the learned position table");
+  if (h->desc.arch == PG_ARCH_ESM2 && T > h->rot_rows) return fail(h, PG_ERR_ARG, "pg_forward_logprobs: sequence longer than rotary tables");
+  if (T > h->max_rows) return fail(h, PG_ERR_ARG, "pg_forward_logprobs: sequence longer than workspace");
+  PG_CUDA_OK(cudaSetDevice(h->desc.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // one row: positions / win_start as 1-element device arrays kept in row_sel scratch
+  int32_t hostv[2] = {mask_pos, win_start};
+  PG_CUDA_OK(cudaMemcpyAsync(h->row_sel, hostv, sizeof(hostv), cudaMemcpyHostToDevice, s));
+  int rc = forward_rows(h, tokens, n_tokens, h->row_sel, h->row_sel + 1, 0, 1, T, s);
+  if (rc) return fail(h, rc, tls_error());
+  for (int r0 = 0; r0 < T; r0 += h->head_cap) {
+    HeadLaunch hl = head_args(h, T);
+    hl.x = h->x + static_cast<long long>(r0) * h->desc.embed_dim;
+    hl.P = (T - r0) < h->head_cap ? (T - r0) : h->head_cap; hl.all_rows = 1;
+    hl.out = out_logprobs + static_cast<long long>(r0) * h->desc.vocab;
+    rc = launch_head(hl, s);
+    if (rc) return fail(h, rc, tls_error());
+  }
+  return PG_OK;
+}
+
+int pg_score_mutants(const float* table, int32_t n_rows, int32_t vocab, const int32_t* site_row, const int32_t* site_wt,
+                     const int32_t* site_mt, const int32_t* row_offsets, int32_t M, float* out_scores, pg_stream stream) {
+  if (M < 0 || n_rows < 0 || vocab <= 0) return set_error(PG_ERR_ARG, "pg_score_mutants: bad sizes");
+  if (M == 0) return PG_OK;
+  if (!table || !site_row || !site_wt || !site_mt || !row_offsets || !out_scores) return set_error(PG_ERR_ARG, "pg_score_mutants: null buffer");
+  return launch_score(table, n_rows, vocab, site_row, site_wt, site_mt, row_offsets, M, out_scores, static_cast<cudaStream_t>(stream));
+}
+
+int pg_gemm(const pg_gemm_args* a, pg_stream stream) {
+  if (!a) return set_error(PG_ERR_ARG, "pg_gemm: null args");
+  GemmLaunch g{};
+  g.a = a->a; g.lda = a->lda; g.w = a->w; g.ldw = a->ldw; g.bias = a->bias;
+  g.M = a->M; g.N = a->N; g.K = a->K; g.nseg = a->nseg; g.epi = a->epi;
+  g.out = static_cast<__half*>(a->out_h); g.ldo = a->ldo; g.out_lo_off = a->out_lo_off;
+  g.resid = a->resid; g.ldr = a->ldr;
+  g.rot_cos = a->rot_cos; g.rot_sin = a->rot_sin; g.rot_T = a->rot_T; g.rot_dim = a->rot_dim;
+  return launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+int pg_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int32_t rows, int32_t d, void* out,
+                     int64_t ldo, int64_t lo_off, pg_stream stream) {
+  if (!x || !gamma || !beta || !out) return set_error(PG_ERR_ARG, "pg_layernorm_f16: null buffer");
+  return launch_layernorm_f16(x, ldx, gamma, beta, rows, d, static_cast<__half*>(out), ldo, lo_off, static_cast<cudaStream_t>(stream));
+}
+
+int pg_attention(const pg_attn_args* a, pg_stream stream) {
+  if (!a || !a->qkv || !a->out) return set_error(PG_ERR_ARG, "pg_attention: null args");
+  AttnLaunch l{};
+  l.qkv = static_cast<const __half*>(a->qkv); l.ld = a->ld; l.lo_off = a->lo_off;
+  l.out = static_cast<__half*>(a->out); l.ldo = a->ldo; l.out_lo_off = a->out_lo_off;
+  l.B = a->B; l.T = a->T; l.heads = a->heads; l.nseg = a->nseg; l.causal = a->causal; l.alibi_slopes = a->alibi_slopes;
+  return launch_attention(l, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

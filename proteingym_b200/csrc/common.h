@@ -1,0 +1,83 @@
+// Shared host-side declarations for libpgscore.so (internal; the public ABI is include/pgscore.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/pgscore.h"
+
+namespace pg {
+
+// Last error text for handle-less entry points (thread-local so concurrent per-GPU threads do not clobber each other).
+std::string& tls_error();
+int set_error(int code, const std::string& msg);
+
+#define PG_CUDA_OK(expr)                                                                                   \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess)                                                                                 \
+      return ::pg::set_error(PG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+  } while (0)
+
+int num_sms();
+
+// ---- kernel launchers (each returns a pg_status) ----
+struct GemmLaunch {
+  const void* a; int64_t lda;
+  const void* w; int64_t ldw;
+  const float* bias;
+  int M, N, K, nseg, epi;
+  __half* out; int64_t ldo; int64_t out_lo_off;
+  float* resid; int64_t ldr;
+  const float* rot_cos; const float* rot_sin; int rot_T; int rot_dim;
+};
+int launch_gemm(const GemmLaunch& g, cudaStream_t s);
+
+int launch_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int rows, int d, __half* out,
+                         int64_t ldo, int64_t lo_off, cudaStream_t s);
+
+struct AttnLaunch {
+  const __half* qkv; int64_t ld; int64_t lo_off;
+  __half* out; int64_t ldo; int64_t out_lo_off;
+  int B, T, heads, nseg, causal;
+  const float* alibi_slopes;
+};
+int launch_attention(const AttnLaunch& a, cudaStream_t s);
+
+// x[row, :] = token embedding (mask row zeroed, token-dropout rescale) + learned position; optional LayerNorm-before.
+struct EmbedLaunch {
+  const int32_t* tokens; int n_tokens;
+  const int32_t* positions;  // [P] masked token index or -1
+  const int32_t* win_start;  // [P] or null
+  int P, T, d;
+  const float* embed;        // [vocab, d] fp32 (mask row as loaded)
+  const float* pos_table;    // [max_pos+2, d] or null (ESM2)
+  const float* lnb_gamma; const float* lnb_beta;  // emb_layer_norm_before or null
+  int token_dropout; int mask_idx; int p_offset;  // p_offset: first row index p of this chunk
+  float* x;                  // [P*T, d]
+};
+int launch_embed(const EmbedLaunch& e, cudaStream_t s);
+
+// LM head on selected rows (esm/modules.py:322-328) + log_softmax: out [P, vocab].
+struct HeadLaunch {
+  const float* x; int d; int T;          // residual stream [P*T, d]
+  const int32_t* row_in_seq;             // [P] token index within the window to emit (device) or null when all rows
+  int P;                                 // number of output rows
+  int all_rows;                          // 1: emit every row of x (P == rows), row_in_seq ignored
+  const float* lna_g; const float* lna_b;    // emb_layer_norm_after
+  const float* dense_w; const float* dense_b;  // [d, d], [d]
+  const float* ln_g; const float* ln_b;      // lm_head.layer_norm
+  const float* out_w; const float* out_b;    // [vocab, d] tied embedding, [vocab]
+  int vocab;
+  float* scratch_a; float* scratch_b;    // [P, d] each
+  float* out;                            // [P, vocab]
+};
+int launch_head(const HeadLaunch& h, cudaStream_t s);
+
+int launch_score(const float* table, int n_rows, int vocab, const int32_t* site_row, const int32_t* site_wt,
+                 const int32_t* site_mt, const int32_t* row_offsets, int M, float* out, cudaStream_t s);
+
+}  // namespace pg

@@ -1,0 +1,337 @@
+// K3 — tcgen05/TMA GEMM with fused epilogues for the linear layers of the ESM / Tranception forward
+// (reference ops: esm/multihead_attention.py:243-261,395; esm/modules.py:138-140).
+//
+//   C[M,N] = epilogue( A[M,K] * W[N,K]^T + bias )        A, W fp16 K-major (row-major), fp32 accumulate in TMEM.
+//
+// Precision: the reference is fp32. With nseg == 3 each operand is an fp16 (hi | lo) pair stored as two column blocks
+// and the K loop runs three segments  hi*hi + lo*hi + hi*lo  into the same TMEM accumulator (~22-bit operands).
+//
+// Structure (one persistent CTA per SM, 384 threads, no clusters):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (128x64 of A, 256x64 of W, 128B swizzle) into a 4-stage ring
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16) x4 per stage; tcgen05.commit frees the
+//               stage and, after the last k-block, publishes the accumulator
+//   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, so the epilogue of tile i overlaps the
+//               MMAs of tile i+1)
+//   warps 4-11  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> bias / erf-GELU / residual / rotary ->
+//               global (fp16 hi[/lo] or fp32 residual stream)
+// Roofline: tensor bound. Algorithmic FLOPs = 2*M*N*K*nseg.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace pg {
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UK = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int FIRST_EPI_WARP = 4;
+constexpr int GEMM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;
+constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KiB
+constexpr uint32_t B_BYTES = BN * BK * 2;  // 32 KiB
+constexpr uint32_t OFF_B = STAGES * A_BYTES;
+constexpr uint32_t OFF_BAR = OFF_B + STAGES * B_BYTES;
+constexpr uint32_t GEMM_SMEM = OFF_BAR + 256 + 1024;  // + barriers + 1 KiB alignment slack
+constexpr uint32_t TMEM_COLS = 512;
+
+struct GemmKParams {
+  int M, N, K, nseg;
+  int a_off[3], b_off[3];
+  const float* bias;
+  int epi;
+  __half* out; long long ldo; long long lo_off;
+  float* resid; long long ldr;
+  const float* rot_cos; const float* rot_sin; int rot_T; int rot_dim;
+  int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// Store 32 consecutive columns of one row as fp16 (hi, optional lo). Fast path: 4 x 16-byte stores.
+__device__ __forceinline__ void store_row_f16(const float (&v)[32], __half* out, long long ldo, long long lo_off, long long row,
+                                              int gcol, int N) {
+  __half* dst = out + row * ldo + gcol;
+  if (gcol + 32 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((lo_off & 7) == 0)) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      __half h0, l0, h1, l1;
+      split_hi_lo(v[2 * j], h0, l0);
+      split_hi_lo(v[2 * j + 1], h1, l1);
+      hi[j] = pack_h2(h0, h1);
+      lo[j] = pack_h2(l0, l1);
+    }
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+    if (lo_off > 0) {
+      uint4* l4 = reinterpret_cast<uint4*>(dst + lo_off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) l4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+    }
+  } else {
+    for (int j = 0; j < 32; ++j) {
+      if (gcol + j < N) {
+        __half h, l;
+        split_hi_lo(v[j], h, l);
+        dst[j] = h;
+        if (lo_off > 0) dst[lo_off + j] = l;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + OFF_B;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kblocks = p.K / BK;
+  const int ntiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
+            tma_load_2d(smA + stage * A_BYTES, &tmA, &full[stage], p.a_off[seg] + kb * BK, m_blk * BM);
+            tma_load_2d(smB + stage * B_BYTES, &tmB, &full[stage], p.b_off[seg] + kb * BK, n_blk * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t tphase = (it >> 1) & 1;
+        mbar_wait(&tempty[buf], tphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        uint32_t accumulate = 0;
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = make_desc_sw128(smem_u32(smA + stage * A_BYTES), 1024);
+            const uint64_t bdesc = make_desc_sw128(smem_u32(smB + stage * B_BYTES), 1024);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              // advance 16 fp16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+              umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp >= FIRST_EPI_WARP) {
+    const int q = warp & 3;                           // TMEM lane quadrant this warp may read
+    const int half_id = (warp - FIRST_EPI_WARP) >> 2;  // which 128-column half of the tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      const int buf = it & 1;
+      const uint32_t tphase = (it >> 1) & 1;
+      mbar_wait(&tfull[buf], tphase);
+      tc_fence_after();
+      const long long row = static_cast<long long>(m_blk) * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int cp = 0; cp < 2; ++cp) {  // pairs of 32-column chunks = one 64-wide head
+        const int col0 = half_id * 128 + cp * 64;
+        const int gcol = n_blk * BN + col0;
+        if (gcol >= p.N) break;  // warp-uniform
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + col0;
+        tmem_ld_32x32b_x32(taddr, r0);
+        tmem_ld_32x32b_x32(taddr + 32, r1);
+        tmem_ld_wait();
+        float v0[32], v1[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float b0 = (p.bias && gcol + j < p.N) ? __ldg(p.bias + gcol + j) : 0.f;
+          const float b1 = (p.bias && gcol + 32 + j < p.N) ? __ldg(p.bias + gcol + 32 + j) : 0.f;
+          v0[j] = __uint_as_float(r0[j]) + b0;
+          v1[j] = __uint_as_float(r1[j]) + b1;
+        }
+        if (p.epi == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v0[j] = gelu_erf(v0[j]);
+            v1[j] = gelu_erf(v1[j]);
+          }
+        } else if (p.epi == 3 && gcol < 2 * p.rot_dim) {
+          // rotary: x*cos + rotate_half(x)*sin over one 64-wide head; cos/sin[t, j] for j in [0,32) (both halves equal)
+          const int t = static_cast<int>(row % p.rot_T);
+          const float* cs = p.rot_cos + static_cast<long long>(t) * 32;
+          const float* sn = p.rot_sin + static_cast<long long>(t) * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float c = row_ok ? __ldg(cs + j) : 1.f, s = row_ok ? __ldg(sn + j) : 0.f;
+            const float a = v0[j], b = v1[j];
+            v0[j] = a * c - b * s;
+            v1[j] = b * c + a * s;
+          }
+        }
+        if (row_ok) {
+          if (p.epi == 2) {
+            float* dst = p.resid + row * p.ldr + gcol;
+            if (gcol + 64 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+              float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 x = d4[j];
+                x.x += v0[4 * j]; x.y += v0[4 * j + 1]; x.z += v0[4 * j + 2]; x.w += v0[4 * j + 3];
+                d4[j] = x;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 x = d4[8 + j];
+                x.x += v1[4 * j]; x.y += v1[4 * j + 1]; x.z += v1[4 * j + 2]; x.w += v1[4 * j + 3];
+                d4[8 + j] = x;
+              }
+            } else {
+              for (int j = 0; j < 32; ++j) {
+                if (gcol + j < p.N) dst[j] += v0[j];
+                if (gcol + 32 + j < p.N) dst[32 + j] += v1[j];
+              }
+            }
+          } else {
+            store_row_f16(v0, p.out, p.ldo, p.lo_off, row, gcol, p.N);
+            if (gcol + 32 < p.N) store_row_f16(v1, p.out, p.ldo, p.lo_off, row, gcol + 32, p.N);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+// 2D fp16 row-major tensor [rows, cols] with row pitch ld (elements); box = [box_rows, 64 cols], 128B swizzle,
+// out-of-bounds elements read as zero.
+int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(PG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16)
+    return set_error(PG_ERR_ARG, "TMA operand must be 16-byte aligned with a 16-byte-multiple row pitch");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(PG_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(static_cast<int>(r)));
+  return PG_OK;
+}
+
+int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(PG_ERR_ARG, "gemm: empty problem");
+  if (g.K % BK) return set_error(PG_ERR_ARG, "gemm: K must be a multiple of 64");
+  if (g.nseg != 1 && g.nseg != 3) return set_error(PG_ERR_ARG, "gemm: nseg must be 1 or 3");
+  if (g.epi < 0 || g.epi > 3) return set_error(PG_ERR_ARG, "gemm: bad epilogue");
+  if (g.epi == 2 ? !g.resid : !g.out) return set_error(PG_ERR_ARG, "gemm: missing output");
+  if (g.epi == 3 && (!g.rot_cos || !g.rot_sin || g.rot_T <= 0 || g.rot_dim % 64)) return set_error(PG_ERR_ARG, "gemm: bad rotary args");
+  static bool attr_set = false;
+  if (!attr_set) {
+    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    attr_set = true;
+  }
+  const uint64_t width = static_cast<uint64_t>(g.K) * (g.nseg == 3 ? 2 : 1);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_f16_2d(&tmA, g.a, g.M, width, g.lda, BM, BK);
+  if (rc) return rc;
+  rc = make_tmap_f16_2d(&tmB, g.w, g.N, width, g.ldw, BN, BK);
+  if (rc) return rc;
+  GemmKParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K; p.nseg = g.nseg;
+  // segments: hi*hi, lo*hi, hi*lo
+  p.a_off[0] = 0; p.b_off[0] = 0;
+  p.a_off[1] = g.K; p.b_off[1] = 0;
+  p.a_off[2] = 0; p.b_off[2] = g.K;
+  p.bias = g.bias; p.epi = g.epi;
+  p.out = g.out; p.ldo = g.ldo; p.lo_off = g.out_lo_off;
+  p.resid = g.resid; p.ldr = g.ldr;
+  p.rot_cos = g.rot_cos; p.rot_sin = g.rot_sin; p.rot_T = g.rot_T; p.rot_dim = g.rot_dim;
+  p.tiles_m = (g.M + BM - 1) / BM;
+  p.tiles_n = (g.N + BN - 1) / BN;
+  const int ntiles = p.tiles_m * p.tiles_n;
+  const int grid = ntiles < num_sms() ? ntiles : num_sms();
+  gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, p);
+  PG_CUDA_OK(cudaGetLastError());
+  return PG_OK;
+}
+
+}  // namespace pg

@@ -1,0 +1,138 @@
+"""Host-side driver of the B200 ESM scorer: owns a libpgscore handle and exposes the two operations the reference's
+masked-marginal path consists of (compute_fitness.py:486-514):
+
+  * ``masked_marginal_table(seq)``   -> the ``token_probs`` [L+2, 33] table (one masked copy per token, batched), and
+  * ``score_mutants(table, mutants)`` -> ``label_row`` over the whole DMS frame.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .alphabet import ALPHABET
+from .checkpoint import EsmConfig, rotary_tables
+from .mutants import parse_mutants
+from .windows import optimal_window_starts
+
+PRECISIONS = {"f16": _lib.PG_PREC_F16, "f16x3": _lib.PG_PREC_F16X3}
+
+
+class EsmScorer:
+    def __init__(self, config: EsmConfig, state: dict, precision: str = "f16x3", device: int = 0, max_rows: int = 0):
+        if not torch.cuda.is_available():
+            raise _lib.PgError("no CUDA device: the B200 scorer has no CPU fallback")
+        self.lib = _lib.load()
+        self.config = config
+        self.device = torch.device("cuda", device)
+        self.precision = precision
+        desc = _lib.PgModelDesc(
+            arch=_lib.PG_ARCH_ESM2 if config.arch == "esm2" else _lib.PG_ARCH_ESM1B, layers=config.layers,
+            embed_dim=config.embed_dim, heads=config.heads, ffn_dim=config.ffn_dim, vocab=config.vocab,
+            max_positions=config.max_positions, token_dropout=int(config.token_dropout),
+            emb_ln_before=int(config.emb_layer_norm_before), precision=PRECISIONS[precision], device=device,
+            max_rows=max_rows)
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.pg_create(C.byref(desc), C.byref(self.handle)))
+        try:
+            self._upload(state)
+        except Exception:
+            self.close()
+            raise
+
+    def _upload(self, state: dict):
+        cfg = self.config
+        tensors = {k: v for k, v in state.items() if "rot_emb.inv_freq" not in k}
+        if cfg.arch == "esm2":
+            inv = state["layers.0.self_attn.rot_emb.inv_freq"]
+            cos, sin = rotary_tables(inv, 4096)
+            tensors["rotary.cos"], tensors["rotary.sin"] = cos, sin
+        # fp32 staging copy on the device (ESM-1v 2.6 GB, ESM2-3B 11 GB); the library repacks and we free it
+        gpu = [(n, t.to(self.device, torch.float32).contiguous()) for n, t in tensors.items()]
+        arr = (_lib.PgTensor * len(gpu))()
+        for i, (n, t) in enumerate(gpu):
+            arr[i].name = n.encode()
+            arr[i].data = t.data_ptr()
+            arr[i].shape[0] = t.shape[0]
+            arr[i].shape[1] = t.shape[1] if t.dim() == 2 else 1
+        torch.cuda.synchronize(self.device)
+        _lib.check(self.lib.pg_load_weights(self.handle, arr, len(gpu)), self.handle)
+        del gpu
+        torch.cuda.empty_cache()
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.pg_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------------------
+    def masked_marginal_rows(self, tokens: torch.Tensor, positions, model_window: int = 1024) -> torch.Tensor:
+        """log_softmax rows [P, 33] for the given masked token indices (device int32 ``tokens`` of the full sequence).
+        Windows follow the reference's ``--scoring-window optimal`` rule (compute_fitness.py:492-495)."""
+        n_tokens = int(tokens.numel())
+        pos_np = np.asarray(positions, dtype=np.int32)
+        starts_np, T = optimal_window_starts(pos_np, n_tokens, model_window)
+        P = len(pos_np)
+        out = torch.empty((P, self.config.vocab), dtype=torch.float32, device=self.device)
+        if P == 0:
+            return out
+        stage = torch.from_numpy(np.stack([pos_np, starts_np])).to(self.device, non_blocking=True)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        windowed = n_tokens > model_window
+        _lib.check(self.lib.pg_masked_marginals(self.handle, tokens.data_ptr(), n_tokens, stage[0].data_ptr(),
+                                                stage[1].data_ptr() if windowed else None, None, P, T,
+                                                out.data_ptr(), stream), self.handle)
+        self._keepalive = stage
+        return out
+
+    def masked_marginal_table(self, sequence: str, positions=None, model_window: int = 1024) -> torch.Tensor:
+        """The reference's ``token_probs[0]``: [L+2, 33] on the device. ``positions`` (token indices, BOS = 0) restricts
+        the work to the rows ``label_row`` will actually read; other rows are NaN. Default: every residue position
+        (the reference also runs the BOS/EOS copies, whose rows no mutant can address)."""
+        tok_np = ALPHABET.tokenize_sequence(sequence)
+        tokens = torch.from_numpy(tok_np).to(self.device)
+        if positions is None:
+            positions = np.arange(1, len(sequence) + 1, dtype=np.int32)
+        positions = np.asarray(positions, dtype=np.int32)
+        rows = self.masked_marginal_rows(tokens, positions, model_window)
+        table = torch.full((len(tok_np), self.config.vocab), float("nan"), dtype=torch.float32, device=self.device)
+        table[torch.from_numpy(positions.astype(np.int64)).to(self.device)] = rows
+        return table
+
+    def wt_marginal_table(self, sequence: str) -> torch.Tensor:
+        """One unmasked forward, log_softmax of every token (compute_fitness.py:475)."""
+        tok_np = ALPHABET.tokenize_sequence(sequence)
+        tokens = torch.from_numpy(tok_np).to(self.device)
+        out = torch.empty((len(tok_np), self.config.vocab), dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.pg_forward_logprobs(self.handle, tokens.data_ptr(), len(tok_np), 0, len(tok_np), -1,
+                                                out.data_ptr(), stream), self.handle)
+        return out
+
+    def score_mutants(self, table: torch.Tensor, mutants, sequence: str, offset_idx: int = 1) -> torch.Tensor:
+        """``df.apply(label_row)`` for all rows at once (compute_fitness.py:505-514) -> float32 [M] on the device."""
+        site_row, site_wt, site_mt, offs = parse_mutants(mutants, sequence, offset_idx)
+        M = len(offs) - 1
+        out = torch.empty((M,), dtype=torch.float32, device=self.device)
+        if M == 0:
+            return out
+        if len(site_row) and (site_row.min() < 0 or site_row.max() >= table.shape[0]):
+            raise IndexError("mutation position outside the sequence")
+        dev = lambda a: torch.from_numpy(a).to(self.device, non_blocking=True)
+        d_row, d_wt, d_mt, d_off = dev(site_row), dev(site_wt), dev(site_mt), dev(offs)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.pg_score_mutants(table.data_ptr(), table.shape[0], table.shape[1], d_row.data_ptr(),
+                                             d_wt.data_ptr(), d_mt.data_ptr(), d_off.data_ptr(), M, out.data_ptr(),
+                                             stream))
+        self._keepalive2 = (d_row, d_wt, d_mt, d_off)
+        return out

@@ -1,0 +1,198 @@
+"""Seeded synthetic inputs at true architecture sizes.
+
+There are no checkpoints, DMS CSVs or network in the build/GPU boxes, so parity and throughput
+work uses:
+  * synthetic fair-esm-format checkpoints (v1 = ESM-1b/ESM-1v ``{"args": Namespace, "model": state}``,
+    v2 = ESM2 ``{"cfg": {"model": Namespace}, "model": state}``) that the *unmodified* reference loader accepts
+    (reference: proteingym/baselines/esm/esm/pretrained.py:85-99,162-181,184-218), and
+  * synthetic DMS tables / mapping files with the reference's column contract
+    (reference: proteingym/baselines/esm/compute_fitness.py:288-326).
+
+This module is product-side support code (used by bench.py, tests and the golden-vector scripts); it is NOT the
+oracle and contains no scoring arithmetic.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+AA20 = "ACDEFGHIKLMNPQRSTVWY"
+
+
+@dataclass
+class EsmArch:
+    kind: str  # "esm1v" (ESM-1b/ESM-1v: learned positions) | "esm2" (rotary)
+    layers: int
+    embed_dim: int
+    heads: int
+    ffn_dim: int
+    token_dropout: bool = True
+    emb_layer_norm_before: bool = False  # ESM-1b True, ESM-1v False (decided by key presence, pretrained.py:80-82)
+    max_positions: int = 1024
+    vocab: int = 33
+
+
+ESM1V_650M = EsmArch("esm1v", 33, 1280, 20, 5120)
+ESM1B_650M = EsmArch("esm1v", 33, 1280, 20, 5120, emb_layer_norm_before=True)
+ESM2_650M = EsmArch("esm2", 33, 1280, 20, 5120)
+ESM2_3B = EsmArch("esm2", 36, 2560, 40, 10240)
+
+
+def _uniform(g, shape, bound):
+    return (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
+
+
+def make_esm_state(arch: EsmArch, seed: int = 0, qk_gain: float = 2.0) -> dict:
+    """State dict with the key names of the reference modules (un-prefixed).
+
+    Distributions follow the reference constructors' defaults (nn.Embedding N(0,1); nn.Linear U(+-1/sqrt(fan_in));
+    q/k/v xavier-uniform with gain 1/sqrt(2), multihead_attention.py:138-155) except that biases and LayerNorm affine
+    terms are made non-trivial so a dropped bias shows up in parity tests, and q/k are scaled by ``qk_gain`` so the
+    attention softmax is far from uniform.
+    """
+    g = torch.Generator().manual_seed(seed)
+    d, f, V = arch.embed_dim, arch.ffn_dim, arch.vocab
+    st = {}
+    # nn.Embedding's N(0,1) would give tied-output logits of std sqrt(d) (~36 at d=1280), far from a trained model's;
+    # 0.1 keeps log-prob differences in the single digits like real ESM checkpoints.
+    emb = 0.1 * torch.randn((V, d), generator=g)
+    emb[1].zero_()  # padding_idx row (nn.Embedding(padding_idx=1))
+    st["embed_tokens.weight"] = emb
+    if arch.kind == "esm1v":
+        pos = 0.1 * torch.randn((arch.max_positions + 2, d), generator=g)
+        pos[1].zero_()
+        st["embed_positions.weight"] = pos
+        if arch.emb_layer_norm_before:
+            st["emb_layer_norm_before.weight"] = 1 + 0.1 * torch.randn(d, generator=g)
+            st["emb_layer_norm_before.bias"] = 0.05 * torch.randn(d, generator=g)
+    for i in range(arch.layers):
+        p = f"layers.{i}."
+        xb = math.sqrt(3.0 / (2 * d))  # xavier_uniform gain 1/sqrt(2): sqrt(6/(2d))/sqrt(2)
+        for nm, gain in (("q", qk_gain), ("k", qk_gain), ("v", 1.0)):
+            st[p + f"self_attn.{nm}_proj.weight"] = _uniform(g, (d, d), xb) * gain
+            st[p + f"self_attn.{nm}_proj.bias"] = _uniform(g, (d,), 1 / math.sqrt(d)) * gain
+        st[p + "self_attn.out_proj.weight"] = _uniform(g, (d, d), math.sqrt(6.0 / (2 * d)))
+        st[p + "self_attn.out_proj.bias"] = _uniform(g, (d,), 1 / math.sqrt(d))
+        st[p + "self_attn_layer_norm.weight"] = 1 + 0.1 * torch.randn(d, generator=g)
+        st[p + "self_attn_layer_norm.bias"] = 0.05 * torch.randn(d, generator=g)
+        st[p + "fc1.weight"] = _uniform(g, (f, d), 1 / math.sqrt(d))
+        st[p + "fc1.bias"] = _uniform(g, (f,), 1 / math.sqrt(d))
+        st[p + "fc2.weight"] = _uniform(g, (d, f), 1 / math.sqrt(f))
+        st[p + "fc2.bias"] = _uniform(g, (d,), 1 / math.sqrt(f))
+        st[p + "final_layer_norm.weight"] = 1 + 0.1 * torch.randn(d, generator=g)
+        st[p + "final_layer_norm.bias"] = 0.05 * torch.randn(d, generator=g)
+        if arch.kind == "esm2":
+            hd = d // arch.heads
+            st[p + "self_attn.rot_emb.inv_freq"] = 1.0 / (10000 ** (torch.arange(0, hd, 2).float() / hd))
+    st["emb_layer_norm_after.weight"] = 1 + 0.1 * torch.randn(d, generator=g)
+    st["emb_layer_norm_after.bias"] = 0.05 * torch.randn(d, generator=g)
+    st["lm_head.dense.weight"] = _uniform(g, (d, d), 1 / math.sqrt(d))
+    st["lm_head.dense.bias"] = _uniform(g, (d,), 1 / math.sqrt(d))
+    st["lm_head.layer_norm.weight"] = 1 + 0.1 * torch.randn(d, generator=g)
+    st["lm_head.layer_norm.bias"] = 0.05 * torch.randn(d, generator=g)
+    st["lm_head.bias"] = 0.1 * torch.randn(V, generator=g)
+    # tied: same tensor object, so torch.save keeps the aliasing like the released checkpoints do
+    st["lm_head.weight"] = st["embed_tokens.weight"]
+    return st
+
+
+def write_esm_checkpoint(path: str, arch: EsmArch, seed: int = 0, state: dict | None = None) -> dict:
+    """Write ``state`` (or a fresh seeded one) in the fair-esm on-disk format the reference loader dispatches on:
+    file stem starting with ``esm2`` -> v2, anything else -> v1 (pretrained.py:184-188)."""
+    st = state if state is not None else make_esm_state(arch, seed)
+    stem = os.path.basename(path)
+    if arch.kind == "esm2":
+        assert stem.startswith("esm2"), "reference dispatches v2 on the file name (pretrained.py:187)"
+        cfg = argparse.Namespace(encoder_layers=arch.layers, encoder_embed_dim=arch.embed_dim,
+                                 encoder_attention_heads=arch.heads, token_dropout=arch.token_dropout)
+        blob = {"cfg": {"model": cfg},
+                "model": {("encoder.lm_head." + k[len("lm_head."):] if k.startswith("lm_head.")
+                           else "encoder.sentence_encoder." + k): v for k, v in st.items()}}
+    else:
+        assert not stem.startswith("esm2")
+        args = argparse.Namespace(arch="roberta_large", layers=arch.layers, embed_dim=arch.embed_dim,
+                                  ffn_embed_dim=arch.ffn_dim, attention_heads=arch.heads,
+                                  max_positions=arch.max_positions, token_dropout=arch.token_dropout,
+                                  final_bias=True)
+        blob = {"args": args,
+                "model": {("encoder.lm_head." + k[len("lm_head."):] if k.startswith("lm_head.")
+                           else "encoder.sentence_encoder." + k): v for k, v in st.items()}}
+    torch.save(blob, path)
+    return st
+
+
+def random_protein(L: int, seed: int) -> str:
+    rng = np.random.RandomState(seed)
+    return "".join(AA20[i] for i in rng.randint(0, 20, size=L))
+
+
+def all_single_mutants(seq: str, first: int = 1, last: int | None = None, offset: int = 1):
+    """All 19 substitutions at (1-based, offset-adjusted) positions first..last."""
+    last = len(seq) if last is None else last
+    out = []
+    for pos in range(first, last + 1):
+        wt = seq[pos - offset]
+        for a in AA20:
+            if a != wt:
+                out.append(f"{wt}{pos}{a}")
+    return out
+
+
+def sample_mutants(seq: str, n: int, seed: int, multi_frac: float = 0.0, max_sites: int = 5, offset: int = 1):
+    """Uniform sample without replacement from the 19*L singles; a fraction
+    ``multi_frac`` of rows are turned into 2..max_sites multi-mutants ("A24G:T30S")."""
+    rng = np.random.RandomState(seed)
+    singles = all_single_mutants(seq, offset=offset)
+    idx = rng.choice(len(singles), size=min(n, len(singles)), replace=False)
+    muts = [singles[i] for i in idx]
+    if multi_frac > 0:
+        for r in range(len(muts)):
+            if rng.rand() < multi_frac:
+                k = rng.randint(2, max_sites + 1)
+                pos = rng.choice(len(seq), size=k, replace=False)
+                parts = []
+                for p in sorted(pos):
+                    wt = seq[p]
+                    mt = AA20[rng.randint(0, 20)]
+                    while mt == wt:
+                        mt = AA20[rng.randint(0, 20)]
+                    parts.append(f"{wt}{p + offset}{mt}")
+                muts[r] = ":".join(parts)
+    return muts
+
+
+def apply_mutant(seq: str, mutant: str, offset: int = 1) -> str:
+    s = list(seq)
+    for m in mutant.split(":"):
+        wt, pos, mt = m[0], int(m[1:-1]) - offset, m[-1]
+        assert s[pos] == wt
+        s[pos] = mt
+    return "".join(s)
+
+
+def write_dms_csv(path: str, seq: str, mutants, seed: int = 0):
+    """DMS CSV with the reference's columns (mutant, mutated_sequence, DMS_score, DMS_score_bin)."""
+    import pandas as pd
+    rng = np.random.RandomState(seed)
+    score = rng.randn(len(mutants))
+    df = pd.DataFrame({"mutant": mutants,
+                       "mutated_sequence": [apply_mutant(seq, m) for m in mutants],
+                       "DMS_score": score,
+                       "DMS_score_bin": (score > 0).astype(int)})
+    df.to_csv(path, index=False)
+    return df
+
+
+def write_mapping_csv(path: str, rows):
+    """Reference-file CSV with the columns compute_fitness.main reads (compute_fitness.py:288-307):
+    rows = [(DMS_id, DMS_filename, target_seq), ...]."""
+    import pandas as pd
+    df = pd.DataFrame({"DMS_id": [r[0] for r in rows], "DMS_filename": [r[1] for r in rows],
+                       "target_seq": [r[2] for r in rows]})
+    df.to_csv(path, index=False)
+    return df
