@@ -123,6 +123,14 @@ typedef struct {
 } pg_attn_args;
 int pg_attention(const pg_attn_args* args, pg_stream stream);
 
+/* Launch accounting and per-category device timing (bench.py's roofline leg).
+ * pg_launch_count: kernels launched by this library since load. pg_profile_begin/end: CUDA-event pairs are recorded on
+ * the launching stream around every kernel; _end (after the caller synchronised) returns summed ms and scope counts
+ * for categories {0 embed, 1 layernorm, 2 gemm_qkv, 3 attention, 4 gemm_out, 5 gemm_fc1, 6 gemm_fc2, 7 head, 8 score, 9 other}. */
+long long pg_launch_count(void);
+int pg_profile_begin(void);
+int pg_profile_end(float* ms, int32_t* counts, int32_t ncat);
+
 /* Build/version probe (also what the CPU-only test suite calls to check the library loads). */
 int pg_abi_version(void);
 

@@ -28,6 +28,49 @@ int num_sms() {
   return n;
 }
 
+// ---- launch accounting / profiling -------------------------------------------------------------------------------
+namespace {
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;      // pairs
+  std::vector<int> ev_cat;
+  size_t used = 0;
+  long long launches[CAT_COUNT] = {};
+};
+ProfState& prof() {
+  static ProfState p;
+  return p;
+}
+std::mutex& prof_mu() {
+  static std::mutex m;
+  return m;
+}
+}  // namespace
+
+ProfScope::ProfScope(int c, cudaStream_t st, int launches) : cat(c), s(st), slot(-1) {
+  std::lock_guard<std::mutex> lk(prof_mu());
+  ProfState& p = prof();
+  p.launches[c] += launches;
+  if (!p.on) return;
+  if (p.used + 2 > p.ev.size()) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      p.ev.push_back(e);
+    }
+    p.ev_cat.push_back(c);
+  }
+  slot = static_cast<int>(p.used);
+  p.ev_cat[slot / 2] = c;
+  p.used += 2;
+  cudaEventRecord(p.ev[slot], s);
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(prof_mu());
+  cudaEventRecord(prof().ev[slot + 1], s);
+}
+
 namespace {
 
 // fp32 [N, K] -> fp16 hi at [n, 0:K] and (np == 2) lo at [n, K:2K]; rows scaled by `scale` (q scaling fold).
@@ -112,43 +155,44 @@ int forward_rows(pg_handle h, const int32_t* tokens, int n_tokens, const int32_t
   e.P = Bc; e.T = T; e.d = d; e.embed = h->embed; e.pos_table = (D.arch == PG_ARCH_ESM1B) ? h->pos : nullptr;
   e.lnb_gamma = D.emb_ln_before ? h->lnbg : nullptr; e.lnb_beta = D.emb_ln_before ? h->lnbb : nullptr;
   e.token_dropout = D.token_dropout; e.mask_idx = 32; e.p_offset = p_offset; e.x = h->x;
-  int rc = launch_embed(e, s);
+  int rc;
+  { ProfScope ps(CAT_EMBED, s); rc = launch_embed(e, s); }
   if (rc) return rc;
   const bool rotary = (D.arch == PG_ARCH_ESM2);
   for (int l = 0; l < D.layers; ++l) {
     const Layer& L = h->layers[l];
-    rc = launch_layernorm_f16(h->x, d, L.ln1g, L.ln1b, rows, d, h->abuf, static_cast<int64_t>(d) * np, np == 2 ? d : 0, s);
+    { ProfScope ps(CAT_LN, s); rc = launch_layernorm_f16(h->x, d, L.ln1g, L.ln1b, rows, d, h->abuf, static_cast<int64_t>(d) * np, np == 2 ? d : 0, s); }
     if (rc) return rc;
     GemmLaunch g{};
     g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.wqkv; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.bqkv;
     g.M = rows; g.N = 3 * d; g.K = d; g.nseg = nseg; g.epi = rotary ? 3 : 0;
     g.out = h->qkv; g.ldo = static_cast<int64_t>(3 * d) * np; g.out_lo_off = np == 2 ? 3 * d : 0;
     g.rot_cos = h->rot_cos; g.rot_sin = h->rot_sin; g.rot_T = T; g.rot_dim = d;
-    rc = launch_gemm(g, s);
+    { ProfScope ps(CAT_GEMM_QKV, s); rc = launch_gemm(g, s); }
     if (rc) return rc;
     AttnLaunch a{};
     a.qkv = h->qkv; a.ld = static_cast<int64_t>(3 * d) * np; a.lo_off = np == 2 ? 3 * d : 0;
     a.out = h->abuf; a.ldo = static_cast<int64_t>(d) * np; a.out_lo_off = np == 2 ? d : 0;
     a.B = Bc; a.T = T; a.heads = D.heads; a.nseg = nseg; a.causal = 0; a.alibi_slopes = nullptr;
-    rc = launch_attention(a, s);
+    { ProfScope ps(CAT_ATTN, s); rc = launch_attention(a, s); }
     if (rc) return rc;
     g = GemmLaunch{};
     g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.wo; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.bo;
     g.M = rows; g.N = d; g.K = d; g.nseg = nseg; g.epi = 2; g.resid = h->x; g.ldr = d;
-    rc = launch_gemm(g, s);
+    { ProfScope ps(CAT_GEMM_OUT, s); rc = launch_gemm(g, s); }
     if (rc) return rc;
-    rc = launch_layernorm_f16(h->x, d, L.ln2g, L.ln2b, rows, d, h->abuf, static_cast<int64_t>(d) * np, np == 2 ? d : 0, s);
+    { ProfScope ps(CAT_LN, s); rc = launch_layernorm_f16(h->x, d, L.ln2g, L.ln2b, rows, d, h->abuf, static_cast<int64_t>(d) * np, np == 2 ? d : 0, s); }
     if (rc) return rc;
     g = GemmLaunch{};
     g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.w1; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.b1;
     g.M = rows; g.N = f; g.K = d; g.nseg = nseg; g.epi = 1;
     g.out = h->fbuf; g.ldo = static_cast<int64_t>(f) * np; g.out_lo_off = np == 2 ? f : 0;
-    rc = launch_gemm(g, s);
+    { ProfScope ps(CAT_GEMM_FC1, s); rc = launch_gemm(g, s); }
     if (rc) return rc;
     g = GemmLaunch{};
     g.a = h->fbuf; g.lda = static_cast<int64_t>(f) * np; g.w = L.w2; g.ldw = static_cast<int64_t>(f) * np; g.bias = L.b2;
     g.M = rows; g.N = d; g.K = f; g.nseg = nseg; g.epi = 2; g.resid = h->x; g.ldr = d;
-    rc = launch_gemm(g, s);
+    { ProfScope ps(CAT_GEMM_FC2, s); rc = launch_gemm(g, s); }
     if (rc) return rc;
   }
   return PG_OK;
@@ -171,6 +215,37 @@ using namespace pg;
 extern "C" {
 
 int pg_abi_version(void) { return 1; }
+
+long long pg_launch_count(void) {
+  std::lock_guard<std::mutex> lk(prof_mu());
+  long long t = 0;
+  for (int i = 0; i < CAT_COUNT; ++i) t += prof().launches[i];
+  return t;
+}
+
+int pg_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(prof_mu());
+  prof().on = true;
+  prof().used = 0;
+  return PG_OK;
+}
+
+// Stops profiling and returns, per category, the summed device time (ms) and number of timed scopes.
+// The caller must have synchronised the stream(s) first.
+int pg_profile_end(float* ms, int32_t* counts, int32_t ncat) {
+  std::lock_guard<std::mutex> lk(prof_mu());
+  ProfState& p = prof();
+  p.on = false;
+  for (int i = 0; i < ncat; ++i) { ms[i] = 0.f; counts[i] = 0; }
+  for (size_t i = 0; i + 1 < p.used; i += 2) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, p.ev[i], p.ev[i + 1]) != cudaSuccess) continue;
+    const int c = p.ev_cat[i / 2];
+    if (c < ncat) { ms[c] += t; counts[c] += 1; }
+  }
+  p.used = 0;
+  return PG_OK;
+}
 
 const char* pg_last_error(pg_handle h) {
   if (h && !h->err.empty()) return h->err.c_str();
@@ -334,6 +409,7 @@ int pg_masked_marginals(pg_handle h, const int32_t* tokens, int32_t n_tokens, co
     const int Bc = (P - p0) < per ? (P - p0) : static_cast<int>(per);
     int rc = forward_rows(h, tokens, n_tokens, positions, win_start, p0, Bc, T, s);
     if (rc) return fail(h, rc, tls_error());
+    ProfScope ps(CAT_HEAD, s, 4);
     row_select_kernel<<<(Bc + 255) / 256, 256, 0, s>>>(positions, win_start, out_row, p0, Bc, h->row_sel);
     HeadLaunch hl = head_args(h, T);
     hl.row_in_seq = h->row_sel; hl.P = Bc; hl.all_rows = 0;
@@ -364,7 +440,7 @@ int pg_forward_logprobs(pg_handle h, const int32_t* tokens, int32_t n_tokens, in
     hl.x = h->x + static_cast<long long>(r0) * h->desc.embed_dim;
     hl.P = (T - r0) < h->head_cap ? (T - r0) : h->head_cap; hl.all_rows = 1;
     hl.out = out_logprobs + static_cast<long long>(r0) * h->desc.vocab;
-    rc = launch_head(hl, s);
+    { ProfScope ps(CAT_HEAD, s, 3); rc = launch_head(hl, s); }
     if (rc) return fail(h, rc, tls_error());
   }
   return PG_OK;
@@ -375,6 +451,7 @@ int pg_score_mutants(const float* table, int32_t n_rows, int32_t vocab, const in
   if (M < 0 || n_rows < 0 || vocab <= 0) return set_error(PG_ERR_ARG, "pg_score_mutants: bad sizes");
   if (M == 0) return PG_OK;
   if (!table || !site_row || !site_wt || !site_mt || !row_offsets || !out_scores) return set_error(PG_ERR_ARG, "pg_score_mutants: null buffer");
+  ProfScope ps(CAT_SCORE, static_cast<cudaStream_t>(stream));
   return launch_score(table, n_rows, vocab, site_row, site_wt, site_mt, row_offsets, M, out_scores, static_cast<cudaStream_t>(stream));
 }
 
@@ -386,6 +463,7 @@ int pg_gemm(const pg_gemm_args* a, pg_stream stream) {
   g.out = static_cast<__half*>(a->out_h); g.ldo = a->ldo; g.out_lo_off = a->out_lo_off;
   g.resid = a->resid; g.ldr = a->ldr;
   g.rot_cos = a->rot_cos; g.rot_sin = a->rot_sin; g.rot_T = a->rot_T; g.rot_dim = a->rot_dim;
+  ProfScope ps(CAT_OTHER, static_cast<cudaStream_t>(stream));
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 

@@ -24,6 +24,14 @@ int set_error(int code, const std::string& msg);
 
 int num_sms();
 
+// Launch accounting + optional per-category CUDA-event timing (bench.py's roofline leg). Categories:
+enum ProfCat { CAT_EMBED = 0, CAT_LN, CAT_GEMM_QKV, CAT_ATTN, CAT_GEMM_OUT, CAT_GEMM_FC1, CAT_GEMM_FC2, CAT_HEAD, CAT_SCORE, CAT_OTHER, CAT_COUNT };
+struct ProfScope {  // records an event pair around the launches issued in its lifetime when profiling is on
+  ProfScope(int cat, cudaStream_t s, int launches = 1);
+  ~ProfScope();
+  int cat; cudaStream_t s; int slot;
+};
+
 // ---- kernel launchers (each returns a pg_status) ----
 struct GemmLaunch {
   const void* a; int64_t lda;

@@ -108,6 +108,7 @@ def write_esm_checkpoint(path: str, arch: EsmArch, seed: int = 0, state: dict | 
     stem = os.path.basename(path)
     if arch.kind == "esm2":
         assert stem.startswith("esm2"), "reference dispatches v2 on the file name (pretrained.py:187)"
+        assert arch.ffn_dim == 4 * arch.embed_dim, "ESM2 hard-codes ffn = 4 * embed_dim (esm2.py:52)"
         cfg = argparse.Namespace(encoder_layers=arch.layers, encoder_embed_dim=arch.embed_dim,
                                  encoder_attention_heads=arch.heads, token_dropout=arch.token_dropout)
         blob = {"cfg": {"model": cfg},

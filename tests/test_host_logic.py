@@ -1,0 +1,158 @@
+"""CPU: host-side mirror of the reference interface (tokenisation, windows, mutant parsing, checkpoint reading) and that
+the C-ABI library loads and exports every symbol include/pgscore.h declares (no compute calls: no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import esm_oracle as O
+from proteingym_b200 import _lib, checkpoint, synth
+from proteingym_b200.alphabet import ALPHABET
+from proteingym_b200.mutants import parse_mutants
+from proteingym_b200.windows import optimal_window_starts
+
+
+def test_alphabet_matches_reference_vocabulary():
+    assert ALPHABET.all_toks == O.VOCAB and len(ALPHABET) == 33
+    assert (ALPHABET.cls_idx, ALPHABET.padding_idx, ALPHABET.eos_idx, ALPHABET.unk_idx, ALPHABET.mask_idx) == (0, 1, 2, 3, 32)
+    seq = synth.random_protein(57, 1)
+    assert ALPHABET.tokenize_sequence(seq).tolist() == O.tokenize(seq).tolist()
+    assert ALPHABET.tokenize_sequence("").tolist() == [0, 2]
+    with pytest.raises(KeyError):
+        ALPHABET.tokenize_sequence("MKJ")  # data.py:256-257 indexes tok_to_idx directly
+    assert ALPHABET.get_idx("J") == 3  # label_row's get_idx falls back to <unk> (data.py:127-128)
+
+
+@pytest.mark.parametrize("n", [3, 100, 1024, 1025, 1102, 1535, 1536, 1537, 3425])
+def test_windows_match_get_optimal_window(n):
+    pos = np.arange(n)
+    starts, T = optimal_window_starts(pos, n)
+    for i in pos:
+        s, e = O.get_optimal_window(int(i), n, 1024)
+        assert (starts[i], starts[i] + T) == (s, e)
+        assert starts[i] <= i < starts[i] + T
+
+
+def test_parse_mutants_csr_and_reference_errors():
+    seq = "MKVLAAGIC"
+    rows, wts, mts, offs = parse_mutants(["M1A", "K2C:V3L", "C9W"], seq)
+    assert rows.tolist() == [1, 2, 3, 9] and offs.tolist() == [0, 1, 3, 4]
+    assert wts.tolist() == [ALPHABET.get_idx(c) for c in "MKVC"] and mts.tolist() == [ALPHABET.get_idx(c) for c in "ACLW"]
+    r2, *_ = parse_mutants(["M5A"], seq, offset_idx=5)  # --offset-idx / start_idx column (compute_fitness.py:307,427)
+    assert r2.tolist() == [1]
+    with pytest.raises(AssertionError, match="The listed wildtype does not match the provided sequence"):
+        parse_mutants(["A1G"], seq)
+    with pytest.raises(ValueError):
+        parse_mutants(["MxA"], seq)
+    with pytest.raises(IndexError):
+        parse_mutants(["M99A"], seq)
+    e = parse_mutants([], seq)
+    assert e[3].tolist() == [0] and len(e[0]) == 0
+
+
+@pytest.mark.parametrize("kind,fname", [("esm1v", "esm1v_t3_x.pt"), ("esm2", "esm2_t3_x.pt")])
+def test_checkpoint_reader_round_trip(tmp_path, kind, fname):
+    ffn = 256 if kind == "esm2" else 128  # ESM2 hard-codes ffn = 4 * embed_dim (esm2.py:52)
+    arch = synth.EsmArch(kind, 2, 64, 1, ffn, emb_layer_norm_before=(kind == "esm1v"))
+    st = synth.write_esm_checkpoint(str(tmp_path / fname), arch, seed=2)
+    conf, state, name = checkpoint.load_esm_checkpoint(str(tmp_path / fname))
+    assert name == fname[:-3]
+    assert (conf.arch, conf.layers, conf.embed_dim, conf.heads, conf.ffn_dim) == ("esm2" if kind == "esm2" else "esm1b", 2, 64, 1, ffn)
+    assert conf.emb_layer_norm_before == (kind == "esm1v") and conf.token_dropout
+    want = checkpoint.normalise_synth_state(arch, st)
+    assert set(want) == set(state)
+    for k in want:
+        assert torch.equal(want[k], state[k]), k
+    # v1 zeroes the <mask> embedding row (pretrained.py:97) and the tied head sees it; v2 does not
+    assert bool((state["embed_tokens.weight"][32] == 0).all()) == (kind == "esm1v")
+    ostate = O.load_state(st, kind)
+    assert torch.equal(ostate["lm_head.weight"], state["embed_tokens.weight"])
+
+
+def test_checkpoint_reader_rejects_unknown_arch(tmp_path):
+    import argparse
+    p = tmp_path / "weird.pt"
+    torch.save({"args": argparse.Namespace(arch="protein_bert_base"), "model": {}}, str(p))
+    with pytest.raises(ValueError):
+        checkpoint.load_esm_checkpoint(str(p))
+    with pytest.raises(ValueError):
+        checkpoint.load_esm_checkpoint("esm1v_t33_650M_UR90S_1")  # hub names need the network
+
+
+def test_rotary_tables_match_reference_formula():
+    inv = 1.0 / (10000 ** (torch.arange(0, 64, 2).float() / 64))
+    cos, sin = checkpoint.rotary_tables(inv, 300)
+    c2, s2 = O.rotary_tables(300, 64, torch.float32)
+    assert torch.equal(cos, c2[:, :32]) and torch.equal(sin, s2[:, :32]) and torch.equal(c2[:, :32], c2[:, 32:])
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from __graft_entry__ import build
+    build()
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "pgscore.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pg_abi_version() == 1
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "proteingym_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "esm_oracle" not in src, f
+
+
+def test_no_cuda_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from proteingym_b200.esm_engine import EsmScorer
+    arch = synth.EsmArch("esm1v", 1, 64, 1, 64)
+    with pytest.raises(_lib.PgError):
+        EsmScorer(checkpoint.config_from_synth(arch), checkpoint.normalise_synth_state(arch, synth.make_esm_state(arch)))
+
+
+def test_cli_flag_surface_matches_reference():
+    """tests/golden/esm_cli_flags.json was dumped from the reference's create_parser() (compute_fitness.py:100-238)."""
+    import json
+    from proteingym_b200.compute_fitness import create_parser
+
+    def dump(p):
+        out = {}
+        for a in p._actions:
+            if not a.option_strings or a.dest == "help":
+                continue
+            out[a.dest] = {"opts": sorted(a.option_strings), "default": str(a.default), "nargs": str(a.nargs),
+                           "type": getattr(a.type, "__name__", str(a.type)), "choices": list(a.choices) if a.choices else None,
+                           "const": str(a.const)}
+        return out
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "esm_cli_flags.json")))
+    mine = dump(create_parser())
+    assert set(mine) - set(ref) == {"precision", "device"}  # additive flags only
+    for k, v in ref.items():
+        assert mine[k] == v, k
+
+
+def test_cli_resolve_assay_errors_match_reference(tmp_path):
+    from proteingym_b200.compute_fitness import create_parser, resolve_assay
+    synth.write_mapping_csv(str(tmp_path / "map.csv"), [("A1", "a1.csv", "mkv"), ("A1", "a1b.csv", "MKV"), ("B2", "b2.csv", "MKVL")])
+    import pandas as pd
+    pd.DataFrame({"mutant": []}).to_csv(tmp_path / "b2.csv", index=False)
+    base = ["--dms_mapping", str(tmp_path / "map.csv"), "--dms-input", str(tmp_path), "--dms-output", str(tmp_path / "out")]
+    with pytest.raises(ValueError, match="Multiple mappings found"):
+        resolve_assay(create_parser().parse_args(base + ["--dms_index", "0"]))
+    with pytest.raises(ValueError, match="No rows found"):
+        resolve_assay(create_parser().parse_args(base + ["--dms_index", "2"]))
+    synth.write_dms_csv(str(tmp_path / "b2.csv"), "MKVL", ["M1A", "K2C"])
+    a = create_parser().parse_args(base + ["--dms_index", "2"])
+    df, col, off = resolve_assay(a)
+    assert (len(df), col, off, a.sequence) == (2, "mutant", 1, "MKVL") and a.dms_output.endswith("B2.csv")

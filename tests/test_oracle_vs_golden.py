@@ -1,0 +1,71 @@
+"""CPU: the oracle restatement (oracle/esm_oracle.py) against golden vectors produced by the UNMODIFIED reference
+(oracle/gen_golden.py ran /root/reference's compute_fitness.main + fair-esm modules on the same seeded checkpoints)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_SMALL, GOLDEN_WINDOW, load_golden
+from oracle import esm_oracle as O
+
+
+def _kind(arch):
+    return "esm2" if arch.kind == "esm2" else "esm1v"
+
+
+@pytest.mark.parametrize("name", GOLDEN_SMALL)
+def test_oracle_table_and_scores_match_reference(name):
+    g = load_golden(name)
+    arch, seq = g["arch"], g["seq"]
+    st = O.load_state(g["state"](), _kind(arch))
+    table = O.masked_marginal_table(st, seq, _kind(arch), arch.layers, arch.heads, arch.token_dropout)
+    assert table.shape == g["table"].shape == (len(seq) + 2, 33)
+    assert np.abs(table.numpy() - g["table"]).max() < 5e-5  # fp32 summation-order noise only
+    col = g["meta"]["ckpt_names"][0].split(".")[0]
+    got = O.score_mutants(g["df"]["mutant"], seq, table)
+    assert np.abs(got - g["df"][col].to_numpy()).max() < 1e-4
+
+
+def test_oracle_ensemble_column_matches_reference():
+    # compute_fitness.py:530-537: Ensemble_ESM1v = mean of the per-checkpoint columns
+    g = load_golden("tiny_esm1v")
+    arch, seq, df = g["arch"], g["seq"], g["df"]
+    cols = [c.split(".")[0] for c in g["meta"]["ckpt_names"]]
+    assert "Ensemble_ESM1v" in df.columns and len(cols) == 2
+    acc = np.zeros(len(df))
+    for c, seed in zip(cols, (g["meta"]["seed"], g["meta"]["extra_seed"])):
+        st = O.load_state(g["state"](seed), "esm1v")
+        t = O.masked_marginal_table(st, seq, "esm1v", arch.layers, arch.heads)
+        s = O.score_mutants(df["mutant"], seq, t)
+        assert np.abs(s - df[c].to_numpy()).max() < 1e-4
+        acc += s
+    assert np.abs(acc / 2 - df["Ensemble_ESM1v"].to_numpy()).max() < 1e-4
+
+
+@pytest.mark.parametrize("name", GOLDEN_WINDOW)
+def test_oracle_windowed_rows_match_reference(name):
+    # L+2 = 1102 > 1024: per-position optimal windows (compute_fitness.py:492-495); check a spread of positions
+    g = load_golden(name)
+    arch, seq = g["arch"], g["seq"]
+    st = O.load_state(g["state"](), _kind(arch))
+    pos = [0, 1, 300, 511, 512, 513, 560, 589, 590, 591, 700, 1100, 1101]
+    table = O.masked_marginal_table(st, seq, _kind(arch), arch.layers, arch.heads, positions=pos)
+    assert np.abs(table[pos].numpy() - g["table"][pos]).max() < 5e-5
+
+
+def test_oracle_true_size_rows_match_reference():
+    # BASELINE config 1 at true ESM-1v 650M size: a few rows of the 288-row table the reference produced
+    g = load_golden("blat_esm1v_650m")
+    arch, seq = g["arch"], g["seq"]
+    st = O.load_state(g["state"](), "esm1v")
+    pos = [24, 150, 286]
+    table = O.masked_marginal_table(st, seq, "esm1v", arch.layers, arch.heads, positions=pos, batch=3)
+    assert np.abs(table[pos].numpy() - g["table"][pos]).max() < 2e-4
+
+
+def test_oracle_fp64_agrees_with_fp32():
+    g = load_golden("tiny_esm2")
+    arch, seq = g["arch"], g["seq"]
+    t32 = O.masked_marginal_table(O.load_state(g["state"](), "esm2"), seq, "esm2", arch.layers, arch.heads, positions=range(1, 20))
+    t64 = O.masked_marginal_table(O.load_state(g["state"](), "esm2", torch.float64), seq, "esm2", arch.layers, arch.heads,
+                                  dtype=torch.float64, positions=range(1, 20))
+    assert (t32[1:20].double() - t64[1:20]).abs().max() < 5e-5
