@@ -83,7 +83,8 @@ def test_gemm_matches_fp64(M, N, K, nseg, epi):
     got = resid.double() if epi == 2 else out[:, :N].double() + (out[:, N:].double() if nseg == 3 else 0)
     err = (got - ref).abs().max().item()
     # fp32 accumulate of exactly-representable products; the fp16 output rounding dominates for single-plane outputs
-    bound = 3e-5 if (epi == 2 or nseg == 3) else 2.5e-3 * max(1.0, ref.abs().max().item() / 4)
+    amax = ref.abs().max().item()
+    bound = 4e-7 * (K * nseg) ** 0.5 * max(4.0, amax) if (epi == 2 or nseg == 3) else 2.5e-3 * max(1.0, amax / 4)
     assert err < bound, (err, bound)
 
 
