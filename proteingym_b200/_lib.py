@@ -33,7 +33,7 @@ class PgAttnArgs(C.Structure):
     _fields_ = [("qkv", C.c_void_p), ("ld", C.c_int64), ("lo_off", C.c_int64),
                 ("out", C.c_void_p), ("ldo", C.c_int64), ("out_lo_off", C.c_int64),
                 ("B", C.c_int32), ("T", C.c_int32), ("heads", C.c_int32), ("nseg", C.c_int32),
-                ("causal", C.c_int32), ("alibi_slopes", C.c_void_p)]
+                ("causal", C.c_int32), ("alibi_slopes", C.c_void_p), ("impl", C.c_int32)]
 
 
 # every symbol include/pgscore.h declares, with its ctypes signature

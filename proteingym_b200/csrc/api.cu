@@ -174,7 +174,7 @@ int forward_rows(pg_handle h, const int32_t* tokens, int n_tokens, const int32_t
     a.qkv = h->qkv; a.ld = static_cast<int64_t>(3 * d) * np; a.lo_off = np == 2 ? 3 * d : 0;
     a.out = h->abuf; a.ldo = static_cast<int64_t>(d) * np; a.out_lo_off = np == 2 ? d : 0;
     a.B = Bc; a.T = T; a.heads = D.heads; a.nseg = nseg; a.causal = 0; a.alibi_slopes = nullptr;
-    { ProfScope ps(CAT_ATTN, s); rc = launch_attention(a, s); }
+    { ProfScope ps(CAT_ATTN, s); rc = launch_attention_tc(a, s); }
     if (rc) return rc;
     g = GemmLaunch{};
     g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.wo; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.bo;
@@ -479,6 +479,9 @@ int pg_attention(const pg_attn_args* a, pg_stream stream) {
   l.qkv = static_cast<const __half*>(a->qkv); l.ld = a->ld; l.lo_off = a->lo_off;
   l.out = static_cast<__half*>(a->out); l.ldo = a->ldo; l.out_lo_off = a->out_lo_off;
   l.B = a->B; l.T = a->T; l.heads = a->heads; l.nseg = a->nseg; l.causal = a->causal; l.alibi_slopes = a->alibi_slopes;
+  ProfScope ps(CAT_OTHER, static_cast<cudaStream_t>(stream));
+  const bool tc_ok = !a->causal && !a->alibi_slopes;
+  if (a->impl == 2 || (a->impl == 0 && tc_ok)) return launch_attention_tc(l, static_cast<cudaStream_t>(stream));
   return launch_attention(l, static_cast<cudaStream_t>(stream));
 }
 

@@ -1,0 +1,400 @@
+// K4 — tcgen05/TMEM fused multi-head self-attention (non-causal), head_dim 64, equal-length sequences.
+// Reference arithmetic: esm/multihead_attention.py:357 (QK^T), :379 (fp32 softmax), :387 (PV); q pre-scaled / pre-rotated.
+//
+// One persistent CTA per SM (384 threads); work item = (sequence, head, 128-query tile):
+//   warp 0     TMA producer: Q tile (128x64) and a ring of 128-key K / V tiles (SWIZZLE_128B), in MMA consumption order
+//   warp 1     MMA issuer (one thread):  S = Q K^T  (tcgen05.mma M128 N<=128 K16, K-major B)  -> TMEM S[2] (fp32)
+//                                         O += P V   (A = P from swizzled smem, B = V MN-major)   -> TMEM O (128x64 fp32)
+//   warp 2     TMEM allocator
+//   warps 4-11 softmax: thread = (query row, 64-key half) (tcgen05.ld 32x32b), exp2 in fp32, P -> fp16 (hi[, lo]) -> smem
+//
+// Softmax is exact two-pass instead of online rescaling: pass A runs QK^T (hi*hi only) just to get each row's max,
+// pass B recomputes S, forms P = exp(S - max) and accumulates O directly in TMEM — no O correction step, and the
+// tensor pipe has headroom because the kernel is exp-throughput bound (16 MUFU/clk/SM) in single-pass mode.
+// NP == 2 (f16x3 parity mode): Q,K,V arrive as hi|lo planes, S = QhKh + QlKh + QhKl, O = PhVh + PlVh + PhVl.
+// Roofline: tensor/MUFU bound; algorithmic FLOPs = 4*T^2*64 per (sequence, head).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace pg {
+
+namespace {
+
+constexpr int QT = 128, KT = 128;
+constexpr uint32_t TILE = 16384;  // 128 rows x 64 fp16
+constexpr int NSLOT = 4;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t S_COL0 = 0, O_COL = 256;
+
+template <int NP>
+struct Smem {
+  static constexpr uint32_t Q = 0;
+  static constexpr uint32_t KV = NP * TILE;
+  static constexpr uint32_t P = KV + NSLOT * NP * TILE;
+  static constexpr uint32_t BAR = P + NP * 2 * TILE;
+  static constexpr uint32_t TOTAL = BAR + 256 + 1024 + 1024;
+};
+
+struct AttnTcParams {
+  int B, T, heads, nqt, nkb;
+  int d;                  // heads * 64
+  long long lo_off;       // column offset of the lo planes in qkv
+  __half* out; long long ldo; long long out_lo_off;
+};
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {  // 2^x, one MUFU; inputs here are <= ~0, tiny results flush to 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo_elem, float hi_elem) {  // packed RN convert: {hi_elem, lo_elem}
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
+  using L = Smem<NP>;
+  uint8_t* sQ = smem + L::Q;
+  uint8_t* sKV = smem + L::KV;
+  uint8_t* sP = smem + L::P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;            // [NSLOT]
+  uint64_t* kv_empty = kv_full + NSLOT;    // [NSLOT]
+  uint64_t* s_full = kv_empty + NSLOT;     // [2]
+  uint64_t* s_empty = s_full + 2;          // [2]
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 1;
+  uint64_t* o_full = p_empty + 1;
+  uint64_t* o_empty = o_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_empty + 1);
+  float* red = reinterpret_cast<float*>(smem + L::BAR + 256);  // [2][128] cross-warpgroup row reductions
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nitems = p.B * p.heads * p.nqt;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tm);
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int i = 0; i < NSLOT; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 8);
+    }
+    mbar_init(p_full, 8);
+    mbar_init(p_empty, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 8);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  auto nkeys = [&](int j) {  // keys of block j rounded up to the MMA granularity
+    const int rem = p.T - j * KT;
+    const int n = rem < KT ? rem : KT;
+    return (n + 15) & ~15;
+  };
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        const int qt = item % p.nqt, bh = item / p.nqt;
+        const int h = bh % p.heads, b = bh / p.heads;
+        const int row0 = b * p.T;
+        const int cq = h * 64, ck = p.d + h * 64, cv = 2 * p.d + h * 64;
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, NP * TILE);
+        for (int pl = 0; pl < NP; ++pl) tma_load_2d(sQ + pl * TILE, &tm, q_full, cq + pl * static_cast<int>(p.lo_off), row0 + qt * QT);
+        auto load_block = [&](int col, int j, int planes) {
+          mbar_wait(&kv_empty[slot], phase ^ 1);
+          mbar_arrive_expect_tx(&kv_full[slot], planes * TILE);
+          for (int pl = 0; pl < planes; ++pl)
+            tma_load_2d(sKV + (slot * NP + pl) * TILE, &tm, &kv_full[slot], col + pl * static_cast<int>(p.lo_off), row0 + j * KT);
+          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+        };
+        for (int j = 0; j < p.nkb; ++j) load_block(ck, j, 1);  // pass A: K hi only
+        load_block(ck, 0, NP);                                  // pass B: K0, then (K_{j+1}, V_j) ...
+        for (int j = 0; j < p.nkb; ++j) {
+          if (j + 1 < p.nkb) load_block(ck, j + 1, NP);
+          load_block(cv, j, NP);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_o = make_idesc_f16(QT, 64, 0, 1);  // A = P (K-major), B = V (MN-major)
+      int slot = 0;
+      uint32_t phase = 0;
+      uint32_t sblk = 0, pblk = 0;
+      int it = 0;
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        mbar_wait(q_full, it & 1);
+        auto issue_qk = [&](int j, bool full) {
+          const uint32_t buf = sblk & 1;
+          mbar_wait(&kv_full[slot], phase);
+          mbar_wait(&s_empty[buf], ((sblk >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t idesc_s = make_idesc_f16(QT, nkeys(j), 0, 0);
+          const uint32_t k_addr = smem_u32(sKV + slot * NP * TILE);
+          const uint32_t tmem_s = tmem_base + S_COL0 + buf * KT;
+          const uint64_t qh = make_desc_sw128(q_addr, 1024), kh = make_desc_sw128(k_addr, 1024);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_s, qh + 2 * ks, kh + 2 * ks, idesc_s, ks > 0);
+          if (NP == 2 && full) {
+            const uint64_t ql = make_desc_sw128(q_addr + TILE, 1024), kl = make_desc_sw128(k_addr + TILE, 1024);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_s, ql + 2 * ks, kh + 2 * ks, idesc_s, 1);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_s, qh + 2 * ks, kl + 2 * ks, idesc_s, 1);
+          }
+          umma_commit(&kv_empty[slot]);
+          umma_commit(&s_full[buf]);
+          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+          ++sblk;
+        };
+        for (int j = 0; j < p.nkb; ++j) issue_qk(j, false);  // pass A (row max only)
+        issue_qk(0, true);
+        for (int j = 0; j < p.nkb; ++j) {
+          if (j + 1 < p.nkb) issue_qk(j + 1, true);
+          else umma_commit(q_empty);  // all QK MMAs of this item issued: Q tile free once they complete
+          mbar_wait(&kv_full[slot], phase);
+          mbar_wait(p_full, pblk & 1);
+          if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(sKV + slot * NP * TILE);
+          const uint32_t tmem_o = tmem_base + O_COL;
+          const int nks = nkeys(j) >> 4;
+          for (int ks = 0; ks < nks; ++ks) {
+            // A: P[128 x 16 keys] inside 64-key swizzle atoms of 16 KiB; B: V[16 keys x 64] = 2 KiB further per step
+            const uint32_t pa = p_addr + (ks >> 2) * TILE + (ks & 3) * 32;
+            const uint64_t ph = make_desc_sw128(pa, 1024);
+            const uint64_t vh = make_desc_sw128(v_addr + ks * 2048, 1024, 1024);
+            umma_f16(tmem_o, ph, vh, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+            if (NP == 2) {
+              const uint64_t pl = make_desc_sw128(pa + 2 * TILE, 1024);
+              const uint64_t vl = make_desc_sw128(v_addr + TILE + ks * 2048, 1024, 1024);
+              umma_f16(tmem_o, pl, vh, idesc_o, 1);
+              umma_f16(tmem_o, ph, vl, idesc_o, 1);
+            }
+          }
+          umma_commit(&kv_empty[slot]);
+          umma_commit(p_empty);
+          if (j == p.nkb - 1) umma_commit(o_full);
+          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+          ++pblk;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================= softmax + epilogue
+    // 8 warps: thread = (query row, 64-key column half g). Two warps per scheduler hide each other's latencies.
+    const int wq = warp & 3;
+    const int g = (warp - 4) >> 2;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
+    constexpr float LOG2E = 1.4426950408889634f;
+    uint32_t sblk = 0, pblk = 0;
+    int it = 0;
+    uint8_t* prow = sP + g * TILE + row * 128;  // this thread's row inside its 64-key swizzle atom
+    const int sw = row & 7;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+      const int qt = item % p.nqt, bh = item / p.nqt;
+      const int h = bh % p.heads, b = bh / p.heads;
+      // ---- pass A: row max over this thread's columns ----
+      float m = -INFINITY;
+      for (int j = 0; j < p.nkb; ++j, ++sblk) {
+        const uint32_t buf = sblk & 1;
+        mbar_wait(&s_full[buf], (sblk >> 1) & 1);
+        tc_fence_after();
+        const int valid = p.T - j * KT - g * 64;  // valid keys in this thread's 64 columns (may be <= 0 or >= 64)
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          if (c * 32 >= valid) break;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL0 + buf * KT + g * 64 + c * 32, r);
+          tmem_ld_wait();
+          if (valid - c * 32 >= 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < valid) m = fmaxf(m, __uint_as_float(r[i]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[buf]);
+      }
+      red[g * 128 + row] = m;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      m = fmaxf(m, red[(g ^ 1) * 128 + row]);
+      const float m2 = m * LOG2E;
+      float l = 0.f;
+      // ---- pass B: P = exp(S - max) ----
+      for (int j = 0; j < p.nkb; ++j, ++sblk, ++pblk) {
+        const uint32_t buf = sblk & 1;
+        mbar_wait(&s_full[buf], (sblk >> 1) & 1);
+        tc_fence_after();
+        const int valid = p.T - j * KT - g * 64;
+        const int ncols = nkeys(j) - g * 64;  // columns the PV MMA will read from this thread's half
+        uint32_t r[2][32];
+        if (ncols > 0) tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL0 + buf * KT + g * 64, r[0]);
+        if (ncols > 32) tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL0 + buf * KT + g * 64 + 32, r[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[buf]);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c * 32 < ncols) {
+            if (valid - c * 32 >= 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float e = ex2_approx(fmaf(__uint_as_float(r[c][i]), LOG2E, -m2));
+                l += e;
+                r[c][i] = __float_as_uint(e);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float e = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(r[c][i]), LOG2E, -m2)) : 0.f;
+                l += e;
+                r[c][i] = __float_as_uint(e);
+              }
+            }
+          }
+        }
+        mbar_wait(p_empty, (pblk & 1) ^ 1);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {  // 8 keys = one 16-byte chunk of the 128-byte swizzled row
+            if (c * 32 + q8 * 8 < ncols) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float x0 = __uint_as_float(r[c][q8 * 8 + 2 * u]), x1 = __uint_as_float(r[c][q8 * 8 + 2 * u + 1]);
+                hi[u] = cvt_f16x2(x0, x1);
+                if (NP == 2) {
+                  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
+                  lo[u] = cvt_f16x2(x0 - hf.x, x1 - hf.y);
+                }
+              }
+              uint8_t* dst = prow + (((c * 4 + q8) ^ sw) << 4);
+              *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              if (NP == 2) *reinterpret_cast<uint4*>(dst + 2 * TILE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      // ---- epilogue: O / l -> fp16 hi[/lo]; this thread owns 32 of the 64 head-dim columns ----
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read the pass-A maxima
+      red[g * 128 + row] = l;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      l += red[(g ^ 1) * 128 + row];
+      mbar_wait(o_full, it & 1);
+      tc_fence_after();
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + g * 32, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      const int qidx = qt * QT + row;
+      if (qidx < p.T) {
+        const float rl = 1.f / l;
+        __half* orow = p.out + (static_cast<long long>(b) * p.T + qidx) * p.ldo + h * 64 + g * 32;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float x0 = __uint_as_float(o[2 * u]) * rl, x1 = __uint_as_float(o[2 * u + 1]) * rl;
+          hi[u] = cvt_f16x2(x0, x1);
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
+          lo[u] = cvt_f16x2(x0 - hf.x, x1 - hf.y);
+        }
+        uint4* d4 = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d4[u] = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
+        if (p.out_lo_off > 0) {
+          uint4* l4 = reinterpret_cast<uint4*>(orow + p.out_lo_off);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) l4[u] = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // red[] reuse by the next item
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace
+
+int launch_attention_tc(const AttnLaunch& a, cudaStream_t s) {
+  if (a.B <= 0 || a.T <= 0) return PG_OK;
+  if (a.causal || a.alibi_slopes) return set_error(PG_ERR_UNSUPPORTED, "attention_tc: causal/ALiBi not supported by this kernel");
+  if (a.nseg != 1 && a.nseg != 3) return set_error(PG_ERR_ARG, "attention: nseg must be 1 or 3");
+  if (a.ld % 8 || a.lo_off % 8 || a.ldo % 8 || a.out_lo_off % 8 || (reinterpret_cast<uintptr_t>(a.out) & 15))
+    return set_error(PG_ERR_ARG, "attention_tc: pitches must be multiples of 8 elements and out 16-byte aligned");
+  AttnTcParams p{};
+  p.B = a.B; p.T = a.T; p.heads = a.heads; p.d = a.heads * 64;
+  p.nqt = (a.T + QT - 1) / QT; p.nkb = (a.T + KT - 1) / KT;
+  p.lo_off = a.lo_off; p.out = a.out; p.ldo = a.ldo; p.out_lo_off = a.out_lo_off;
+  const int np = a.nseg == 3 ? 2 : 1;
+  const uint64_t width = static_cast<uint64_t>(3) * p.d * np;
+  if (np == 2 && a.lo_off != 3ll * p.d) return set_error(PG_ERR_ARG, "attention_tc: lo planes must follow the hi planes (lo_off == 3*d)");
+  CUtensorMap tm;
+  int rc = make_tmap_f16_2d(&tm, a.qkv, static_cast<uint64_t>(a.B) * a.T, width, a.ld, 128, 64);
+  if (rc) return rc;
+  const long long nitems = static_cast<long long>(a.B) * a.heads * p.nqt;
+  const int grid = nitems < num_sms() ? static_cast<int>(nitems) : num_sms();
+  static bool set1 = false, set2 = false;
+  if (np == 1) {
+    if (!set1) {
+      PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<1>::TOTAL));
+      set1 = true;
+    }
+    attn_tc_kernel<1><<<grid, 384, Smem<1>::TOTAL, s>>>(tm, p);
+  } else {
+    if (!set2) {
+      PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::TOTAL));
+      set2 = true;
+    }
+    attn_tc_kernel<2><<<grid, 384, Smem<2>::TOTAL, s>>>(tm, p);
+  }
+  PG_CUDA_OK(cudaGetLastError());
+  return PG_OK;
+}
+
+}  // namespace pg

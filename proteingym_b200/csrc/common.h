@@ -89,3 +89,10 @@ int launch_score(const float* table, int n_rows, int vocab, const int32_t* site_
                  const int32_t* site_mt, const int32_t* row_offsets, int M, float* out, cudaStream_t s);
 
 }  // namespace pg
+
+namespace pg {
+// 2D fp16 row-major tensor map [rows, cols] (pitch ld elements), box [box_rows, box_cols], SWIZZLE_128B, OOB -> 0.
+int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols);
+int launch_attention_tc(const AttnLaunch& a, cudaStream_t s);  // tcgen05/TMEM attention (non-causal, no ALiBi)
+}  // namespace pg

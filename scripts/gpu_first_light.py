@@ -4,7 +4,8 @@ import ctypes as C, os, subprocess, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 
-STAGES = ["gemm_small", "gemm_epi", "gemm_x3", "gemm_big", "ln", "attn", "attn_x3", "model_esm1v", "model_esm2", "model_x3", "score"]
+STAGES = ["gemm_small", "gemm_epi", "gemm_x3", "gemm_big", "ln", "attn", "attn_x3", "attn_perf", "model_esm1v", "model_esm2", "model_x3"]
+if os.environ.get("PG_STAGES"): STAGES = os.environ["PG_STAGES"].split(",")
 
 def hilo(t):
     hi = t.to(torch.float16); lo = (t - hi.float()).to(torch.float16); return torch.cat([hi, lo], dim=1).contiguous()
@@ -96,7 +97,7 @@ def stage_ln():
         got = out[:, :d].double() + out[:, d:].double()
         print(f"  ln rows={rows} d={d} rc={rc}: max|err|={(got-ref).abs().max().item():.3e}  hi-only err={(out[:, :d].double()-ref).abs().max().item():.3e}")
 
-def run_attn(B, T, H, nseg, causal=0):
+def run_attn(B, T, H, nseg, causal=0, impl=0):
     from proteingym_b200 import _lib
     lib = _lib.load()
     d = H * 64; g = torch.Generator(device="cuda").manual_seed(1)
@@ -111,16 +112,40 @@ def run_attn(B, T, H, nseg, causal=0):
     out = torch.zeros(B * T, d * np_, device="cuda", dtype=torch.float16)
     a = _lib.PgAttnArgs(); a.qkv = q16.data_ptr(); a.ld = 3 * d * np_; a.lo_off = 3 * d if nseg == 3 else 0
     a.out = out.data_ptr(); a.ldo = d * np_; a.out_lo_off = d if nseg == 3 else 0
-    a.B, a.T, a.heads, a.nseg, a.causal = B, T, H, nseg, causal
+    a.B, a.T, a.heads, a.nseg, a.causal, a.impl = B, T, H, nseg, causal, impl
     rc = lib.pg_attention(C.byref(a), None); torch.cuda.synchronize()
+    if rc: print("  rc", rc, lib.pg_last_error(None)); return
     got = out[:, :d].double() + (out[:, d:].double() if nseg == 3 else 0)
     err = (got - ref).abs()
-    print(f"  attn B={B} T={T} H={H} nseg={nseg} causal={causal} rc={rc}: max|err|={err.max().item():.3e} mean={err.mean().item():.3e}")
+    print(f"  attn impl={impl} B={B} T={T} H={H} nseg={nseg} causal={causal} rc={rc}: max|err|={err.max().item():.3e} mean={err.mean().item():.3e} nan={torch.isnan(got).sum().item()}")
+    if err.max().item() > 1e-2 or torch.isnan(got).any():
+        e2 = err.view(B, T, H, 64)
+        print("   err by query-tile:", [round(e2[:, i:i+128].max().item(), 4) for i in range(0, T, 128)], " by head-dim half:", e2[..., :32].max().item(), e2[..., 32:].max().item())
+        print("   got[0,:6]", got[0, :6].tolist(), "ref", ref[0, :6].tolist())
 
 def stage_attn():
-    run_attn(2, 64, 2, 1); run_attn(3, 100, 2, 1); run_attn(2, 514, 4, 1); run_attn(1, 1024, 2, 1); run_attn(2, 130, 2, 1, causal=1)
+    run_attn(2, 64, 2, 1, impl=1); run_attn(2, 130, 2, 1, causal=1, impl=1)
+    for (B, T, H) in ((1, 16, 1), (2, 64, 2), (1, 128, 1), (3, 100, 2), (2, 200, 1), (2, 514, 4), (1, 1024, 2), (40, 514, 20)): run_attn(B, T, H, 1, impl=2)
 def stage_attn_x3():
-    run_attn(2, 64, 2, 3); run_attn(3, 100, 2, 3); run_attn(2, 514, 4, 3)
+    for (B, T, H) in ((1, 16, 1), (2, 64, 2), (3, 100, 2), (2, 514, 4), (40, 514, 20)): run_attn(B, T, H, 3, impl=2)
+def stage_attn_perf():
+    from proteingym_b200 import _lib
+    lib = _lib.load()
+    B, T, H = 128, 514, 20; d = H * 64
+    for nseg in (1, 3):
+        np_ = 2 if nseg == 3 else 1
+        qkv = (torch.randn(B * T, 3 * d * np_, device="cuda") * 0.5).half(); out = torch.empty(B * T, d * np_, device="cuda", dtype=torch.float16)
+        for impl in (1, 2):
+            a = _lib.PgAttnArgs(); a.qkv = qkv.data_ptr(); a.ld = 3 * d * np_; a.lo_off = 3 * d if nseg == 3 else 0
+            a.out = out.data_ptr(); a.ldo = d * np_; a.out_lo_off = d if nseg == 3 else 0
+            a.B, a.T, a.heads, a.nseg, a.causal, a.impl = B, T, H, nseg, 0, impl
+            for _ in range(2): lib.pg_attention(C.byref(a), None)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record()
+            for _ in range(5): lib.pg_attention(C.byref(a), None)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            print(f"  attn perf impl={impl} nseg={nseg} B={B} T={T} H={H}: {ms:.3f} ms  {4*B*H*T*T*64/ms/1e9:.1f} algorithmic TFLOP/s")
 
 def run_model(kind, precision, L=70, layers=2, d=128, heads=2, ffn=256, lnb=False):
     from proteingym_b200 import synth, checkpoint
