@@ -29,7 +29,9 @@ constexpr int GEMM_THREADS = (FIRST_EPI_WARP + NUM_EPI_WARPS) * 32;
 constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KiB
 constexpr uint32_t B_BYTES = BN * BK * 2;  // 32 KiB
 constexpr uint32_t OFF_B = STAGES * A_BYTES;
-constexpr uint32_t OFF_BAR = OFF_B + STAGES * B_BYTES;
+constexpr uint32_t OFF_STG = OFF_B + STAGES * B_BYTES;      // epilogue staging: 4 KiB per epilogue warp
+constexpr uint32_t STG_BYTES = 4096;
+constexpr uint32_t OFF_BAR = OFF_STG + NUM_EPI_WARPS * STG_BYTES;
 constexpr uint32_t GEMM_SMEM = OFF_BAR + 256 + 1024;  // + barriers + 1 KiB alignment slack
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -46,47 +48,48 @@ struct GemmKParams {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// Store 32 consecutive columns of one row as fp16 (hi, optional lo). Fast path: 4 x 16-byte stores.
-__device__ __forceinline__ void store_row_f16(const float (&v)[32], __half* out, long long ldo, long long lo_off, long long row,
-                                              int gcol, int N) {
-  __half* dst = out + row * ldo + gcol;
-  if (gcol + 32 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((lo_off & 7) == 0)) {
-    uint32_t hi[16], lo[16];
+// Epilogue staging: each warp owns a 32-row x 128-byte tile in shared memory laid out for a SWIZZLE_128B TMA store
+// (16-byte chunk c of row r lives at chunk c ^ (r & 7)), so the per-thread row writes are bank-conflict free and the
+// global write is one coalesced bulk tensor store (or reduce-add) per 32x64 fp16 / 32x32 fp32 block, clipped at M and N.
+__device__ __forceinline__ void stage_row_f16(uint8_t* stg, int lane, const float (&v0)[32], const float (&v1)[32], bool lo_plane) {
+  uint8_t* row = stg + lane * 128;
+  const int sw = lane & 7;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      __half h0, l0, h1, l1;
-      split_hi_lo(v[2 * j], h0, l0);
-      split_hi_lo(v[2 * j + 1], h1, l1);
-      hi[j] = pack_h2(h0, h1);
-      lo[j] = pack_h2(l0, l1);
-    }
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
+  for (int c = 0; c < 8; ++c) {
+    uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) d4[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-    if (lo_off > 0) {
-      uint4* l4 = reinterpret_cast<uint4*>(dst + lo_off);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) l4[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-    }
-  } else {
-    for (int j = 0; j < 32; ++j) {
-      if (gcol + j < N) {
-        __half h, l;
-        split_hi_lo(v[j], h, l);
-        dst[j] = h;
-        if (lo_off > 0) dst[lo_off + j] = l;
+    for (int u = 0; u < 4; ++u) {
+      const float x0 = (c < 4) ? v0[c * 8 + 2 * u] : v1[(c - 4) * 8 + 2 * u];
+      const float x1 = (c < 4) ? v0[c * 8 + 2 * u + 1] : v1[(c - 4) * 8 + 2 * u + 1];
+      const uint32_t hi = cvt_f16x2_rn(x0, x1);
+      if (lo_plane) {
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+        w[u] = cvt_f16x2_rn(x0 - hf.x, x1 - hf.y);
+      } else {
+        w[u] = hi;
       }
     }
+    *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
+}
+__device__ __forceinline__ void stage_row_f32(uint8_t* stg, int lane, const float (&v)[32]) {
+  uint8_t* row = stg + lane * 128;
+  const int sw = lane & 7;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(row + ((c ^ sw) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo,
+               const __grid_constant__ CUtensorMap tmRes, const GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
   uint8_t* smA = smem;
   uint8_t* smB = smem + OFF_B;
+  uint8_t* smStg = smem + OFF_STG;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
@@ -220,32 +223,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v1[j] = b * c + a * s;
           }
         }
-        if (row_ok) {
-          if (p.epi == 2) {
-            float* dst = p.resid + row * p.ldr + gcol;
-            if (gcol + 64 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-              float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 x = d4[j];
-                x.x += v0[4 * j]; x.y += v0[4 * j + 1]; x.z += v0[4 * j + 2]; x.w += v0[4 * j + 3];
-                d4[j] = x;
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 x = d4[8 + j];
-                x.x += v1[4 * j]; x.y += v1[4 * j + 1]; x.z += v1[4 * j + 2]; x.w += v1[4 * j + 3];
-                d4[8 + j] = x;
-              }
-            } else {
-              for (int j = 0; j < 32; ++j) {
-                if (gcol + j < p.N) dst[j] += v0[j];
-                if (gcol + 32 + j < p.N) dst[32 + j] += v1[j];
-              }
+        uint8_t* stg = smStg + (warp - FIRST_EPI_WARP) * STG_BYTES;
+        const int grow0 = m_blk * BM + q * 32;
+        if (p.epi == 2) {
+#pragma unroll 1
+          for (int hh = 0; hh < 2; ++hh) {
+            if (gcol + hh * 32 >= p.N) break;
+            if (hh == 0) stage_row_f32(stg, lane, v0); else stage_row_f32(stg, lane, v1);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_2d(&tmRes, stg, gcol + hh * 32, grow0);
+              bulk_commit();
+              bulk_wait_read0();
             }
-          } else {
-            store_row_f16(v0, p.out, p.ldo, p.lo_off, row, gcol, p.N);
-            if (gcol + 32 < p.N) store_row_f16(v1, p.out, p.ldo, p.lo_off, row, gcol + 32, p.N);
+            __syncwarp();
+          }
+        } else {
+#pragma unroll 1
+          for (int pl = 0; pl < 2; ++pl) {
+            if (pl == 1 && p.lo_off <= 0) break;
+            stage_row_f16(stg, lane, v0, v1, pl == 1);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(pl ? &tmLo : &tmHi, stg, gcol, grow0);
+              bulk_commit();
+              bulk_wait_read0();
+            }
+            __syncwarp();
           }
         }
       }
@@ -255,6 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  if (warp >= FIRST_EPI_WARP && lane == 0) bulk_wait0();  // all bulk stores of this warp have landed
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
@@ -280,21 +287,25 @@ EncodeTiledFn get_encode_fn() {
 
 // 2D fp16 row-major tensor [rows, cols] with row pitch ld (elements); box = [box_rows, 64 cols], 128B swizzle,
 // out-of-bounds elements read as zero.
-int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                     uint32_t box_cols) {
+static int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                        uint32_t box_cols, int elem_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(PG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16)
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * elem_bytes) % 16)
     return set_error(PG_ERR_ARG, "TMA operand must be 16-byte aligned with a 16-byte-multiple row pitch");
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(PG_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(static_cast<int>(r)));
   return PG_OK;
+}
+int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols) {
+  return make_tmap_2d(m, ptr, rows, cols, ld, box_rows, box_cols, 2);
 }
 
 int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
@@ -315,6 +326,18 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   if (rc) return rc;
   rc = make_tmap_f16_2d(&tmB, g.w, g.N, width, g.ldw, BN, BK);
   if (rc) return rc;
+  CUtensorMap tmHi{}, tmLo{}, tmRes{};
+  if (g.epi == 2) {
+    rc = make_tmap_2d(&tmRes, g.resid, g.M, g.N, g.ldr, 32, 32, 4);
+    if (rc) return rc;
+  } else {
+    rc = make_tmap_2d(&tmHi, g.out, g.M, g.N, g.ldo, 32, 64, 2);
+    if (rc) return rc;
+    if (g.out_lo_off > 0) {
+      rc = make_tmap_2d(&tmLo, g.out + g.out_lo_off, g.M, g.N, g.ldo, 32, 64, 2);
+      if (rc) return rc;
+    }
+  }
   GemmKParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K; p.nseg = g.nseg;
   // segments: hi*hi, lo*hi, hi*lo
@@ -329,7 +352,7 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   p.tiles_n = (g.N + BN - 1) / BN;
   const int ntiles = p.tiles_m * p.tiles_n;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, p);
+  gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmHi, tmLo, tmRes, p);
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;
 }
