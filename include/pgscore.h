@@ -96,7 +96,8 @@ int pg_score_mutants(const float* table, int32_t n_rows, int32_t vocab, const in
  *   epi 1: same with exact-erf GELU (esm/modules.py:17-24)
  *   epi 2: resid[M, ldr] (fp32) += acc + bias
  *   epi 3: as 0, with rotary applied to the first 2*rot_dim columns ([q | k], heads of 64; esm/rotary_embedding.py:11-20),
- *          token index = row % rot_T, cos/sin tables [rot_T, 32] fp32 in rot_cos/rot_sin. */
+ *          token index = row % rot_T, cos/sin tables [rot_T, 32] fp32 in rot_cos/rot_sin.
+ *   epi 4: as 0 with squared ReLU relu(x)^2 (tranception/activations.py:79-84). bias may be NULL (no bias). */
 typedef struct {
   const void* a; int64_t lda;
   const void* w; int64_t ldw;

@@ -46,7 +46,24 @@ struct GemmKParams {
   int tiles_m, tiles_n;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-erf GELU (esm/modules.py:17-24): 0.5*x*(1+erf(x/sqrt2)) = 0.5*x + 0.5*|x|*erf(|x|/sqrt2).
+// erf via Abramowitz & Stegun 7.1.26 (abs error <= 1.5e-7; measured |gelu error| <= 4.7e-7, below torch's own fp32 gelu),
+// branch-free: MUFU.RCP + MUFU.EX2 + ~11 FMA-pipe ops instead of erff()'s two divergent code paths, so the fc1 epilogue
+// fits under the MMAs of the next tile even in single-pass mode.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, ax, 1.0f)));  // 1/(1 + 0.3275911*|x|/sqrt2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));  // exp(-x^2/2)
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  return fmaf(0.5f * ax, erf_abs, 0.5f * x);
+}
 
 // Epilogue staging: each warp owns a 32-row x 128-byte tile in shared memory laid out for a SWIZZLE_128B TMA store
 // (16-byte chunk c of row r lives at chunk c ^ (r & 7)), so the per-thread row writes are bank-conflict free and the
@@ -80,6 +97,7 @@ __device__ __forceinline__ void stage_row_f32(uint8_t* stg, int lane, const floa
     *reinterpret_cast<float4*>(row + ((c ^ sw) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
 
+template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo,
@@ -197,20 +215,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_32x32b_x32(taddr + 32, r1);
         tmem_ld_wait();
         float v0[32], v1[32];
+        if (p.bias != nullptr && gcol + 64 <= p.N) {  // fast path: 16 vector loads of the (warp-uniform) bias slice
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float b0 = (p.bias && gcol + j < p.N) ? __ldg(p.bias + gcol + j) : 0.f;
-          const float b1 = (p.bias && gcol + 32 + j < p.N) ? __ldg(p.bias + gcol + 32 + j) : 0.f;
-          v0[j] = __uint_as_float(r0[j]) + b0;
-          v1[j] = __uint_as_float(r1[j]) + b1;
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = __ldg(b4 + j), y = __ldg(b4 + 8 + j);
+            v0[4 * j] = __uint_as_float(r0[4 * j]) + x.x; v0[4 * j + 1] = __uint_as_float(r0[4 * j + 1]) + x.y;
+            v0[4 * j + 2] = __uint_as_float(r0[4 * j + 2]) + x.z; v0[4 * j + 3] = __uint_as_float(r0[4 * j + 3]) + x.w;
+            v1[4 * j] = __uint_as_float(r1[4 * j]) + y.x; v1[4 * j + 1] = __uint_as_float(r1[4 * j + 1]) + y.y;
+            v1[4 * j + 2] = __uint_as_float(r1[4 * j + 2]) + y.z; v1[4 * j + 3] = __uint_as_float(r1[4 * j + 3]) + y.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float b0 = (p.bias && gcol + j < p.N) ? __ldg(p.bias + gcol + j) : 0.f;
+            const float b1 = (p.bias && gcol + 32 + j < p.N) ? __ldg(p.bias + gcol + 32 + j) : 0.f;
+            v0[j] = __uint_as_float(r0[j]) + b0;
+            v1[j] = __uint_as_float(r1[j]) + b1;
+          }
         }
-        if (p.epi == 1) {
+        if (EPI == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             v0[j] = gelu_erf(v0[j]);
             v1[j] = gelu_erf(v1[j]);
           }
-        } else if (p.epi == 3 && gcol < 2 * p.rot_dim) {
+        } else if (EPI == 4) {  // squared ReLU (Tranception MLP, tranception/activations.py:79-84)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = fmaxf(v0[j], 0.f), b = fmaxf(v1[j], 0.f);
+            v0[j] = a * a;
+            v1[j] = b * b;
+          }
+        } else if (EPI == 3 && gcol < 2 * p.rot_dim) {
           // rotary: x*cos + rotate_half(x)*sin over one 64-wide head; cos/sin[t, j] for j in [0,32) (both halves equal)
           const int t = static_cast<int>(row % p.rot_T);
           const float* cs = p.rot_cos + static_cast<long long>(t) * 32;
@@ -225,33 +262,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         uint8_t* stg = smStg + (warp - FIRST_EPI_WARP) * STG_BYTES;
         const int grow0 = m_blk * BM + q * 32;
-        if (p.epi == 2) {
+        if (EPI == 2) {
 #pragma unroll 1
           for (int hh = 0; hh < 2; ++hh) {
             if (gcol + hh * 32 >= p.N) break;
+            if (lane == 0) bulk_wait_read0();  // the previous bulk store has finished reading this warp's staging tile
+            __syncwarp();
             if (hh == 0) stage_row_f32(stg, lane, v0); else stage_row_f32(stg, lane, v1);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
               tma_reduce_add_2d(&tmRes, stg, gcol + hh * 32, grow0);
               bulk_commit();
-              bulk_wait_read0();
             }
-            __syncwarp();
           }
         } else {
 #pragma unroll 1
           for (int pl = 0; pl < 2; ++pl) {
             if (pl == 1 && p.lo_off <= 0) break;
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
             stage_row_f16(stg, lane, v0, v1, pl == 1);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(pl ? &tmLo : &tmHi, stg, gcol, grow0);
+              if (pl) tma_store_2d(&tmLo, stg, gcol, grow0);
+              else tma_store_2d(&tmHi, stg, gcol, grow0);
               bulk_commit();
-              bulk_wait_read0();
             }
-            __syncwarp();
           }
         }
       }
@@ -312,12 +350,16 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(PG_ERR_ARG, "gemm: empty problem");
   if (g.K % BK) return set_error(PG_ERR_ARG, "gemm: K must be a multiple of 64");
   if (g.nseg != 1 && g.nseg != 3) return set_error(PG_ERR_ARG, "gemm: nseg must be 1 or 3");
-  if (g.epi < 0 || g.epi > 3) return set_error(PG_ERR_ARG, "gemm: bad epilogue");
+  if (g.epi < 0 || g.epi > 4) return set_error(PG_ERR_ARG, "gemm: bad epilogue");
   if (g.epi == 2 ? !g.resid : !g.out) return set_error(PG_ERR_ARG, "gemm: missing output");
   if (g.epi == 3 && (!g.rot_cos || !g.rot_sin || g.rot_T <= 0 || g.rot_dim % 64)) return set_error(PG_ERR_ARG, "gemm: bad rotary args");
   static bool attr_set = false;
   if (!attr_set) {
-    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     attr_set = true;
   }
   const uint64_t width = static_cast<uint64_t>(g.K) * (g.nseg == 3 ? 2 : 1);
@@ -352,7 +394,13 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   p.tiles_n = (g.N + BN - 1) / BN;
   const int ntiles = p.tiles_m * p.tiles_n;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  gemm_tc_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmHi, tmLo, tmRes, p);
+  switch (g.epi) {
+    case 0: gemm_tc_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmHi, tmLo, tmRes, p); break;
+    case 1: gemm_tc_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmHi, tmLo, tmRes, p); break;
+    case 2: gemm_tc_kernel<2><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmHi, tmLo, tmRes, p); break;
+    case 3: gemm_tc_kernel<3><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmHi, tmLo, tmRes, p); break;
+    default: gemm_tc_kernel<4><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmHi, tmLo, tmRes, p); break;
+  }
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;
 }

@@ -65,19 +65,21 @@ def stage_gemm_x3():
 def stage_gemm_big():
     from proteingym_b200 import _lib
     lib = _lib.load()
-    for (M, N, K, nseg) in ((32768, 3840, 1280, 1), (32768, 5120, 1280, 1), (32768, 1280, 5120, 1), (32768, 3840, 1280, 3)):
+    for (M, N, K, nseg, epi) in ((65536, 3840, 1280, 1, 0), (65536, 5120, 1280, 1, 1), (65536, 1280, 5120, 1, 2), (65536, 1280, 1280, 1, 2), (65536, 3840, 1280, 3, 0), (65536, 5120, 1280, 3, 1), (65536, 1280, 5120, 3, 2)):
         np_ = 2 if nseg == 3 else 1
         a = torch.randn(M, K * np_, device="cuda").half(); w = torch.randn(N, K * np_, device="cuda").half(); b = torch.zeros(N, device="cuda")
         out = torch.empty(M, N * np_, device="cuda", dtype=torch.float16)
         args = _lib.PgGemmArgs(); args.a = a.data_ptr(); args.lda = K * np_; args.w = w.data_ptr(); args.ldw = K * np_; args.bias = b.data_ptr()
-        args.M, args.N, args.K, args.nseg, args.epi = M, N, K, nseg, 0; args.out_h = out.data_ptr(); args.ldo = N * np_; args.out_lo_off = N if nseg == 3 else 0
+        args.M, args.N, args.K, args.nseg, args.epi = M, N, K, nseg, epi; args.out_h = out.data_ptr(); args.ldo = N * np_; args.out_lo_off = N if nseg == 3 else 0
+        if epi == 2:
+            res = torch.zeros(M, N, device="cuda"); args.resid = res.data_ptr(); args.ldr = N
         for _ in range(3): lib.pg_gemm(C.byref(args), None)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); e0.record()
         for _ in range(10): lib.pg_gemm(C.byref(args), None)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        print(f"  gemm {M}x{N}x{K} nseg={nseg}: {ms:.3f} ms  {2*M*N*K*nseg/ms/1e9:.1f} TFLOP/s")
+        print(f"  gemm {M}x{N}x{K} nseg={nseg} epi={epi}: {ms:.3f} ms  {2*M*N*K*nseg/ms/1e9:.1f} TFLOP/s issued")
         a16 = a[:, :K]; w16 = w[:, :K]
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         for _ in range(3): torch.matmul(a16, w16.T)
