@@ -197,3 +197,81 @@ def write_mapping_csv(path: str, rows):
                        "target_seq": [r[2] for r in rows]})
     df.to_csv(path, index=False)
     return df
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Tranception (reference: proteingym/baselines/tranception/tranception/model_pytorch.py, config.py)
+@dataclass
+class TranceptionArch:
+    layers: int
+    embed_dim: int
+    heads: int          # multiple of 4 (grouped ALiBi / depthwise-conv head groups, model_pytorch.py:129-131)
+    ffn_dim: int        # n_inner (None in config.json means 4 * n_embd, model_pytorch.py:284)
+    n_ctx: int = 1024
+    vocab: int = 25
+    ln_eps: float = 1e-5
+
+
+TRANCEPTION_L = TranceptionArch(36, 1280, 20, 5120)
+
+
+def make_tranception_state(arch: TranceptionArch, seed: int = 0, qk_gain: float = 3.0) -> dict:
+    """HF-style state dict keys of ``TranceptionLMHeadModel`` (GPT2 naming; Conv1D weights are [in, out])."""
+    g = torch.Generator().manual_seed(seed)
+    d, f, V, hd = arch.embed_dim, arch.ffn_dim, arch.vocab, arch.embed_dim // arch.heads
+    st = {"transformer.wte.weight": 0.1 * torch.randn((V, d), generator=g)}
+    for i in range(arch.layers):
+        p = f"transformer.h.{i}."
+        st[p + "ln_1.weight"] = 1 + 0.1 * torch.randn(d, generator=g)
+        st[p + "ln_1.bias"] = 0.05 * torch.randn(d, generator=g)
+        w = torch.randn((d, 3 * d), generator=g) / math.sqrt(d)
+        w[:, :2 * d] *= qk_gain / 2
+        st[p + "attn.c_attn.weight"] = w
+        st[p + "attn.c_attn.bias"] = 0.1 * torch.randn(3 * d, generator=g)
+        st[p + "attn.c_proj.weight"] = torch.randn((d, d), generator=g) / math.sqrt(d)
+        st[p + "attn.c_proj.bias"] = 0.05 * torch.randn(d, generator=g)
+        for nm in ("query", "key", "value"):
+            for ki, k in enumerate((3, 5, 7)):
+                st[p + f"attn.{nm}_depthwiseconv.{ki}.conv.weight"] = torch.randn((hd, 1, k), generator=g) / math.sqrt(k)
+                st[p + f"attn.{nm}_depthwiseconv.{ki}.conv.bias"] = 0.1 * torch.randn(hd, generator=g)
+        st[p + "ln_2.weight"] = 1 + 0.1 * torch.randn(d, generator=g)
+        st[p + "ln_2.bias"] = 0.05 * torch.randn(d, generator=g)
+        st[p + "mlp.c_fc.weight"] = torch.randn((d, f), generator=g) / math.sqrt(d)
+        st[p + "mlp.c_fc.bias"] = 0.1 * torch.randn(f, generator=g)
+        st[p + "mlp.c_proj.weight"] = torch.randn((f, d), generator=g) / math.sqrt(f) * 0.5
+        st[p + "mlp.c_proj.bias"] = 0.05 * torch.randn(d, generator=g)
+    st["transformer.ln_f.weight"] = 1 + 0.1 * torch.randn(d, generator=g)
+    st["transformer.ln_f.bias"] = 0.05 * torch.randn(d, generator=g)
+    st["lm_head.weight"] = st["transformer.wte.weight"]  # tied (GPT2 ties input and output embeddings)
+    return st
+
+
+def write_tranception_checkpoint(folder: str, arch: TranceptionArch, seed: int = 0, state: dict | None = None) -> dict:
+    """HF checkpoint directory: config.json + pytorch_model.bin (what score_tranception_proteingym.py:79,100 reads)."""
+    import json
+    os.makedirs(folder, exist_ok=True)
+    st = state if state is not None else make_tranception_state(arch, seed)
+    cfg = {"n_embd": arch.embed_dim, "n_head": arch.heads, "n_layer": arch.layers, "n_ctx": arch.n_ctx, "n_positions": arch.n_ctx,
+           "n_inner": arch.ffn_dim, "vocab_size": arch.vocab, "layer_norm_epsilon": arch.ln_eps, "activation_function": "squared_relu",
+           "attention_mode": "tranception", "position_embedding": "grouped_alibi", "scale_attn_weights": True,
+           "architectures": ["TranceptionLMHeadModel"], "model_type": "tranception"}
+    with open(os.path.join(folder, "config.json"), "w") as fh:
+        json.dump(cfg, fh, indent=1)
+    torch.save(st, os.path.join(folder, "pytorch_model.bin"))
+    return st
+
+
+def random_indels(seq: str, n: int, seed: int, max_len: int = 4):
+    """Synthetic indel variants of ``seq`` (full mutated sequences, as the DMS_indels files list them)."""
+    rng = np.random.RandomState(seed)
+    out = set()
+    while len(out) < n:
+        pos = rng.randint(0, len(seq))
+        k = rng.randint(1, max_len + 1)
+        if rng.rand() < 0.5:
+            s = seq[:pos] + "".join(AA20[i] for i in rng.randint(0, 20, size=k)) + seq[pos:]
+        else:
+            s = seq[:pos] + seq[pos + k:]
+        if s != seq and len(s) > 2:
+            out.add(s)
+    return sorted(out)

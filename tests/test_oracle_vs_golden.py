@@ -1,6 +1,7 @@
 """CPU: the oracle restatement (oracle/esm_oracle.py) against golden vectors produced by the UNMODIFIED reference
 (oracle/gen_golden.py ran /root/reference's compute_fitness.main + fair-esm modules on the same seeded checkpoints)."""
 import numpy as np
+import pandas as pd
 import pytest
 import torch
 
@@ -69,3 +70,45 @@ def test_oracle_fp64_agrees_with_fp32():
     t64 = O.masked_marginal_table(O.load_state(g["state"](), "esm2", torch.float64), seq, "esm2", arch.layers, arch.heads,
                                   dtype=torch.float64, positions=range(1, 20))
     assert (t32[1:20].double() - t64[1:20]).abs().max() < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ Tranception
+def _load_tranception(name):
+    import json, os
+    import pandas as pd
+    from conftest import GOLDEN
+    from proteingym_b200 import synth
+    meta = json.load(open(os.path.join(GOLDEN, f"{name}_meta.json")))
+    arch = synth.TranceptionArch(**meta["arch"])
+    return dict(meta=meta, arch=arch, state=synth.make_tranception_state(arch, meta["seed"]),
+                dms=pd.read_csv(os.path.join(GOLDEN, f"{name}_dms.csv")),
+                scores=pd.read_csv(os.path.join(GOLDEN, f"{name}_reference_scores.csv")),
+                logits=np.load(os.path.join(GOLDEN, f"{name}_padded_batch_logits.npy")))
+
+
+@pytest.mark.parametrize("name", ["tranception_subs", "tranception_indels", "tranception_long"])
+def test_tranception_oracle_matches_reference_hybrid(name):
+    from oracle import tranception_oracle as TO
+    g = _load_tranception(name)
+    arch, seq = g["arch"], g["meta"]["target_seq"]
+    # forward: the reference scored a right-padded batch of two sequences; unpadded evaluation must agree on real tokens
+    for row, s in enumerate((seq[:min(len(seq), 60)], seq[:23])):
+        ids = torch.tensor([TO.tokenize(s)])
+        lg = TO.forward(g["state"], ids, arch.layers, arch.heads, arch.ln_eps)[0].numpy()
+        assert np.abs(lg - g["logits"][row, :len(s) + 2]).max() < 2e-4
+    got = TO.score_mutants(g["state"], g["dms"], seq, arch.layers, arch.heads, arch.n_ctx, indel_mode=g["meta"]["indel_mode"],
+                           scoring_window=g["meta"]["scoring_window"])
+    ref = g["scores"]
+    assert list(got.columns) == list(ref.columns) and len(got) == len(ref)
+    key = got.columns[0] if got.columns[0] in ("mutated_sequence", "mutant") else "mutated_sequence"
+    m = pd.merge(ref, got, on="mutated_sequence", suffixes=("_ref", "")) if "mutated_sequence" in ref else None
+    for c in ("avg_score_L_to_R", "avg_score_R_to_L", "avg_score"):
+        a = ref[c].to_numpy(dtype=np.float64)
+        b = got[c].to_numpy(dtype=np.float64)
+        assert np.abs(a - b).max() < 2e-5, c  # same row order as the reference
+
+
+def test_tranception_slopes_match_reference_list():
+    from oracle import tranception_oracle as TO
+    assert TO.get_slopes(20) == [0.25, 0.0625, 0.015625, 0.00390625, 0.5] * 4  # SURVEY.md hard-parts note; model_pytorch.py:59-71
+    assert len(TO.get_slopes(12)) == 12 and TO.get_slopes(4) == [2 ** -8] * 4
