@@ -24,7 +24,9 @@ enum pg_status { PG_OK = 0, PG_ERR_ARG = 1, PG_ERR_CUDA = 2, PG_ERR_STATE = 3, P
 
 enum pg_arch {
   PG_ARCH_ESM1B = 0, /* ESM-1b / ESM-1v: learned positions (esm/model/esm1.py:83-102) */
-  PG_ARCH_ESM2 = 1   /* ESM2: rotary (esm/model/esm2.py:40-74) */
+  PG_ARCH_ESM2 = 1,  /* ESM2: rotary (esm/model/esm2.py:40-74) */
+  PG_ARCH_TRANCEPTION = 2 /* Tranception decoder: grouped ALiBi, depthwise-conv q/k/v, relu^2 MLP
+                             (tranception/model_pytorch.py:90-632); max_positions = n_ctx, vocab = 25 */
 };
 
 /* Tensor-core operand precision. The reference is strict fp32.
@@ -80,6 +82,18 @@ int pg_masked_marginals(pg_handle h, const int32_t* tokens, int32_t n_tokens, co
  * `T` tokens starting at `win_start`, emitting log_softmax for every token: out [T, vocab]. mask_pos = -1 for none. */
 int pg_forward_logprobs(pg_handle h, const int32_t* tokens, int32_t n_tokens, int32_t win_start, int32_t T,
                         int32_t mask_pos, float* out_logprobs, pg_stream stream);
+
+/* Replaces one batch of get_tranception_scores_mutated_sequences (tranception/utils/scoring_utils.py:97-128): forward of B
+ * right-padded sequences + shifted token log-likelihood summed over the real tokens of each sequence.
+ *   ids   [B, T] int32 (device): [CLS] seq [SEP] then [PAD]; lens [B]: number of real tokens (len(seq) + 2)
+ *   log_prior [Lp, vocab] fp32 + prior_row [B, T] int32 (device) or both NULL: retrieval fusion of
+ *             model_pytorch.py:806-830 — for row (b, t) with prior_row >= 0 the predicted distribution becomes
+ *             (1 - alpha) * log_softmax + alpha * log_prior[prior_row]  (the host computes the slice/flip index arithmetic)
+ *   out_sum_logp [B] fp32: sum_{t < len-1} log p(ids[b, t+1] | ids[b, <= t])
+ * Weights for a PG_ARCH_TRANCEPTION handle use the HF names without the "transformer." prefix (Conv1D weights [in, out]),
+ * plus "h.{i}.attn.conv_taps" [768, 8] (look-back taps + bias per q/k/v, head group, channel) and "alibi_slopes" [heads, 1]. */
+int pg_ar_loglik(pg_handle h, const int32_t* ids, const int32_t* lens, int32_t B, int32_t T, const float* log_prior,
+                 const int32_t* prior_row, float alpha, float* out_sum_logp, pg_stream stream);
 
 /* Replaces label_row over the whole DMS frame (compute_fitness.py:240-250, :505-514):
  *   score[m] = sum_{s in [row_offsets[m], row_offsets[m+1])} table[site_row[s], site_mt[s]] - table[site_row[s], site_wt[s]]

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpgscore.so")
 
-PG_ARCH_ESM1B, PG_ARCH_ESM2 = 0, 1
+PG_ARCH_ESM1B, PG_ARCH_ESM2, PG_ARCH_TRANCEPTION = 0, 1, 2
 PG_PREC_F16, PG_PREC_F16X3 = 0, 1
 
 
@@ -49,6 +49,8 @@ SIGNATURES = {
                                       C.c_void_p]),
     "pg_score_mutants": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int32, C.c_void_p, C.c_void_p]),
+    "pg_ar_loglik": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
+                               C.c_void_p]),
     "pg_gemm": (C.c_int, [C.POINTER(PgGemmArgs), C.c_void_p]),
     "pg_layernorm_f16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_int64, C.c_int64, C.c_void_p]),

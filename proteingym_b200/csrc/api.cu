@@ -84,6 +84,16 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int N, int K, fl
   out[static_cast<long long>(n) * K * np + k] = hi;
   if (np == 2) out[static_cast<long long>(n) * K * np + K + k] = lo;
 }
+// Conv1D weights are stored [in = K, out = N] (x @ W); repack to the K-major [N, np*K] operand layout.
+__global__ void pack_weight_t_kernel(const float* __restrict__ w, int N, int K, __half* __restrict__ out, int np) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(N) * K) return;
+  const int n = static_cast<int>(i / K), k = static_cast<int>(i % K);
+  __half hi, lo;
+  split_hi_lo(w[static_cast<long long>(k) * N + n], hi, lo);
+  out[static_cast<long long>(n) * K * np + k] = hi;
+  if (np == 2) out[static_cast<long long>(n) * K * np + K + k] = lo;
+}
 __global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, float scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i] * scale;
@@ -93,6 +103,7 @@ struct Layer {
   __half *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
   float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
   float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+  float* conv_taps = nullptr;  // Tranception: [3][4][64][8]
 };
 
 }  // namespace
@@ -116,6 +127,9 @@ struct pg_handle_s {
   __half *abuf = nullptr, *qkv = nullptr, *fbuf = nullptr;
   float *hs_a = nullptr, *hs_b = nullptr;
   int32_t* row_sel = nullptr;  // [head_cap] token index within the window to emit
+  // Tranception
+  __half* qkv2 = nullptr;
+  float *tok_logp = nullptr, *slopes = nullptr;
 };
 
 namespace pg {
@@ -198,6 +212,55 @@ int forward_rows(pg_handle h, const int32_t* tokens, int n_tokens, const int32_t
   return PG_OK;
 }
 
+// Tranception decoder stack over B right-padded sequences of T tokens (model_pytorch.py:526-612): no padding mask is needed
+// because pads sit to the right of every real token and attention is causal.
+int forward_tranception(pg_handle h, const int32_t* ids, int B, int T, cudaStream_t s) {
+  const pg_model_desc& D = h->desc;
+  const int d = D.embed_dim, f = D.ffn_dim, np = h->np, nseg = (np == 2) ? 3 : 1;
+  const int rows = B * T;
+  int rc;
+  { ProfScope ps(CAT_EMBED, s); rc = launch_gather_embed(ids, h->embed, rows, d, D.vocab, h->x, s); }
+  if (rc) return rc;
+  for (int l = 0; l < D.layers; ++l) {
+    const Layer& L = h->layers[l];
+    { ProfScope ps(CAT_LN, s); rc = launch_layernorm_f16(h->x, d, L.ln1g, L.ln1b, rows, d, h->abuf, static_cast<int64_t>(d) * np, np == 2 ? d : 0, s); }
+    if (rc) return rc;
+    GemmLaunch g{};
+    g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.wqkv; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.bqkv;
+    g.M = rows; g.N = 3 * d; g.K = d; g.nseg = nseg; g.epi = 0;
+    g.out = h->qkv; g.ldo = static_cast<int64_t>(3 * d) * np; g.out_lo_off = np == 2 ? 3 * d : 0;
+    { ProfScope ps(CAT_GEMM_QKV, s); rc = launch_gemm(g, s); }
+    if (rc) return rc;
+    { ProfScope ps(CAT_OTHER, s); rc = launch_qkv_conv(h->qkv, h->qkv2, static_cast<int64_t>(3 * d) * np, np == 2 ? 3 * d : 0, B, T, D.heads, L.conv_taps, 0.125f, s); }
+    if (rc) return rc;
+    AttnLaunch a{};
+    a.qkv = h->qkv2; a.ld = static_cast<int64_t>(3 * d) * np; a.lo_off = np == 2 ? 3 * d : 0;
+    a.out = h->abuf; a.ldo = static_cast<int64_t>(d) * np; a.out_lo_off = np == 2 ? d : 0;
+    a.B = B; a.T = T; a.heads = D.heads; a.nseg = nseg; a.causal = 1; a.alibi_slopes = h->slopes;
+    { ProfScope ps(CAT_ATTN, s); rc = launch_attention(a, s); }
+    if (rc) return rc;
+    g = GemmLaunch{};
+    g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.wo; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.bo;
+    g.M = rows; g.N = d; g.K = d; g.nseg = nseg; g.epi = 2; g.resid = h->x; g.ldr = d;
+    { ProfScope ps(CAT_GEMM_OUT, s); rc = launch_gemm(g, s); }
+    if (rc) return rc;
+    { ProfScope ps(CAT_LN, s); rc = launch_layernorm_f16(h->x, d, L.ln2g, L.ln2b, rows, d, h->abuf, static_cast<int64_t>(d) * np, np == 2 ? d : 0, s); }
+    if (rc) return rc;
+    g = GemmLaunch{};
+    g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.w1; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.b1;
+    g.M = rows; g.N = f; g.K = d; g.nseg = nseg; g.epi = 4;
+    g.out = h->fbuf; g.ldo = static_cast<int64_t>(f) * np; g.out_lo_off = np == 2 ? f : 0;
+    { ProfScope ps(CAT_GEMM_FC1, s); rc = launch_gemm(g, s); }
+    if (rc) return rc;
+    g = GemmLaunch{};
+    g.a = h->fbuf; g.lda = static_cast<int64_t>(f) * np; g.w = L.w2; g.ldw = static_cast<int64_t>(f) * np; g.bias = L.b2;
+    g.M = rows; g.N = d; g.K = f; g.nseg = nseg; g.epi = 2; g.resid = h->x; g.ldr = d;
+    { ProfScope ps(CAT_GEMM_FC2, s); rc = launch_gemm(g, s); }
+    if (rc) return rc;
+  }
+  return PG_OK;
+}
+
 HeadLaunch head_args(pg_handle h, int T) {
   HeadLaunch hl{};
   hl.x = h->x; hl.d = h->desc.embed_dim; hl.T = T;
@@ -259,7 +322,8 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
     return set_error(PG_ERR_ARG, "pg_create: non-positive model dimension");
   if (D.embed_dim != D.heads * 64) return set_error(PG_ERR_UNSUPPORTED, "pg_create: head_dim must be 64");
   if (D.embed_dim % 64 || D.ffn_dim % 64) return set_error(PG_ERR_UNSUPPORTED, "pg_create: embed_dim and ffn_dim must be multiples of 64");
-  if (D.arch != PG_ARCH_ESM1B && D.arch != PG_ARCH_ESM2) return set_error(PG_ERR_UNSUPPORTED, "pg_create: unknown arch");
+  if (D.arch != PG_ARCH_ESM1B && D.arch != PG_ARCH_ESM2 && D.arch != PG_ARCH_TRANCEPTION) return set_error(PG_ERR_UNSUPPORTED, "pg_create: unknown arch");
+  if (D.arch == PG_ARCH_TRANCEPTION && D.heads % 4) return set_error(PG_ERR_UNSUPPORTED, "pg_create: Tranception needs heads % 4 == 0 (model_pytorch.py:129-131)");
   if (D.precision != PG_PREC_F16 && D.precision != PG_PREC_F16X3) return set_error(PG_ERR_ARG, "pg_create: unknown precision");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return set_error(PG_ERR_CUDA, "pg_create: no CUDA device (the B200 path has no CPU fallback)");
@@ -282,6 +346,12 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
     A(&L.w1, static_cast<size_t>(f) * d * np); A(&L.w2, static_cast<size_t>(d) * f * np);
     A(&L.bqkv, 3 * d); A(&L.bo, d); A(&L.b1, f); A(&L.b2, d);
     A(&L.ln1g, d); A(&L.ln1b, d); A(&L.ln2g, d); A(&L.ln2b, d);
+    if (D.arch == PG_ARCH_TRANCEPTION) A(&L.conv_taps, 3 * 4 * 64 * 8);
+  }
+  if (D.arch == PG_ARCH_TRANCEPTION) {
+    A(&h->qkv2, static_cast<size_t>(h->max_rows) * 3 * d * np);
+    A(&h->tok_logp, static_cast<size_t>(h->max_rows));
+    A(&h->slopes, D.heads);
   }
   A(&h->embed, static_cast<size_t>(D.vocab) * d);
   if (D.arch == PG_ARCH_ESM1B) A(&h->pos, static_cast<size_t>(D.max_positions + 2) * d);
@@ -334,6 +404,40 @@ int pg_load_weights(pg_handle h, const pg_tensor* tensors, int32_t n) {
     const long long tot = static_cast<long long>(N) * K;
     pack_weight_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256>>>(src, N, K, scale, dst, np);
   };
+  auto pack_t = [&](__half* dst, const float* src, int N, int K) {
+    if (!src) return;
+    const long long tot = static_cast<long long>(N) * K;
+    pack_weight_t_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256>>>(src, N, K, dst, np);
+  };
+  if (D.arch == PG_ARCH_TRANCEPTION) {
+    // HF GPT2-style names with the "transformer." prefix stripped by the host; Conv1D weights are [in, out].
+    for (int l = 0; l < D.layers; ++l) {
+      Layer& L = h->layers[l];
+      const std::string p = "h." + std::to_string(l) + ".";
+      pack_t(L.wqkv, get(p + "attn.c_attn.weight", d, 3 * d), 3 * d, d);
+      copy(L.bqkv, get(p + "attn.c_attn.bias", 3 * d, 1), 3 * d);
+      pack_t(L.wo, get(p + "attn.c_proj.weight", d, d), d, d);
+      copy(L.bo, get(p + "attn.c_proj.bias", d, 1), d);
+      pack_t(L.w1, get(p + "mlp.c_fc.weight", d, f), f, d);
+      copy(L.b1, get(p + "mlp.c_fc.bias", f, 1), f);
+      pack_t(L.w2, get(p + "mlp.c_proj.weight", f, d), d, f);
+      copy(L.b2, get(p + "mlp.c_proj.bias", d, 1), d);
+      copy(L.ln1g, get(p + "ln_1.weight", d, 1), d);
+      copy(L.ln1b, get(p + "ln_1.bias", d, 1), d);
+      copy(L.ln2g, get(p + "ln_2.weight", d, 1), d);
+      copy(L.ln2b, get(p + "ln_2.bias", d, 1), d);
+      copy(L.conv_taps, get(p + "attn.conv_taps", 3 * 4 * 64, 8), 3 * 4 * 64 * 8);
+    }
+    copy(h->embed, get("wte.weight", D.vocab, d), static_cast<size_t>(D.vocab) * d);
+    copy(h->lnag, get("ln_f.weight", d, 1), d);
+    copy(h->lnab, get("ln_f.bias", d, 1), d);
+    copy(h->slopes, get("alibi_slopes", D.heads, 1), D.heads);
+    if (!missing.empty()) return fail(h, PG_ERR_ARG, "pg_load_weights: missing or mis-shaped tensors: " + missing);
+    PG_CUDA_OK(cudaGetLastError());
+    PG_CUDA_OK(cudaDeviceSynchronize());
+    h->loaded = true;
+    return PG_OK;
+  }
   const float qscale = 0.125f;  // head_dim^-1/2 with head_dim == 64 (multihead_attention.py:103,261); exact power of two
   for (int l = 0; l < D.layers; ++l) {
     Layer& L = h->layers[l];
@@ -395,6 +499,7 @@ int pg_masked_marginals(pg_handle h, const int32_t* tokens, int32_t n_tokens, co
                         const int32_t* out_row, int32_t P, int32_t T, float* out_logprobs, pg_stream stream) {
   if (!h) return set_error(PG_ERR_ARG, "pg_masked_marginals: null handle");
   if (!h->loaded) return fail(h, PG_ERR_STATE, "pg_masked_marginals: weights not loaded");
+  if (h->desc.arch == PG_ARCH_TRANCEPTION) return fail(h, PG_ERR_STATE, "pg_masked_marginals: handle is a Tranception model (use pg_ar_loglik)");
   if (!tokens || !positions || !out_logprobs) return fail(h, PG_ERR_ARG, "pg_masked_marginals: null buffer");
   if (P < 0 || T <= 0 || T > n_tokens) return fail(h, PG_ERR_ARG, "pg_masked_marginals: bad P/T");
   if (h->desc.arch == PG_ARCH_ESM1B && T > h->desc.max_positions)
@@ -424,6 +529,7 @@ int pg_forward_logprobs(pg_handle h, const int32_t* tokens, int32_t n_tokens, in
                         float* out_logprobs, pg_stream stream) {
   if (!h) return set_error(PG_ERR_ARG, "pg_forward_logprobs: null handle");
   if (!h->loaded) return fail(h, PG_ERR_STATE, "pg_forward_logprobs: weights not loaded");
+  if (h->desc.arch == PG_ARCH_TRANCEPTION) return fail(h, PG_ERR_STATE, "pg_forward_logprobs: handle is a Tranception model (use pg_ar_loglik)");
   if (!tokens || !out_logprobs || T <= 0 || win_start < 0 || win_start + T > n_tokens) return fail(h, PG_ERR_ARG, "pg_forward_logprobs: bad arguments");
   if (h->desc.arch == PG_ARCH_ESM1B && T > h->desc.max_positions) return fail(h, PG_ERR_ARG, "pg_forward_logprobs: sequence longer than the learned position table");
   if (h->desc.arch == PG_ARCH_ESM2 && T > h->rot_rows) return fail(h, PG_ERR_ARG, "pg_forward_logprobs: sequence longer than rotary tables");
@@ -441,6 +547,33 @@ int pg_forward_logprobs(pg_handle h, const int32_t* tokens, int32_t n_tokens, in
     hl.P = (T - r0) < h->head_cap ? (T - r0) : h->head_cap; hl.all_rows = 1;
     hl.out = out_logprobs + static_cast<long long>(r0) * h->desc.vocab;
     { ProfScope ps(CAT_HEAD, s, 3); rc = launch_head(hl, s); }
+    if (rc) return fail(h, rc, tls_error());
+  }
+  return PG_OK;
+}
+
+int pg_ar_loglik(pg_handle h, const int32_t* ids, const int32_t* lens, int32_t B, int32_t T, const float* log_prior,
+                 const int32_t* prior_row, float alpha, float* out_sum_logp, pg_stream stream) {
+  if (!h) return set_error(PG_ERR_ARG, "pg_ar_loglik: null handle");
+  if (!h->loaded) return fail(h, PG_ERR_STATE, "pg_ar_loglik: weights not loaded");
+  if (h->desc.arch != PG_ARCH_TRANCEPTION) return fail(h, PG_ERR_STATE, "pg_ar_loglik: handle is not a Tranception model");
+  if (B < 0 || T <= 0) return fail(h, PG_ERR_ARG, "pg_ar_loglik: bad B/T");
+  if (B == 0) return PG_OK;
+  if (!ids || !lens || !out_sum_logp) return fail(h, PG_ERR_ARG, "pg_ar_loglik: null buffer");
+  if ((log_prior == nullptr) != (prior_row == nullptr)) return fail(h, PG_ERR_ARG, "pg_ar_loglik: log_prior and prior_row go together");
+  if (T > h->desc.max_positions) return fail(h, PG_ERR_ARG, "pg_ar_loglik: sequence longer than n_ctx");
+  if (T > h->max_rows) return fail(h, PG_ERR_ARG, "pg_ar_loglik: sequence longer than workspace");
+  PG_CUDA_OK(cudaSetDevice(h->desc.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long per = h->max_rows / T;
+  for (int b0 = 0; b0 < B; b0 += static_cast<int>(per)) {
+    const int Bc = (B - b0) < per ? (B - b0) : static_cast<int>(per);
+    const int32_t* idc = ids + static_cast<long long>(b0) * T;
+    int rc = forward_tranception(h, idc, Bc, T, s);
+    if (rc) return fail(h, rc, tls_error());
+    ProfScope ps(CAT_HEAD, s, 2);
+    rc = launch_ar_head(h->x, h->desc.embed_dim, Bc, T, h->desc.vocab, idc, lens + b0, h->lnag, h->lnab, h->embed, log_prior,
+                        prior_row ? prior_row + static_cast<long long>(b0) * T : nullptr, alpha, h->tok_logp, out_sum_logp + b0, s);
     if (rc) return fail(h, rc, tls_error());
   }
   return PG_OK;

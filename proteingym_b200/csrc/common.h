@@ -96,3 +96,12 @@ int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
                      uint32_t box_cols);
 int launch_attention_tc(const AttnLaunch& a, cudaStream_t s);  // tcgen05/TMEM attention (non-causal, no ALiBi)
 }  // namespace pg
+
+namespace pg {
+int launch_gather_embed(const int32_t* ids, const float* wte, long long rows, int d, int vocab, float* x, cudaStream_t s);
+int launch_qkv_conv(const __half* in, __half* out, int64_t ld, int64_t lo_off, int B, int T, int heads, const float* taps,
+                    float qscale, cudaStream_t s);
+int launch_ar_head(const float* x, int d, int B, int T, int vocab, const int32_t* ids, const int32_t* lens, const float* lnf_g,
+                   const float* lnf_b, const float* wte, const float* log_prior, const int32_t* prior_row, float alpha,
+                   float* tok_logp, float* out_sum, cudaStream_t s);
+}  // namespace pg

@@ -1,0 +1,210 @@
+// Tranception-specific helper kernels (HBM-bound, fp32 arithmetic):
+//   gather_embed_kernel   x[row] = wte[ids[row]]                                   (model_pytorch.py:526-532, no position table)
+//   qkv_conv_kernel       depthwise causal conv (k = 1,3,5,7 by head group) on q, k and v + the 1/sqrt(hd) query scale
+//                         (model_pytorch.py:73-88, :240-251, :158-159)
+//   ar_head_kernel        ln_f -> tied lm_head (no bias) -> log_softmax -> optional retrieval-prior fusion -> log p(next token)
+//                         (model_pytorch.py:612, :783, :806-830; utils/scoring_utils.py:121-128)
+//   seq_sum_kernel        per-sequence sum over the real (non-pad) predicted tokens, fixed order
+#include "common.h"
+#include "ptx.cuh"
+
+namespace pg {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum_t(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_t(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float block_sum_t(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum_t(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) {
+    t = warp_sum_t(t);
+    if (lane == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+__global__ void gather_embed_kernel(const int32_t* __restrict__ ids, const float* __restrict__ wte, int d, int vocab,
+                                    float* __restrict__ x) {
+  const long long r = blockIdx.x;
+  int tok = ids[r];
+  tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+  const float4* src = reinterpret_cast<const float4*>(wte + static_cast<long long>(tok) * d);
+  float4* dst = reinterpret_cast<float4*>(x + r * d);
+  for (int j = threadIdx.x; j < d / 4; j += blockDim.x) dst[j] = src[j];
+}
+
+// One thread per (row, 8-channel chunk). taps: [3 (q,k,v)][4 groups][64 channels][8] = 7 look-back taps + bias.
+// in/out: [B*T, ld] fp16 with columns [q | k | v] (+ lo plane at lo_off). out[t] = bias + sum_o tap[o] * in[t - o].
+__global__ void qkv_conv_kernel(const __half* __restrict__ in, __half* __restrict__ out, long long ld, long long lo_off, int B, int T,
+                                int heads, const float* __restrict__ taps, float qscale) {
+  const int d = heads * 64;
+  const int chunks = 3 * d / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long long>(B) * T * chunks) return;
+  const int ck = static_cast<int>(gid % chunks);
+  const long long row = gid / chunks;
+  const int t = static_cast<int>(row % T);
+  const int c0 = ck * 8;
+  const int which = c0 / d, head = (c0 % d) / 64, ch0 = c0 % 64;
+  const int group = head / (heads / 4);
+  const float* tp = taps + ((static_cast<long long>(which) * 4 + group) * 64 + ch0) * 8;
+  const int klen = group == 0 ? 1 : 2 * group + 1;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = tp[i * 8 + 7];
+  for (int o = 0; o < klen && o <= t; ++o) {
+    const __half* src = in + (row - o) * ld + c0;
+    const uint4 hv = *reinterpret_cast<const uint4*>(src);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&hv);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h2[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+    if (lo_off > 0) {
+      const uint4 lv = *reinterpret_cast<const uint4*>(src + lo_off);
+      const __half2* l2 = reinterpret_cast<const __half2*>(&lv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(l2[i]);
+        v[2 * i] += f.x; v[2 * i + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(tp[i * 8 + o], v[i], acc[i]);
+  }
+  const float sc = which == 0 ? qscale : 1.f;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half h0, l0, h1, l1;
+    split_hi_lo(acc[2 * i] * sc, h0, l0);
+    split_hi_lo(acc[2 * i + 1] * sc, h1, l1);
+    hi[i] = pack_h2(h0, h1);
+    lo[i] = pack_h2(l0, l1);
+  }
+  __half* dst = out + row * ld + c0;
+  *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (lo_off > 0) *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+struct ArHeadParams {
+  const float* x; int d; int T; int vocab;
+  const int32_t* ids; const int32_t* lens;
+  const float* lnf_g; const float* lnf_b; const float* wte;
+  const float* log_prior; const int32_t* prior_row; float alpha;
+  float* tok_logp;  // [B*T]
+};
+
+// One block (128 threads) per token row r = (b, t): log p(ids[b, t+1] | ids[b, <=t]); 0 for t >= len-1.
+__global__ void ar_head_kernel(ArHeadParams p) {
+  __shared__ float sh[33];
+  extern __shared__ float dyn[];
+  float* y = dyn;
+  float* logits = dyn + p.d;
+  const long long r = blockIdx.x;
+  const int b = static_cast<int>(r / p.T), t = static_cast<int>(r % p.T);
+  const int len = p.lens[b];
+  if (t + 1 >= len) {  // block-uniform
+    if (threadIdx.x == 0) p.tok_logp[r] = 0.f;
+    return;
+  }
+  const float* xr = p.x + r * p.d;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < p.d; j += blockDim.x) s += xr[j];
+  const float mean = block_sum_t(s, sh) / p.d;
+  float ss = 0.f;
+  for (int j = threadIdx.x; j < p.d; j += blockDim.x) {
+    const float c = xr[j] - mean;
+    ss += c * c;
+  }
+  const float rstd = rsqrtf(block_sum_t(ss, sh) / p.d + 1e-5f);
+  for (int j = threadIdx.x; j < p.d; j += blockDim.x) y[j] = (xr[j] - mean) * rstd * p.lnf_g[j] + p.lnf_b[j];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int v = warp; v < p.vocab; v += nw) {
+    const float* wr = p.wte + static_cast<long long>(v) * p.d;
+    float acc = 0.f;
+    for (int j = lane; j < p.d; j += 32) acc = fmaf(y[j], wr[j], acc);
+    acc = warp_sum_t(acc);
+    if (lane == 0) logits[v] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float m = -INFINITY;
+    for (int v = lane; v < p.vocab; v += 32) m = fmaxf(m, logits[v]);
+    m = warp_max_t(m);
+    float se = 0.f;
+    for (int v = lane; v < p.vocab; v += 32) se += expf(logits[v] - m);
+    se = warp_sum_t(se);
+    if (lane == 0) {
+      const int label = p.ids[r + 1];
+      float lp = logits[label] - (m + logf(se));
+      if (p.log_prior && p.prior_row) {
+        const int pr = p.prior_row[r];
+        if (pr >= 0) lp = (1.f - p.alpha) * lp + p.alpha * p.log_prior[static_cast<long long>(pr) * p.vocab + label];
+      }
+      p.tok_logp[r] = lp;
+    }
+  }
+}
+
+// One warp per sequence: sum tok_logp[b, 0 .. len-2] (lane-strided partials, then a fixed shuffle tree).
+__global__ void seq_sum_kernel(const float* __restrict__ tok_logp, const int32_t* __restrict__ lens, int B, int T,
+                               float* __restrict__ out) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  const int n = lens[b] - 1;
+  float s = 0.f;
+  for (int t = lane; t < n; t += 32) s += tok_logp[static_cast<long long>(b) * T + t];
+  s = warp_sum_t(s);
+  if (lane == 0) out[b] = s;
+}
+
+}  // namespace
+
+int launch_gather_embed(const int32_t* ids, const float* wte, long long rows, int d, int vocab, float* x, cudaStream_t s) {
+  if (rows <= 0) return PG_OK;
+  gather_embed_kernel<<<static_cast<unsigned>(rows), 128, 0, s>>>(ids, wte, d, vocab, x);
+  PG_CUDA_OK(cudaGetLastError());
+  return PG_OK;
+}
+
+int launch_qkv_conv(const __half* in, __half* out, int64_t ld, int64_t lo_off, int B, int T, int heads, const float* taps,
+                    float qscale, cudaStream_t s) {
+  const long long n = static_cast<long long>(B) * T * (3 * heads * 64 / 8);
+  if (n <= 0) return PG_OK;
+  if (heads % 4) return set_error(PG_ERR_ARG, "qkv_conv: heads must be a multiple of 4");
+  qkv_conv_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(in, out, ld, lo_off, B, T, heads, taps, qscale);
+  PG_CUDA_OK(cudaGetLastError());
+  return PG_OK;
+}
+
+int launch_ar_head(const float* x, int d, int B, int T, int vocab, const int32_t* ids, const int32_t* lens, const float* lnf_g,
+                   const float* lnf_b, const float* wte, const float* log_prior, const int32_t* prior_row, float alpha,
+                   float* tok_logp, float* out_sum, cudaStream_t s) {
+  if (B <= 0 || T <= 0) return PG_OK;
+  ArHeadParams p{x, d, T, vocab, ids, lens, lnf_g, lnf_b, wte, log_prior, prior_row, alpha, tok_logp};
+  ar_head_kernel<<<static_cast<unsigned>(static_cast<long long>(B) * T), 128, (d + vocab) * sizeof(float), s>>>(p);
+  seq_sum_kernel<<<(B + 3) / 4, 128, 0, s>>>(tok_logp, lens, B, T, out_sum);
+  PG_CUDA_OK(cudaGetLastError());
+  return PG_OK;
+}
+
+}  // namespace pg

@@ -1,0 +1,291 @@
+"""Host-side driver of the B200 Tranception scorer (reference: proteingym/baselines/tranception).
+
+``TranceptionScorer.score_mutants`` mirrors ``TranceptionLMHeadModel.score_mutants`` (tranception/model_pytorch.py:878-928):
+slice (``get_sequence_slices``, utils/scoring_utils.py:152-203), score every distinct slice left-to-right and on the reversed
+string (``get_tranception_scores_mutated_sequences``, :77-150), divide by the full sequence length, subtract the wild type
+scored in the same window, average the two directions, append the WT row. The forward + token log-likelihood runs in the
+CUDA library (``pg_ar_loglik``); pandas is used only for the same bookkeeping the reference does with it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import math
+import os
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _lib
+
+VOCAB = ["[UNK]", "[CLS]", "[SEP]", "[PAD]", "[MASK]"] + list("ACDEFGHIKLMNPQRSTVWY")
+TOK = {t: i for i, t in enumerate(VOCAB)}
+CLS, SEP, PAD = 1, 2, 3
+AA_vocab = "ACDEFGHIKLMNPQRSTVWY"
+
+
+def alibi_slopes(heads: int):
+    """Grouped ALiBi (model_pytorch.py:50-71): geometric slopes for heads/4 heads, the list repeated four times, so head h
+    gets slopes[h mod (heads/4)] while its conv-kernel group is h div (heads/4)."""
+    def geometric(n):
+        start = 2 ** (-2 ** -(math.log2(n) - 3))
+        return [start ** (i + 1) for i in range(n)]
+
+    def plain(n):
+        if math.log2(n).is_integer():
+            return geometric(n)
+        c = 2 ** math.floor(math.log2(n))
+        return geometric(c) + plain(2 * c)[0::2][:n - c]
+    return plain(heads // 4) * 4
+
+
+def conv_taps(state: dict, layer: int, heads: int) -> torch.Tensor:
+    """[3 (q,k,v) * 4 groups * 64 channels, 8]: look-back taps tap[o] (out[t] = bias + sum_o tap[o] * x[t-o]) and the bias in
+    column 7. Group 0 is the identity; groups 1..3 carry the depthwise Conv1d(k=3,5,7, padding=k-1, truncated) weights
+    (model_pytorch.py:73-88, :240-251): conv weight index j multiplies x[t-(k-1)+j], i.e. look-back o = k-1-j."""
+    taps = torch.zeros(3, 4, 64, 8, dtype=torch.float32)
+    taps[:, 0, :, 0] = 1.0
+    for wi, nm in enumerate(("query", "key", "value")):
+        for gi, k in enumerate((3, 5, 7)):
+            w = state[f"h.{layer}.attn.{nm}_depthwiseconv.{gi}.conv.weight"].float()  # [hd, 1, k]
+            b = state[f"h.{layer}.attn.{nm}_depthwiseconv.{gi}.conv.bias"].float()
+            taps[wi, gi + 1, :, :k] = torch.flip(w[:, 0, :], dims=(1,))
+            taps[wi, gi + 1, :, 7] = b
+    return taps.reshape(3 * 4 * 64, 8).contiguous()
+
+
+def load_tranception_checkpoint(folder: str):
+    """HF checkpoint directory -> (config dict, state with the ``transformer.`` prefix stripped), as
+    ``TranceptionLMHeadModel.from_pretrained`` would consume it (score_tranception_proteingym.py:79-100)."""
+    cfg = json.load(open(os.path.join(folder, "config.json")))
+    pbin = os.path.join(folder, "pytorch_model.bin")
+    if os.path.exists(pbin):
+        raw = torch.load(pbin, map_location="cpu", weights_only=True)
+    else:
+        from safetensors.torch import load_file
+        raw = load_file(os.path.join(folder, "model.safetensors"))
+    state = {}
+    for k, v in raw.items():
+        if k.endswith("attn.bias") or k.endswith("attn.masked_bias") or k == "transformer.alibi" or k == "lm_head.weight":
+            continue  # causal-mask / alibi buffers and the tied output matrix
+        state[k[len("transformer."):] if k.startswith("transformer.") else k] = v.float().contiguous()
+    return cfg, state
+
+
+def tokenize(seq: str) -> list:
+    return [CLS] + [TOK.get(c, 0) for c in seq] + [SEP]
+
+
+def replace_ambiguous(seq: str) -> str:
+    """encode_batch (model_pytorch.py:930-938): X/B/J/Z are replaced by a random compatible residue (np.random, unseeded)."""
+    for ch, repl in (("X", AA_vocab), ("B", "DN"), ("J", "IL"), ("Z", "EQ")):
+        if ch in seq:
+            s = list(seq)
+            pos = [i for i, c in enumerate(s) if c == ch]
+            picks = np.random.choice(a=list(repl), size=len(pos), replace=True)
+            for i, p in zip(pos, picks):
+                s[i] = p
+            seq = "".join(s)
+    return seq
+
+
+class TranceptionScorer:
+    def __init__(self, config: dict, state: dict, precision: str = "f16x3", device: int = 0, max_rows: int = 0):
+        if not torch.cuda.is_available():
+            raise _lib.PgError("no CUDA device: the B200 scorer has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        d, heads, layers = int(config["n_embd"]), int(config["n_head"]), int(config["n_layer"])
+        ffn = int(config["n_inner"]) if config.get("n_inner") else 4 * d
+        self.n_ctx = int(config.get("n_ctx", config.get("n_positions", 1024)))
+        if abs(float(config.get("layer_norm_epsilon", 1e-5)) - 1e-5) > 1e-12:
+            raise _lib.PgError("layer_norm_epsilon != 1e-5 is not supported")
+        if config.get("activation_function", "squared_relu") != "squared_relu":
+            raise _lib.PgError("only the squared_relu activation is supported")
+        self.vocab = int(config.get("vocab_size", 25))
+        self.config = config
+        desc = _lib.PgModelDesc(arch=_lib.PG_ARCH_TRANCEPTION, layers=layers, embed_dim=d, heads=heads, ffn_dim=ffn, vocab=self.vocab,
+                                max_positions=self.n_ctx, token_dropout=0, emb_ln_before=0,
+                                precision={"f16": _lib.PG_PREC_F16, "f16x3": _lib.PG_PREC_F16X3}[precision], device=device,
+                                max_rows=max_rows)
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.pg_create(C.byref(desc), C.byref(self.handle)))
+        try:
+            tensors = {k: v for k, v in state.items() if "depthwiseconv" not in k}
+            for l in range(layers):
+                tensors[f"h.{l}.attn.conv_taps"] = conv_taps(state, l, heads)
+            tensors["alibi_slopes"] = torch.tensor(alibi_slopes(heads), dtype=torch.float32).view(-1, 1)
+            gpu = [(n, t.to(self.device, torch.float32).contiguous()) for n, t in tensors.items()]
+            arr = (_lib.PgTensor * len(gpu))()
+            for i, (n, t) in enumerate(gpu):
+                arr[i].name = n.encode()
+                arr[i].data = t.data_ptr()
+                arr[i].shape[0] = t.shape[0]
+                arr[i].shape[1] = t.shape[1] if t.dim() == 2 else 1
+            torch.cuda.synchronize(self.device)
+            _lib.check(self.lib.pg_load_weights(self.handle, arr, len(gpu)), self.handle)
+            del gpu
+        except Exception:
+            self.close()
+            raise
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.pg_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------------------
+    def sequence_logprobs(self, seqs, prior=None, windows=None, flip=False, alpha=0.6, msa_start=0, msa_end=None, chunk_rows=1 << 17):
+        """sum_t log p(tok_{t+1} | tok_<=t) of ``[CLS] s [SEP]`` for every string in ``seqs`` (float32 numpy).
+        ``prior`` ([L_full, vocab] log-probabilities) with per-sequence ``windows`` [(start, end)] enables the retrieval
+        fusion of model_pytorch.py:806-830; ``flip`` marks right-to-left scoring (the strings are already reversed)."""
+        n = len(seqs)
+        out = np.zeros(n, dtype=np.float32)
+        if n == 0:
+            return out
+        order = np.argsort([len(s) for s in seqs], kind="stable")
+        d_prior = torch.from_numpy(np.ascontiguousarray(prior, dtype=np.float32)).to(self.device) if prior is not None else None
+        msa_end = (prior.shape[0] if msa_end is None else msa_end) if prior is not None else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        i = 0
+        while i < n:
+            T = len(seqs[order[min(n - 1, i)]]) + 2
+            # grow the chunk while the padded row count stays within budget (sequences are sorted by length)
+            j = i
+            while j < n and (j - i + 1) * (len(seqs[order[j]]) + 2) <= chunk_rows:
+                j += 1
+            j = max(j, i + 1)
+            idx = order[i:j]
+            T = len(seqs[idx[-1]]) + 2
+            ids = np.full((len(idx), T), PAD, dtype=np.int32)
+            lens = np.zeros(len(idx), dtype=np.int32)
+            prow = np.full((len(idx), T), -1, dtype=np.int32) if prior is not None else None
+            for r, k in enumerate(idx):
+                t = tokenize(replace_ambiguous(seqs[k]))
+                ids[r, :len(t)] = t
+                lens[r] = len(t)
+                if prior is not None:
+                    ws, we = windows[k]
+                    lo, hi = max(ws, msa_start), min(we, msa_end)
+                    if hi > lo:
+                        if flip:
+                            a0 = max(0, we - msa_end)
+                            prow[r, a0:a0 + hi - lo] = np.arange(hi - 1, lo - 1, -1)
+                        else:
+                            a0 = max(0, msa_start - ws)
+                            prow[r, a0:a0 + hi - lo] = np.arange(lo, hi)
+            d_ids = torch.from_numpy(ids).to(self.device)
+            d_lens = torch.from_numpy(lens).to(self.device)
+            d_prow = torch.from_numpy(prow).to(self.device) if prow is not None else None
+            d_out = torch.empty(len(idx), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.pg_ar_loglik(self.handle, d_ids.data_ptr(), d_lens.data_ptr(), len(idx), T,
+                                             d_prior.data_ptr() if d_prior is not None else None,
+                                             d_prow.data_ptr() if d_prow is not None else None, float(alpha), d_out.data_ptr(), stream),
+                       self.handle)
+            out[idx] = d_out.cpu().numpy()
+            i = j
+        return out
+
+    # ------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _window(pos, L, W):
+        half = W // 2
+        if L <= W:
+            return 0, L
+        if pos < half:
+            return 0, W
+        if pos >= L - half:
+            return L - W, L
+        return max(0, pos - half), min(L, pos + half)
+
+    def slices(self, df, target_seq, scoring_window="optimal", indel_mode=False, start_idx=1) -> pd.DataFrame:
+        """Rows (mutated_sequence, sliced_mutated_sequence, window_start, window_end): every mutant's window followed by the
+        wild type cut with the same window, de-duplicated in first-seen order (scoring_utils.py:152-203)."""
+        ctx = self.n_ctx - 2
+        L = len(target_seq)
+        mseqs = list(df["mutated_sequence"])
+        recs = []
+        if scoring_window == "optimal":
+            spans = []
+            for mut, ms in zip(df["mutant"], mseqs):
+                if indel_mode:
+                    spans.append((0, len(ms)))
+                else:
+                    centre = int(np.array([int(m[1:-1]) - start_idx for m in mut.split(":")]).mean())
+                    spans.append(self._window(centre, L, ctx))
+            recs += [(ms, ms[a:b], a, b) for ms, (a, b) in zip(mseqs, spans)]
+            for a, b in spans:
+                e = L if indel_mode else b
+                recs.append((target_seq, target_seq[a:e], a, e))
+        elif scoring_window == "sliding":
+            for w in range(1 + int(L / ctx)):
+                a = w * ctx
+                recs += [(ms, ms[a:a + ctx], a, min(len(ms), a + ctx)) for ms in mseqs]
+                recs += [(target_seq, target_seq[a:a + ctx], a, min(L, a + ctx)) for _ in mseqs]
+        else:
+            raise ValueError(scoring_window)
+        out = pd.DataFrame(recs, columns=["mutated_sequence", "sliced_mutated_sequence", "window_start", "window_end"])
+        return out.drop_duplicates().reset_index(drop=True)
+
+    def _direction(self, sl, target_seq, name, scoring_window, reverse, prior_kw):
+        strings = [s[::-1] for s in sl["sliced_mutated_sequence"]] if reverse else list(sl["sliced_mutated_sequence"])
+        windows = list(zip(sl["window_start"], sl["window_end"]))
+        sc = sl.copy()
+        sc["score"] = self.sequence_logprobs(strings, windows=windows, flip=reverse, **prior_kw).astype(np.float32)
+        if scoring_window == "sliding":
+            sc = sc[["mutated_sequence", "score"]].groupby("mutated_sequence").sum().reset_index()
+        sc["score"] = sc["score"] / sc["mutated_sequence"].map(len)
+        is_wt = sc.mutated_sequence == target_seq
+        mut, wt = sc[~is_wt], sc[is_wt]
+        if scoring_window == "optimal":
+            d = pd.merge(mut, wt, how="left", on=["window_start"], suffixes=("", "_wt"))
+            d[name] = d["score"] - d["score_wt"]
+        else:
+            d = mut.copy()
+            d[name] = d["score"] - list(wt["score"])[0]
+        return d[["mutated_sequence", name]]
+
+    def score_mutants(self, DMS_data: pd.DataFrame, target_seq: str, scoring_mirror=True, indel_mode=False, scoring_window="optimal",
+                      log_prior=None, retrieval_inference_weight=0.6, MSA_start=0, MSA_end=None) -> pd.DataFrame:
+        df = DMS_data.copy()
+        if "mutated_sequence" not in df and not indel_mode:
+            df["mutated_sequence"] = df["mutant"].apply(lambda m: apply_substitutions(target_seq, m))
+        assert "mutated_sequence" in df, "DMS file to score does not have mutated_sequence column"
+        if "mutant" not in df:
+            df["mutant"] = df["mutated_sequence"]
+        df = df[["mutated_sequence", "mutant"]].reset_index(drop=True)
+        sl = self.slices(df, target_seq, scoring_window, indel_mode)
+        pk = dict(prior=log_prior, alpha=retrieval_inference_weight, msa_start=MSA_start, msa_end=MSA_end) if log_prior is not None else {}
+        print("Scoring sequences from left to right")
+        out = self._direction(sl, target_seq, "avg_score_L_to_R", scoring_window, False, pk)
+        if scoring_mirror:
+            print("Scoring sequences from right to left")
+            rl = self._direction(sl, target_seq, "avg_score_R_to_L", scoring_window, True, pk)
+            out = pd.merge(out, rl, on="mutated_sequence", how="left", suffixes=("", "_R_to_L"))
+            out["avg_score"] = (out["avg_score_L_to_R"] + out["avg_score_R_to_L"]) / 2.0
+        else:
+            out["avg_score"] = out["avg_score_L_to_R"]
+        col = "mutant" if indel_mode else "mutated_sequence"
+        if target_seq in DMS_data[col].values:  # WT row scores 0 by definition (model_pytorch.py:917-927)
+            cols = [col, "avg_score_L_to_R", "avg_score_R_to_L", "avg_score"] if scoring_mirror else [col, "avg_score_L_to_R", "avg_score"]
+            out = pd.concat([out, pd.DataFrame([[target_seq] + [0] * (len(cols) - 1)], columns=cols)], ignore_index=True)
+        return out
+
+
+def apply_substitutions(focus_seq: str, mutant: str, start_idx: int = 1) -> str:
+    """scoring_utils.get_mutated_sequence (:16-31), same assertion messages."""
+    s = list(focus_seq)
+    for m in mutant.split(":"):
+        f, pos, t = m[0], int(m[1:-1]), m[-1]
+        rel = pos - start_idx
+        assert f == focus_seq[rel], "Invalid from_AA or mutant position: " + str(m) + " from_AA: " + str(f) + " relative pos: " + str(rel) + " focus_seq: " + str(focus_seq)
+        assert t in AA_vocab, "Mutant to_AA is invalid: " + str(m)
+        s[rel] = t
+    return "".join(s)

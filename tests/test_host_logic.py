@@ -156,3 +156,51 @@ def test_cli_resolve_assay_errors_match_reference(tmp_path):
     a = create_parser().parse_args(base + ["--dms_index", "2"])
     df, col, off = resolve_assay(a)
     assert (len(df), col, off, a.sequence) == (2, "mutant", 1, "MKVL") and a.dms_output.endswith("B2.csv")
+
+
+# ------------------------------------------------------------------------------------------------ Tranception host logic
+def test_tranception_slopes_taps_tokens_slices_match_oracle():
+    import pandas as pd
+    from oracle import tranception_oracle as TO
+    from proteingym_b200 import tranception_engine as TE
+    for heads in (4, 8, 12, 20, 24):
+        assert np.allclose(TE.alibi_slopes(heads), TO.get_slopes(heads), rtol=0, atol=0)
+    assert TE.VOCAB == TO.VOCAB and TE.tokenize("MSIQ") == [1, 15, 20, 12, 18, 2] == TO.tokenize("MSIQ")
+    # conv taps reproduce the reference-style depthwise conv
+    arch = synth.TranceptionArch(1, 256, 4, 256)
+    st = {k[len("transformer."):]: v for k, v in synth.make_tranception_state(arch, 3).items() if k.startswith("transformer.")}
+    taps = TE.conv_taps(st, 0, 4).view(3, 4, 64, 8)
+    x = torch.randn(1, 1, 30, 64)
+    for gi, k in enumerate((3, 5, 7)):
+        ref = TO.depthwise_causal_conv(x, st[f"h.0.attn.key_depthwiseconv.{gi}.conv.weight"], st[f"h.0.attn.key_depthwiseconv.{gi}.conv.bias"])
+        got = torch.zeros_like(x) + taps[1, gi + 1, :, 7]
+        for o in range(7):
+            shifted = torch.cat([torch.zeros(1, 1, o, 64), x[:, :, :30 - o]], dim=2)
+            got = got + shifted * taps[1, gi + 1, :, o]
+        assert (got - ref).abs().max() < 1e-5
+    assert torch.equal(taps[:, 0, :, 0], torch.ones(3, 64)) and taps[:, 0, :, 1:].abs().sum() == 0
+    # slices: same rows, same order as the oracle restatement of get_sequence_slices
+    sc = object.__new__(TE.TranceptionScorer)
+    sc.n_ctx = 64
+    seq = synth.random_protein(150, 2)
+    muts = synth.sample_mutants(seq, 40, 1, multi_frac=0.3)
+    df = pd.DataFrame({"mutant": muts, "mutated_sequence": [synth.apply_mutant(seq, m) for m in muts]})
+    for mode in ("optimal", "sliding"):
+        a = sc.slices(df, seq, mode)
+        b = TO.sequence_slices(df, seq, 62, scoring_window=mode)
+        assert a.equals(b), mode
+    ind = synth.random_indels(seq[:50], 20, 3)
+    dfi = pd.DataFrame({"mutant": ind, "mutated_sequence": ind})
+    assert sc.slices(dfi, seq[:50], "optimal", indel_mode=True).equals(TO.sequence_slices(dfi, seq[:50], 62, indel_mode=True))
+    with pytest.raises(AssertionError, match="Invalid from_AA or mutant position"):
+        TE.apply_substitutions("MKV", "A1G")
+
+
+def test_tranception_checkpoint_round_trip(tmp_path):
+    from proteingym_b200 import tranception_engine as TE
+    arch = synth.TranceptionArch(2, 256, 4, 512)
+    st = synth.write_tranception_checkpoint(str(tmp_path / "Tranception_tiny"), arch, seed=2)
+    cfg, state = TE.load_tranception_checkpoint(str(tmp_path / "Tranception_tiny"))
+    assert (cfg["n_embd"], cfg["n_head"], cfg["n_layer"], cfg["n_inner"]) == (256, 4, 2, 512)
+    assert "lm_head.weight" not in state and torch.equal(state["wte.weight"], st["transformer.wte.weight"])
+    assert torch.equal(state["h.1.mlp.c_fc.weight"], st["transformer.h.1.mlp.c_fc.weight"])
