@@ -67,7 +67,7 @@ def load_tranception_checkpoint(folder: str):
         raw = load_file(os.path.join(folder, "model.safetensors"))
     state = {}
     for k, v in raw.items():
-        if k.endswith("attn.bias") or k.endswith("attn.masked_bias") or k == "transformer.alibi" or k == "lm_head.weight":
+        if k.endswith(".attn.bias") or k.endswith(".attn.masked_bias") or k == "transformer.alibi" or k == "lm_head.weight":
             continue  # causal-mask / alibi buffers and the tied output matrix
         state[k[len("transformer."):] if k.startswith("transformer.") else k] = v.float().contiguous()
     return cfg, state
