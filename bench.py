@@ -130,7 +130,7 @@ def cpu_port_mutants_per_s(arch, state, seconds, threads):
     # thread count that is fastest on a short probe instead of handicapping the CPU arm with oversubscription
     probe = O.tokenize(make_assay(0, 128 if arch.layers > 8 else 32, 10)[0])[None]
     best = _CPU_CACHE.get("best", (None, float("inf")))
-    for nt in ([] if best[0] else sorted({t for t in (8, 16, 32, 64, threads) if t <= threads})):
+    for nt in ([] if best[0] else sorted({t for t in (8, 16, 32, 64) if t <= threads} or {threads})):
         torch.set_num_threads(nt)
         with torch.no_grad():
             O.esm_forward(st, probe, kind, arch.layers, arch.heads, arch.token_dropout)
@@ -325,6 +325,7 @@ def main():
         torch.cuda.empty_cache()
         return res
 
+    cpu_state = {k: v.cpu() for k, v in state.items()} if (rank == 0 and world == 1 and not a.no_cpu_baseline) else None
     main_res = measure(a.precision, with_e2e=True)
     other = "f16" if a.precision == "f16x3" else "f16x3"
     other_res = measure(other, with_e2e=False) if not a.small else None
@@ -351,8 +352,7 @@ def main():
     if not a.no_cpu_baseline and world == 1:
         log("cpu baseline")
         threads = os.cpu_count() or 1
-        st_cpu = synth.make_esm_state(arch, seed=0)
-        v, info = cpu_port_mutants_per_s(arch, st_cpu, a.cpu_seconds, threads)
+        v, info = cpu_port_mutants_per_s(arch, cpu_state, a.cpu_seconds, threads)
         out["cpu_baseline"] = {"value": v, "unit": "mutants/s", "cores": info["threads"], "host_cpus": threads, "kind": "port",
                                "sample": f"{info['forwards_timed']} batch-1 masked forwards of T={info['T']} (median "
                                          f"{info['t_forward_s']:.3f} s) extrapolated to the reference's L+2 forwards per assay"}
