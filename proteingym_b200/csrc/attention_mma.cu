@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(AttnLaunch a) {
   const uint32_t sK = sQ + NP * TILE_BYTES;                // [2 stages][NP]
   const uint32_t sV = sK + 2 * NP * TILE_BYTES;            // [2 stages][NP]
 
-  const int q0 = blockIdx.x * AQ, head = blockIdx.y, b = blockIdx.z;
+  const int q0 = a.q_begin + blockIdx.x * AQ, head = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int d = a.heads * 64;
@@ -212,7 +212,8 @@ int launch_attention(const AttnLaunch& a, cudaStream_t s) {
   if (a.ld % 8 || a.lo_off % 8 || a.ldo % 2 || a.out_lo_off % 2) return set_error(PG_ERR_ARG, "attention: misaligned pitches");
   if (a.nseg != 1 && a.nseg != 3) return set_error(PG_ERR_ARG, "attention: nseg must be 1 or 3");
   if (a.heads > 65535 || a.B > 65535) return set_error(PG_ERR_ARG, "attention: grid too large");
-  dim3 grid((a.T + AQ - 1) / AQ, a.heads, a.B);
+  if (a.q_begin < 0 || a.q_begin >= a.T) return set_error(PG_ERR_ARG, "attention: bad q_begin");
+  dim3 grid((a.T - a.q_begin + AQ - 1) / AQ, a.heads, a.B);
   if (a.nseg == 1) {
     const int smem = 5 * TILE_BYTES;
     attn_mma_kernel<1><<<grid, 128, smem, s>>>(a);

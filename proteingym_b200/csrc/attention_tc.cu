@@ -1,4 +1,4 @@
-// K4 — tcgen05/TMEM fused multi-head self-attention (non-causal), head_dim 64, equal-length sequences.
+// K4 — tcgen05/TMEM fused multi-head self-attention (bidirectional, or causal + ALiBi for Tranception), head_dim 64.
 // Reference arithmetic: esm/multihead_attention.py:357 (QK^T), :379 (fp32 softmax), :387 (PV); q pre-scaled / pre-rotated.
 //
 // One persistent CTA per SM (384 threads); work item = (sequence, head, 128-query tile):
@@ -13,6 +13,8 @@
 // tensor pipe has headroom because the kernel is exp-throughput bound (16 MUFU/clk/SM) in single-pass mode.
 // NP == 2 (f16x3 parity mode): Q,K,V arrive as hi|lo planes, S = QhKh + QlKh + QhKl, O = PhVh + PlVh + PhVl.
 // Roofline: tensor/MUFU bound; algorithmic FLOPs = 4*T^2*64 per (sequence, head).
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -40,6 +42,8 @@ struct AttnTcParams {
   int d;                  // heads * 64
   long long lo_off;       // column offset of the lo planes in qkv
   __half* out; long long ldo; long long out_lo_off;
+  int causal;                 // keys > query masked (Tranception, model_pytorch.py:162-165); key blocks beyond the diagonal skipped
+  const float* alibi_slopes;  // [heads] or null: score += slope_h * key_index (model_pytorch.py:167-168, :373-380)
 };
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -134,10 +138,11 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
             tma_load_2d(sKV + (slot * NP + pl) * TILE, &tm, &kv_full[slot], col + pl * static_cast<int>(p.lo_off), row0 + j * KT);
           if (++slot == NSLOT) { slot = 0; phase ^= 1; }
         };
-        for (int j = 0; j < p.nkb; ++j) load_block(ck, j, 1);  // pass A: K hi only
-        load_block(ck, 0, NP);                                  // pass B: K0, then (K_{j+1}, V_j) ...
-        for (int j = 0; j < p.nkb; ++j) {
-          if (j + 1 < p.nkb) load_block(ck, j + 1, NP);
+        const int nkb = p.causal ? (qt + 1 < p.nkb ? qt + 1 : p.nkb) : p.nkb;  // QT == KT: the diagonal block is block qt
+        for (int j = 0; j < nkb; ++j) load_block(ck, j, 1);  // pass A: K hi only
+        load_block(ck, 0, NP);                                // pass B: K0, then (K_{j+1}, V_j) ...
+        for (int j = 0; j < nkb; ++j) {
+          if (j + 1 < nkb) load_block(ck, j + 1, NP);
           load_block(cv, j, NP);
         }
       }
@@ -154,6 +159,8 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
       const uint32_t p_addr = smem_u32(sP);
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
         mbar_wait(q_full, it & 1);
+        const int qt_m = item % p.nqt;
+        const int nkb = p.causal ? (qt_m + 1 < p.nkb ? qt_m + 1 : p.nkb) : p.nkb;
         auto issue_qk = [&](int j, bool full) {
           const uint32_t buf = sblk & 1;
           mbar_wait(&kv_full[slot], phase);
@@ -177,10 +184,10 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
           if (++slot == NSLOT) { slot = 0; phase ^= 1; }
           ++sblk;
         };
-        for (int j = 0; j < p.nkb; ++j) issue_qk(j, false);  // pass A (row max only)
+        for (int j = 0; j < nkb; ++j) issue_qk(j, false);  // pass A (row max only)
         issue_qk(0, true);
-        for (int j = 0; j < p.nkb; ++j) {
-          if (j + 1 < p.nkb) issue_qk(j + 1, true);
+        for (int j = 0; j < nkb; ++j) {
+          if (j + 1 < nkb) issue_qk(j + 1, true);
           else umma_commit(q_empty);  // all QK MMAs of this item issued: Q tile free once they complete
           mbar_wait(&kv_full[slot], phase);
           mbar_wait(p_full, pblk & 1);
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
           }
           umma_commit(&kv_empty[slot]);
           umma_commit(p_empty);
-          if (j == p.nkb - 1) umma_commit(o_full);
+          if (j == nkb - 1) umma_commit(o_full);
           if (++slot == NSLOT) { slot = 0; phase ^= 1; }
           ++pblk;
         }
@@ -225,26 +232,32 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
       const int qt = item % p.nqt, bh = item / p.nqt;
       const int h = bh % p.heads, b = bh / p.heads;
+      const int nkb = p.causal ? (qt + 1 < p.nkb ? qt + 1 : p.nkb) : p.nkb;
+      const float slope = p.alibi_slopes ? p.alibi_slopes[h] : 0.f;
+      const bool plain = !p.causal && slope == 0.f;  // ESM path: no per-row limit, no bias
       // ---- pass A: row max over this thread's columns ----
       float m = -INFINITY;
-      for (int j = 0; j < p.nkb; ++j, ++sblk) {
+      for (int j = 0; j < nkb; ++j, ++sblk) {
         const uint32_t buf = sblk & 1;
         mbar_wait(&s_full[buf], (sblk >> 1) & 1);
         tc_fence_after();
         const int valid = p.T - j * KT - g * 64;  // valid keys in this thread's 64 columns (may be <= 0 or >= 64)
+        // causal: this row may look at keys <= its own index, i.e. at most vrow columns of this thread's half
+        const int vrow = (p.causal && j == qt) ? min(valid, row + 1 - g * 64) : valid;
+        const float kb0 = static_cast<float>(j * KT + g * 64);
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           if (c * 32 >= valid) break;
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL0 + buf * KT + g * 64 + c * 32, r);
           tmem_ld_wait();
-          if (valid - c * 32 >= 32) {
+          if (plain && valid - c * 32 >= 32) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < valid) m = fmaxf(m, __uint_as_float(r[i]));
+              if (c * 32 + i < vrow) m = fmaxf(m, fmaf(slope, kb0 + static_cast<float>(c * 32 + i), __uint_as_float(r[i])));
           }
         }
         tc_fence_before();
@@ -257,11 +270,14 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
       const float m2 = m * LOG2E;
       float l = 0.f;
       // ---- pass B: P = exp(S - max) ----
-      for (int j = 0; j < p.nkb; ++j, ++sblk, ++pblk) {
+      const float slope2 = slope * LOG2E;
+      for (int j = 0; j < nkb; ++j, ++sblk, ++pblk) {
         const uint32_t buf = sblk & 1;
         mbar_wait(&s_full[buf], (sblk >> 1) & 1);
         tc_fence_after();
         const int valid = p.T - j * KT - g * 64;
+        const int vrow = (p.causal && j == qt) ? min(valid, row + 1 - g * 64) : valid;
+        const float bias0 = fmaf(slope2, static_cast<float>(j * KT + g * 64), -m2);  // slope*key_index*log2e - max*log2e
         const int ncols = nkeys(j) - g * 64;  // columns the PV MMA will read from this thread's half
         uint32_t r[2][32];
         if (ncols > 0) tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL0 + buf * KT + g * 64, r[0]);
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           if (c * 32 < ncols) {
-            if (valid - c * 32 >= 32) {
+            if (plain && valid - c * 32 >= 32) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const float e = ex2_approx(fmaf(__uint_as_float(r[c][i]), LOG2E, -m2));
@@ -283,7 +299,8 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const float e = (c * 32 + i < valid) ? ex2_approx(fmaf(__uint_as_float(r[c][i]), LOG2E, -m2)) : 0.f;
+                const float arg = fmaf(__uint_as_float(r[c][i]), LOG2E, fmaf(slope2, static_cast<float>(c * 32 + i), bias0));
+                const float e = (c * 32 + i < vrow) ? ex2_approx(arg) : 0.f;
                 l += e;
                 r[c][i] = __float_as_uint(e);
               }
@@ -363,14 +380,22 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
 
 int launch_attention_tc(const AttnLaunch& a, cudaStream_t s) {
   if (a.B <= 0 || a.T <= 0) return PG_OK;
-  if (a.causal || a.alibi_slopes) return set_error(PG_ERR_UNSUPPORTED, "attention_tc: causal/ALiBi not supported by this kernel");
   if (a.nseg != 1 && a.nseg != 3) return set_error(PG_ERR_ARG, "attention: nseg must be 1 or 3");
   if (a.ld % 8 || a.lo_off % 8 || a.ldo % 8 || a.out_lo_off % 8 || (reinterpret_cast<uintptr_t>(a.out) & 15))
     return set_error(PG_ERR_ARG, "attention_tc: pitches must be multiples of 8 elements and out 16-byte aligned");
   AttnTcParams p{};
   p.B = a.B; p.T = a.T; p.heads = a.heads; p.d = a.heads * 64;
   p.nqt = (a.T + QT - 1) / QT; p.nkb = (a.T + KT - 1) / KT;
+  // A last query tile holding only a few rows (T = 514 -> 2 of 128) would cost a full work item; those rows go to the
+  // mma.sync kernel instead, which runs several CTAs per SM next to this persistent kernel's tail.
+  // Measured (B200, T = 514): the serialised mma.sync tail launch costs as much as the wasted tile it removes, so the split is
+  // off by default; PG_ATTN_SPLIT_TAIL=1 enables it for experiments.
+  const int tail = a.T % QT;
+  static const bool want_split = getenv("PG_ATTN_SPLIT_TAIL") != nullptr;
+  const bool split_tail = want_split && a.T > QT && tail > 0 && tail <= 16;
+  if (split_tail) p.nqt -= 1;
   p.lo_off = a.lo_off; p.out = a.out; p.ldo = a.ldo; p.out_lo_off = a.out_lo_off;
+  p.causal = a.causal; p.alibi_slopes = a.alibi_slopes;
   const int np = a.nseg == 3 ? 2 : 1;
   const uint64_t width = static_cast<uint64_t>(3) * p.d * np;
   if (np == 2 && a.lo_off != 3ll * p.d) return set_error(PG_ERR_ARG, "attention_tc: lo planes must follow the hi planes (lo_off == 3*d)");
@@ -394,6 +419,11 @@ int launch_attention_tc(const AttnLaunch& a, cudaStream_t s) {
     attn_tc_kernel<2><<<grid, 384, Smem<2>::TOTAL, s>>>(tm, p);
   }
   PG_CUDA_OK(cudaGetLastError());
+  if (split_tail) {
+    AttnLaunch t = a;
+    t.q_begin = a.T - tail;
+    return launch_attention(t, s);
+  }
   return PG_OK;
 }
 

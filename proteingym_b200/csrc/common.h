@@ -52,6 +52,7 @@ struct AttnLaunch {
   __half* out; int64_t ldo; int64_t out_lo_off;
   int B, T, heads, nseg, causal;
   const float* alibi_slopes;
+  int q_begin = 0;  // first query row handled by this launch (mma.sync kernel only): rows [q_begin, T)
 };
 int launch_attention(const AttnLaunch& a, cudaStream_t s);
 

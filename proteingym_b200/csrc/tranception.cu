@@ -47,30 +47,45 @@ __global__ void gather_embed_kernel(const int32_t* __restrict__ ids, const float
   for (int j = threadIdx.x; j < d / 4; j += blockDim.x) dst[j] = src[j];
 }
 
-// One thread per (row, 8-channel chunk). taps: [3 (q,k,v)][4 groups][64 channels][8] = 7 look-back taps + bias.
+// One thread per (sequence, 8-channel chunk, block of CONV_TB time steps): the 8x(7 taps + bias) coefficients and a 7-row
+// sliding window live in registers, so every input row is read once per block instead of once per tap.
+// taps: [3 (q,k,v)][4 groups][64 channels][8] = 7 look-back taps + bias.
 // in/out: [B*T, ld] fp16 with columns [q | k | v] (+ lo plane at lo_off). out[t] = bias + sum_o tap[o] * in[t - o].
+constexpr int CONV_TB = 16;
 __global__ void qkv_conv_kernel(const __half* __restrict__ in, __half* __restrict__ out, long long ld, long long lo_off, int B, int T,
                                 int heads, const float* __restrict__ taps, float qscale) {
   const int d = heads * 64;
   const int chunks = 3 * d / 8;
+  const int tblocks = (T + CONV_TB - 1) / CONV_TB;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (gid >= static_cast<long long>(B) * T * chunks) return;
-  const int ck = static_cast<int>(gid % chunks);
-  const long long row = gid / chunks;
-  const int t = static_cast<int>(row % T);
+  if (gid >= static_cast<long long>(B) * tblocks * chunks) return;
+  const int ck = static_cast<int>(gid % chunks);  // fastest: neighbouring threads read neighbouring 16-byte chunks of a row
+  const int tb = static_cast<int>((gid / chunks) % tblocks);
+  const int b = static_cast<int>(gid / (static_cast<long long>(chunks) * tblocks));
   const int c0 = ck * 8;
   const int which = c0 / d, head = (c0 % d) / 64, ch0 = c0 % 64;
   const int group = head / (heads / 4);
-  const float* tp = taps + ((static_cast<long long>(which) * 4 + group) * 64 + ch0) * 8;
   const int klen = group == 0 ? 1 : 2 * group + 1;
-  float acc[8];
+  const float4* tp4 = reinterpret_cast<const float4*>(taps + ((static_cast<long long>(which) * 4 + group) * 64 + ch0) * 8);
+  float tap[8][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = tp[i * 8 + 7];
-  for (int o = 0; o < klen && o <= t; ++o) {
-    const __half* src = in + (row - o) * ld + c0;
+  for (int i = 0; i < 8; ++i) {
+    const float4 lo4 = __ldg(tp4 + 2 * i), hi4 = __ldg(tp4 + 2 * i + 1);
+    tap[i][0] = lo4.x; tap[i][1] = lo4.y; tap[i][2] = lo4.z; tap[i][3] = lo4.w;
+    tap[i][4] = hi4.x; tap[i][5] = hi4.y; tap[i][6] = hi4.z; tap[i][7] = hi4.w;
+  }
+  const float sc = which == 0 ? qscale : 1.f;
+  const long long row0 = static_cast<long long>(b) * T;
+  const int t0 = tb * CONV_TB;
+  float win[7][8];  // win[o] = input row t - o
+#pragma unroll
+  for (int o = 0; o < 7; ++o)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) win[o][i] = 0.f;
+  auto load_row = [&](int t, float (&v)[8]) {
+    const __half* src = in + (row0 + t) * ld + c0;
     const uint4 hv = *reinterpret_cast<const uint4*>(src);
     const __half2* h2 = reinterpret_cast<const __half2*>(&hv);
-    float v[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 f = __half22float2(h2[i]);
@@ -85,22 +100,41 @@ __global__ void qkv_conv_kernel(const __half* __restrict__ in, __half* __restric
         v[2 * i] += f.x; v[2 * i + 1] += f.y;
       }
     }
+  };
+  // prime the window with the klen-1 rows before the block (zeros before the start of the sequence)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(tp[i * 8 + o], v[i], acc[i]);
-  }
-  const float sc = which == 0 ? qscale : 1.f;
-  uint32_t hi[4], lo[4];
+  for (int o = 1; o < 7; ++o)
+    if (o < klen && t0 - o >= 0) load_row(t0 - o, win[o]);
+#pragma unroll 1
+  for (int tt = 0; tt < CONV_TB; ++tt) {
+    const int t = t0 + tt;
+    if (t >= T) break;
+    load_row(t, win[0]);
+    float acc[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __half h0, l0, h1, l1;
-    split_hi_lo(acc[2 * i] * sc, h0, l0);
-    split_hi_lo(acc[2 * i + 1] * sc, h1, l1);
-    hi[i] = pack_h2(h0, h1);
-    lo[i] = pack_h2(l0, l1);
+    for (int i = 0; i < 8; ++i) {
+      float a = tap[i][7];
+#pragma unroll
+      for (int o = 0; o < 7; ++o) a = fmaf(tap[i][o], win[o][i], a);  // taps beyond klen are zero
+      acc[i] = a * sc;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half h0, l0, h1, l1;
+      split_hi_lo(acc[2 * i], h0, l0);
+      split_hi_lo(acc[2 * i + 1], h1, l1);
+      hi[i] = pack_h2(h0, h1);
+      lo[i] = pack_h2(l0, l1);
+    }
+    __half* dst = out + (row0 + t) * ld + c0;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (lo_off > 0) *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+    for (int o = 6; o > 0; --o)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) win[o][i] = win[o - 1][i];
   }
-  __half* dst = out + row * ld + c0;
-  *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  if (lo_off > 0) *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 struct ArHeadParams {
@@ -188,7 +222,7 @@ int launch_gather_embed(const int32_t* ids, const float* wte, long long rows, in
 
 int launch_qkv_conv(const __half* in, __half* out, int64_t ld, int64_t lo_off, int B, int T, int heads, const float* taps,
                     float qscale, cudaStream_t s) {
-  const long long n = static_cast<long long>(B) * T * (3 * heads * 64 / 8);
+  const long long n = static_cast<long long>(B) * ((T + CONV_TB - 1) / CONV_TB) * (3 * heads * 64 / 8);
   if (n <= 0) return PG_OK;
   if (heads % 4) return set_error(PG_ERR_ARG, "qkv_conv: heads must be a multiple of 4");
   qkv_conv_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(in, out, ld, lo_off, B, T, heads, taps, qscale);
