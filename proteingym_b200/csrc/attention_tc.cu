@@ -235,6 +235,9 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
       const int nkb = p.causal ? (qt + 1 < p.nkb ? qt + 1 : p.nkb) : p.nkb;
       const float slope = p.alibi_slopes ? p.alibi_slopes[h] : 0.f;
       const bool plain = !p.causal && slope == 0.f;  // ESM path: no per-row limit, no bias
+      // A warp whose 32 query rows all lie beyond T (the tail tile of T = 514 keeps 2 rows of 128) only keeps the barrier
+      // protocol going: no TMEM loads, no exponentials, no P writes (its P rows feed O rows that are never stored).
+      const bool live = qt * QT + wq * 32 < p.T;
       // ---- pass A: row max over this thread's columns ----
       float m = -INFINITY;
       for (int j = 0; j < nkb; ++j, ++sblk) {
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
         const float kb0 = static_cast<float>(j * KT + g * 64);
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
-          if (c * 32 >= valid) break;
+          if (c * 32 >= valid || !live) break;
           uint32_t r[32];
           tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL0 + buf * KT + g * 64 + c * 32, r);
           tmem_ld_wait();
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
         const int valid = p.T - j * KT - g * 64;
         const int vrow = (p.causal && j == qt) ? min(valid, row + 1 - g * 64) : valid;
         const float bias0 = fmaf(slope2, static_cast<float>(j * KT + g * 64), -m2);  // slope*key_index*log2e - max*log2e
-        const int ncols = nkeys(j) - g * 64;  // columns the PV MMA will read from this thread's half
+        const int ncols = live ? nkeys(j) - g * 64 : 0;  // columns the PV MMA will read from this thread's half
         uint32_t r[2][32];
         if (ncols > 0) tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL0 + buf * KT + g * 64, r[0]);
         if (ncols > 32) tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL0 + buf * KT + g * 64 + 32, r[1]);
@@ -341,13 +344,15 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
       mbar_wait(o_full, it & 1);
       tc_fence_after();
       uint32_t o[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + g * 32, o);
-      tmem_ld_wait();
+      if (live) {
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + g * 32, o);
+        tmem_ld_wait();
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
       const int qidx = qt * QT + row;
-      if (qidx < p.T) {
+      if (live && qidx < p.T) {
         const float rl = 1.f / l;
         __half* orow = p.out + (static_cast<long long>(b) * p.T + qidx) * p.ldo + h * 64 + g * 32;
         uint32_t hi[16], lo[16];

@@ -1,0 +1,95 @@
+"""Multi-assay, multi-GPU driver: score every assay of a ProteinGym reference file with ESM masked-marginals on all the
+GPUs of one box. Replaces the SLURM-array pattern of scripts/scoring_DMS_zero_shot/scoring_ESM*_substitutions.sh (one
+``compute_fitness.py --dms_index N`` process per assay) by one process per GPU:
+
+    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 -m proteingym_b200.run_assays \\
+        --model-location ckpt1.pt ckpt2.pt ... --model_type ESM1v --dms_mapping reference_files/DMS_substitutions.csv \\
+        --dms-input DMS_ProteinGym_substitutions --dms-output out/
+
+Weights are read on rank 0 and NCCL-broadcast; assays are assigned by LPT on the analytic cost (sharding.assay_cost); each
+rank writes the CSVs of its own assays (same files compute_fitness.py would write); rank 0 gathers a (assay, seconds,
+mutants) summary. No collective runs on the data path."""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import pandas as pd
+import torch
+
+if __package__ in (None, ""):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main(argv=None):
+    from proteingym_b200 import sharding
+    from proteingym_b200.checkpoint import load_esm_checkpoint
+    from proteingym_b200.esm_engine import EsmScorer
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model-location", nargs="+", required=True)
+    ap.add_argument("--model_type", nargs="+", default=["ESM1v"])
+    ap.add_argument("--dms_mapping", required=True)
+    ap.add_argument("--dms-input", required=True)
+    ap.add_argument("--dms-output", required=True)
+    ap.add_argument("--mutation-col", default="mutant")
+    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "f16"])
+    ap.add_argument("--indices", type=int, nargs="*", default=None, help="subset of dms_index values (default: all rows)")
+    a = ap.parse_args(argv)
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mapping = pd.read_csv(a.dms_mapping)
+    idx = list(range(len(mapping))) if a.indices is None else a.indices
+    os.makedirs(a.dms_output, exist_ok=True)
+    frames = {}
+    summary = {}
+    for ci, ckpt in enumerate(a.model_location):
+        conf = state = None
+        if rank == 0:
+            conf, state, name = load_esm_checkpoint(ckpt)
+        if dist is not None:
+            box = [conf, os.path.basename(ckpt).split(".")[0]] if rank == 0 else [None, None]
+            dist.broadcast_object_list(box, src=0)
+            conf, name = box
+            state = sharding.broadcast_state(state, src=0, device=torch.device("cuda", local))
+        costs = [sharding.assay_cost(len(str(mapping["target_seq"][i])), conf.layers, conf.embed_dim, conf.ffn_dim) for i in idx]
+        mine = [idx[j] for j in sharding.lpt_assign(costs, world)[rank]]
+        scorer = EsmScorer(conf, state, precision=a.precision, device=local)
+        del state
+        for i in mine:
+            row = mapping.iloc[i].replace(np.nan, "")
+            seq = row["target_seq"].upper()
+            col = row["DMS_mutant_column"] if "DMS_mutant_column" in mapping.columns else a.mutation_col
+            off = int(row["start_idx"]) if "start_idx" in mapping.columns and row["start_idx"] != "" else 1
+            if i not in frames:
+                frames[i] = pd.read_csv(os.path.join(a.dms_input, row["DMS_filename"]))
+            t0 = time.time()
+            frames[i][name] = scorer.score_assay(seq, list(frames[i][col]), off).astype(np.float64)
+            summary[(i, name)] = (time.time() - t0, len(frames[i]))
+        scorer.close()
+    for i, df in frames.items():
+        if "ESM1v" in a.model_type:
+            names = [os.path.basename(c).split(".")[0] for c in a.model_location]
+            df["Ensemble_ESM1v"] = sum(df[n] for n in names) / len(names)
+        df.to_csv(os.path.join(a.dms_output, str(mapping["DMS_id"][i]) + ".csv"), index=False)
+    rows = [(int(i), n, float(s), int(m), rank) for (i, n), (s, m) in summary.items()]
+    if dist is not None:
+        allrows = [None] * world
+        dist.all_gather_object(allrows, rows)
+        rows = [r for rr in allrows for r in rr]
+        dist.destroy_process_group()
+    if rank == 0:
+        rep = pd.DataFrame(rows, columns=["dms_index", "checkpoint", "seconds", "mutants", "rank"]).sort_values(["dms_index", "checkpoint"])
+        rep.to_csv(os.path.join(a.dms_output, "_run_assays_summary.csv"), index=False)
+        print(f"scored {rep['mutants'].sum()} mutant-checkpoint rows over {rep['dms_index'].nunique()} assays in "
+              f"{rep.groupby('rank')['seconds'].sum().max():.1f} s (slowest rank)")
+
+
+if __name__ == "__main__":
+    main()

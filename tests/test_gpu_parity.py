@@ -409,3 +409,44 @@ def test_wt_marginals_overlapping_windows_match_oracle():
         probs[s0:s0 + 1024] += lp * w[:, None]
         wsum[s0:s0 + 1024] += w
     assert (got - probs / wsum[:, None]).abs().max().item() < 2e-4
+
+
+def test_run_assays_driver_single_gpu_matches_cli_outputs(tmp_path):
+    """The multi-assay driver (one process per GPU; here world = 1) writes the same CSVs as per-assay compute_fitness runs."""
+    import pandas as pd
+    from proteingym_b200 import run_assays
+    arch = synth.EsmArch("esm1v", 2, 128, 2, 256)
+    st = synth.write_esm_checkpoint(str(tmp_path / "esm1v_tiny_a.pt"), arch, seed=1)
+    (tmp_path / "dms").mkdir()
+    rows = []
+    for k, L in enumerate((40, 90, 25)):
+        seq = synth.random_protein(L, 50 + k)
+        synth.write_dms_csv(str(tmp_path / "dms" / f"a{k}.csv"), seq, synth.sample_mutants(seq, 30, k, multi_frac=0.2))
+        rows.append((f"ASSAY{k}", f"a{k}.csv", seq))
+    synth.write_mapping_csv(str(tmp_path / "map.csv"), rows)
+    run_assays.main(["--model-location", str(tmp_path / "esm1v_tiny_a.pt"), "--model_type", "ESM1v", "--dms_mapping", str(tmp_path / "map.csv"),
+                     "--dms-input", str(tmp_path / "dms"), "--dms-output", str(tmp_path / "out")])
+    ost = O.load_state(st, "esm1v", torch.float64)
+    for k, (aid, fn, seq) in enumerate(rows):
+        got = pd.read_csv(tmp_path / "out" / f"{aid}.csv")
+        table = O.masked_marginal_table(ost, seq, "esm1v", 2, 2, dtype=torch.float64)
+        want = O.score_mutants(got["mutant"], seq, table)
+        assert np.abs(got["esm1v_tiny_a"].to_numpy() - want).max() < TOL
+        assert np.allclose(got["Ensemble_ESM1v"], got["esm1v_tiny_a"])
+    assert (tmp_path / "out" / "_run_assays_summary.csv").exists()
+
+
+def test_esm2_3b_true_size_rows_match_oracle():
+    """BASELINE config 3 architecture (ESM2 3B: 36 x 2560, 40 heads, ffn 10240, rotary) at true size on a short protein:
+    a few masked rows against the fp32 CPU oracle."""
+    arch = synth.ESM2_3B
+    st = synth.make_esm_state(arch, seed=2)
+    seq = synth.random_protein(48, 9)
+    pos = [1, 17, 48]
+    sc = scorer(arch, st, max_rows=4096)
+    got = sc.masked_marginal_table(seq, positions=pos).cpu().numpy()
+    sc.close()
+    ref = O.masked_marginal_table(O.load_state(st, "esm2"), seq, "esm2", arch.layers, arch.heads, positions=pos, batch=3)
+    err = np.abs(got[pos] - ref[pos].numpy()).max()
+    print(f"\\nESM2-3B f16x3 rows: max|dlogp| = {err:.2e}")
+    assert err < 5e-4
