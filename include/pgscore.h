@@ -139,6 +139,19 @@ typedef struct {
 } pg_attn_args;
 int pg_attention(const pg_attn_args* args, pg_stream stream);
 
+/* ---- MSA pre-processing for the Tranception retrieval prior ----
+ * pg_msa_cluster_neighbors replaces calc_num_cluster_members_nogaps[_parallel] (proteingym/utils/weights.py:114-216):
+ *   tokens [N, ld] uint8 (device), 0 = gap/invalid; min_matches[i] = smallest pair_matches for which the reference's float64 test
+ *   `pair_matches / L_non_gaps[i] > identity_threshold` holds; out_neighbors[i] = 1 + #{j != i : matches(i, j) >= min_matches[i]}
+ *   where matches counts positions with tokens[i,k] == tokens[j,k] != 0. Sequence weight = 1 / neighbors (weights.py:51-52).
+ * pg_msa_prior replaces the frequency computation of get_msa_prior (tranception/utils/msa_utils.py:118-128):
+ *   tokens_t [L, N] uint8 (device, column-major MSA; id >= vocab = letter outside the vocabulary), weights [N] fp64;
+ *   out [L, vocab] fp64 = (sum_i w_i [tok == k] + base_rate * W) / (sum_i w_i [tok in vocab] + vocab * base_rate * W). */
+int pg_msa_cluster_neighbors(const uint8_t* tokens, int64_t ld, int32_t N, int32_t L, const int32_t* min_matches,
+                             int32_t* out_neighbors, pg_stream stream);
+int pg_msa_prior(const uint8_t* tokens_t, const double* weights, int32_t N, int32_t L, int32_t vocab, double base_rate, double* out,
+                 pg_stream stream);
+
 /* Launch accounting and per-category device timing (bench.py's roofline leg).
  * pg_launch_count: kernels launched by this library since load. pg_profile_begin/end: CUDA-event pairs are recorded on
  * the launching stream around every kernel; _end (after the caller synchronised) returns summed ms and scope counts

@@ -236,3 +236,58 @@ def score_mutants(st, DMS_data, target_seq, layers, heads, n_ctx=1024, scoring_m
                            columns=[col, "avg_score_L_to_R", "avg_score_R_to_L", "avg_score"] if scoring_mirror else [col, "avg_score_L_to_R", "avg_score"])
         out = pd.concat([out, row], ignore_index=True)
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# MSA pre-processing (retrieval prior + sequence weights) — numpy restatements
+def msa_prior(msa: dict, MSA_start, MSA_end, len_target_seq, weights=None, filter_MSA=True):
+    """get_msa_prior, aggregate_substitution branch (tranception/utils/msa_utils.py:63-138). ``msa``: name -> aligned upper-case string."""
+    vocab = {t: i for i, t in enumerate(VOCAB)}
+    msa = dict(msa)
+    def one_hot(s):
+        o = np.zeros((len(s), len(vocab)))
+        for j, c in enumerate(s):
+            if c in vocab:
+                o[j, vocab[c]] = 1.0
+        return o.flatten()
+    if filter_MSA:
+        names = list(msa.keys())
+        ref = one_hot(msa[names[0]])
+        for n in names:
+            if np.dot(ref, one_hot(msa[n])) / np.dot(ref, ref) < 0.2:
+                del msa[n]
+    if weights is not None:
+        for n in list(msa.keys()):
+            if n not in weights:
+                del msa[n]
+        w = [weights[n] for n in msa]
+    else:
+        w = [1] * len(msa)
+    oh = np.zeros((len(msa), MSA_end - MSA_start, len(vocab)))
+    for i, n in enumerate(msa):
+        for j, c in enumerate(msa[n]):
+            if c in vocab:
+                oh[i, j, vocab[c]] = 1.0
+    w = np.expand_dims(np.array(w), axis=(1, 2))
+    weighted = (oh + 1e-5) * w
+    norm = np.tile(weighted.sum(axis=-1).sum(axis=0).reshape(-1, 1), (1, len(vocab)))
+    prior = np.zeros((len_target_seq, len(vocab)))
+    prior[MSA_start:MSA_end, :] = weighted.sum(axis=0) / norm
+    return prior
+
+
+def cluster_weights(matrix, identity_threshold, empty_value=0):
+    """calc_weights_fast + calc_num_cluster_members_nogaps (proteingym/utils/weights.py:13-53, :114-160)."""
+    matrix = np.asarray(matrix)
+    empty = np.all(matrix == empty_value, axis=1)
+    act = matrix[~empty]
+    N, L = act.shape
+    Lng = 1.0 * L - np.sum(act == empty_value, axis=1)
+    nn = np.ones(N)
+    for i in range(N):
+        eq = (act == act[i]) & (act[i] != empty_value)
+        pm = eq.sum(axis=1)
+        nn[i] += np.sum((pm / Lng[i] > identity_threshold) & (np.arange(N) != i))
+    out = np.zeros(matrix.shape[0])
+    out[~empty] = 1.0 / nn
+    return out

@@ -1,7 +1,7 @@
 """Drop-in for ``proteingym/baselines/tranception/score_tranception_proteingym.py`` (same flags, same output CSV:
 ``mutated_sequence, avg_score_L_to_R, avg_score_R_to_L, avg_score``; reference lines :18-45 flags, :57-77 DMS resolution,
-:105-122 scoring + CSV). Inference-time retrieval needs the MSA prior, whose construction (utils/msa_utils.py:63-138) is a
-"next" row of SURVEY.md §8f: pass a precomputed ``[L_full, 25]`` log-prior with the additive flag ``--MSA_log_prior_npy``.
+:105-122 scoring + CSV). Inference-time retrieval for substitutions builds the unweighted MSA prior on the GPU (msa_prior.py, utils/msa_utils.py:63-138);
+EVE sequence-weight files (MSA_processing) are not reproduced: pass a precomputed ``[L_full, 25]`` log-prior with ``--MSA_log_prior_npy``.
 Additive flags: --precision, --device, --MSA_log_prior_npy."""
 from __future__ import annotations
 
@@ -71,9 +71,18 @@ def main(argv=None):
     if args.inference_time_retrieval:
         if args.indel_mode:
             raise NotImplementedError("retrieval for indels re-aligns the MSA with Clustal Omega (out of scope)")
-        if not args.MSA_log_prior_npy:
-            raise NotImplementedError("inference-time retrieval needs --MSA_log_prior_npy (MSA prior construction is a 'next' row)")
-        log_prior = np.load(args.MSA_log_prior_npy)
+        if args.MSA_log_prior_npy:
+            log_prior = np.load(args.MSA_log_prior_npy)
+        else:
+            if args.MSA_weights_folder is not None:
+                raise NotImplementedError("EVE sequence-weight files need MSA_processing (not reproduced); pass --MSA_log_prior_npy "
+                                          "or omit --MSA_weights_folder for the unweighted prior")
+            from proteingym_b200.msa_prior import msa_log_prior
+            if args.DMS_reference_file_path:
+                msa_file = args.MSA_folder + os.sep + mapping["MSA_filename"][args.DMS_index]
+            else:
+                msa_file = args.MSA_folder + os.sep + args.MSA_filename
+            log_prior = msa_log_prior(msa_file, MSA_start, MSA_end, len(target_seq), device=args.device)  # model_pytorch.py:660-671
     config, state = load_tranception_checkpoint(args.checkpoint)
     scorer = TranceptionScorer(config, state, precision=args.precision, device=args.device)
     if not os.path.isdir(args.output_scores_folder):

@@ -275,3 +275,28 @@ def random_indels(seq: str, n: int, seed: int, max_len: int = 4):
         if s != seq and len(s) > 2:
             out.add(s)
     return sorted(out)
+
+
+def synthetic_msa(target_seq: str, n: int, seed: int, sub_rate=(0.05, 0.9), gap_rate=0.1):
+    """name -> aligned sequence (a2m-like, upper case, '-' gaps, occasional 'X'); first entry is the target itself."""
+    rng = np.random.RandomState(seed)
+    msa = {">target/1-%d" % len(target_seq): target_seq}
+    for i in range(n - 1):
+        r = rng.uniform(*sub_rate)
+        s = list(target_seq)
+        for j in range(len(s)):
+            u = rng.rand()
+            if u < gap_rate:
+                s[j] = "-"
+            elif u < gap_rate + r:
+                s[j] = AA20[rng.randint(0, 20)] if rng.rand() > 0.02 else "X"
+        msa[">seq%d" % i] = "".join(s)
+    return msa
+
+
+def write_a2m(path: str, msa: dict, width: int = 60):
+    with open(path, "w") as fh:
+        for n, s in msa.items():
+            fh.write(n + "\n")
+            for k in range(0, len(s), width):
+                fh.write(s[k:k + width] + "\n")

@@ -105,3 +105,31 @@ def test_true_size_tranception_l_properties():
     lp2 = sc2.sequence_logprobs([seq, seq[:50], seq])
     sc2.close()
     assert np.array_equal(lp1, lp2)
+
+
+def test_msa_prior_and_cluster_weights_kernels_match_reference(tmp_path):
+    """pg_msa_prior / pg_msa_cluster_neighbors against the unmodified reference functions' outputs (oracle/gen_golden_msa.py)
+    and, at a larger size, against the numpy oracle."""
+    from proteingym_b200 import msa_prior as MP
+    meta = json.load(open(os.path.join(GOLDEN, "msa_meta.json")))
+    msa = synth.synthetic_msa(meta["target_seq"], meta["msa_n"], seed=meta["msa_seed"])
+    synth.write_a2m(str(tmp_path / "m.a2m"), msa)
+    got = MP.msa_prior(MP.read_a2m(str(tmp_path / "m.a2m")), meta["MSA_start"], meta["MSA_end"], meta["len_target_seq"])
+    ref = np.load(os.path.join(GOLDEN, "msa_prior_reference.npy"))
+    assert np.abs(got - ref).max() < 1e-14
+    lp = MP.msa_log_prior(str(tmp_path / "m.a2m"), meta["MSA_start"], meta["MSA_end"], meta["len_target_seq"])
+    assert lp.dtype == np.float32 and np.isneginf(lp[0]).all() and np.isfinite(lp[meta["MSA_start"]:meta["MSA_end"]]).all()
+    g = np.load(os.path.join(GOLDEN, "msa_weights_reference.npz"))
+    w = MP.cluster_weights(g["matrix"].astype(np.int64), meta["identity_threshold"])
+    assert np.array_equal(w, g["weights"])
+    # weighted prior + bigger, ragged-size problems vs the numpy oracle (bit-exact integer counts)
+    seq = synth.random_protein(333, 3)
+    big = synth.synthetic_msa(seq, 700, seed=9)
+    names = list(big)
+    wts = {n: 0.05 + (i % 7) / 7.0 for i, n in enumerate(names) if i % 5}
+    a = MP.msa_prior(big, 0, 333, 333, weights=wts)
+    b = TO.msa_prior(big, 0, 333, 333, weights=wts)
+    assert np.abs(a - b).max() < 1e-13
+    mat = MP.encode([big[n] for n in names], unknown=0).astype(np.int64)  # '-' and 'X' -> 0 = gap
+    for thr in (0.8, 0.99, 0.3):
+        assert np.array_equal(MP.cluster_weights(mat, thr), TO.cluster_weights(mat, thr)), thr

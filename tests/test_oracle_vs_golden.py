@@ -112,3 +112,18 @@ def test_tranception_slopes_match_reference_list():
     from oracle import tranception_oracle as TO
     assert TO.get_slopes(20) == [0.25, 0.0625, 0.015625, 0.00390625, 0.5] * 4  # SURVEY.md hard-parts note; model_pytorch.py:59-71
     assert len(TO.get_slopes(12)) == 12 and TO.get_slopes(4) == [2 ** -8] * 4
+
+
+def test_msa_prior_and_weights_oracle_match_reference():
+    import json, os
+    from conftest import GOLDEN
+    from oracle import tranception_oracle as TO
+    from proteingym_b200 import synth
+    meta = json.load(open(os.path.join(GOLDEN, "msa_meta.json")))
+    msa = synth.synthetic_msa(meta["target_seq"], meta["msa_n"], seed=meta["msa_seed"])
+    prior = TO.msa_prior(msa, meta["MSA_start"], meta["MSA_end"], meta["len_target_seq"])
+    ref = np.load(os.path.join(GOLDEN, "msa_prior_reference.npy"))
+    assert prior.shape == ref.shape and np.abs(prior - ref).max() < 1e-15
+    g = np.load(os.path.join(GOLDEN, "msa_weights_reference.npz"))
+    w = TO.cluster_weights(g["matrix"].astype(np.int64), meta["identity_threshold"])
+    assert np.array_equal(w, g["weights"]) and w[5] == 0
