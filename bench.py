@@ -67,6 +67,26 @@ def algorithmic_flops(arch, T, P):
     return P * (lin + att + head), P * lin
 
 
+def secondary(cats, arch, T, P, steps, precision):
+    """Rooflines of the non-dominant kernels from the same event timings: LayerNorm against measured HBM bandwidth
+    (algorithmic bytes: read 4d, write 2d per operand plane, per row), attention as algorithmic TFLOP/s (4*T^2*d per layer)."""
+    out = {}
+    npl = 2 if precision == "f16x3" else 1
+    rows = P * T
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        hbm = 6650.0
+    if "layernorm" in cats and cats["layernorm"]["ms"] > 0:
+        byts = 2 * arch.layers * rows * (4 * arch.embed_dim + 2 * arch.embed_dim * npl) * steps
+        gbs = byts / (cats["layernorm"]["ms"] / 1e3) / 1e9
+        out["layernorm"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}
+    if "attention" in cats and cats["attention"]["ms"] > 0:
+        fl = arch.layers * P * 4.0 * T * T * arch.embed_dim * steps
+        out["attention"] = {"bound": "tensor+mufu", "achieved": fl / (cats["attention"]["ms"] / 1e3) / 1e12, "unit": "TFLOP/s (algorithmic)"}
+    return out
+
+
 def make_assay(i, L, n_mut):
     from proteingym_b200 import synth
     seq = synth.random_protein(L, seed=i)
@@ -321,7 +341,8 @@ def main():
             "whole_step": {"algorithmic_tflop_per_step": f_total / 1e12,
                            "achieved_per_gpu": f_total * a.steps / 1e12 / (ms_total / 1e3),
                            "frac_of_peak": f_total * a.steps / 1e12 / (ms_total / 1e3) / sustained},
-            "kernel_ms_in_timed_region": cats}
+            "kernel_ms_in_timed_region": cats,
+            "secondary": secondary(cats, arch, T, P, a.steps, precision)}
         scorer.close()
         del scorer, devs
         torch.cuda.empty_cache()
@@ -349,7 +370,7 @@ def main():
         out["other_precision_mode"] = {"precision_mode": other, "dtype": DT[other], "value": other_res["value"], "unit": "mutants/s",
                                        "ms_per_step": other_res["ms_per_step"], "clocks": other_res["clocks"],
                                        "roofline": {k: other_res["roofline"][k] for k in ("achieved", "frac", "issued_tflops", "issued_frac",
-                                                                                            "whole_step", "kernel_ms_in_timed_region")}}
+                                                                                            "whole_step", "kernel_ms_in_timed_region", "secondary")}}
 
     if not a.no_cpu_baseline and world == 1:
         log("cpu baseline")
