@@ -255,8 +255,10 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
           tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL0 + buf * KT + g * 64 + c * 32, r);
           tmem_ld_wait();
           if (plain && valid - c * 32 >= 32) {
+            float m4[4] = {m, -INFINITY, -INFINITY, -INFINITY};  // four independent chains instead of one 32-deep FMNMX chain
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
+            m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
@@ -293,12 +295,14 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
         for (int c = 0; c < 2; ++c) {
           if (c * 32 < ncols) {
             if (plain && valid - c * 32 >= 32) {
+              float l4[4] = {0.f, 0.f, 0.f, 0.f};  // break the 32-deep FADD dependency chain (fixed association -> deterministic)
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const float e = ex2_approx(fmaf(__uint_as_float(r[c][i]), LOG2E, -m2));
-                l += e;
+                l4[i & 3] += e;
                 r[c][i] = __float_as_uint(e);
               }
+              l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {

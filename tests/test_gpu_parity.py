@@ -453,3 +453,17 @@ def test_esm2_3b_true_size_rows_match_oracle():
     serr = np.abs(ds(got) - ds(ref.numpy())).max()
     print(f"\\nESM2-3B f16x3: max|dlogp| = {err:.2e}, max|d(score term)| = {serr:.2e}")
     assert serr < TOL and err < 3e-3
+
+
+@pytest.mark.parametrize("L", [1, 2, 1022, 1023])
+def test_boundary_lengths_vs_oracle(L):
+    """L + 2 = 3, 4 (tiny), 1024 (largest un-windowed input) and 1025 (first windowed one: every row's window drops one token)."""
+    arch = synth.EsmArch("esm1v", 1, 64, 1, 64)
+    st = synth.make_esm_state(arch, seed=12)
+    seq = synth.random_protein(L, L)
+    pos = sorted({1, max(1, L // 2), L})
+    sc = scorer(arch, st, max_rows=8192)
+    got = sc.masked_marginal_table(seq, positions=pos).cpu().numpy()
+    sc.close()
+    ref = O.masked_marginal_table(O.load_state(st, "esm1v", torch.float64), seq, "esm1v", 1, 1, dtype=torch.float64, positions=pos)
+    assert np.abs(got[pos] - ref[pos].numpy()).max() < 2e-4
