@@ -130,6 +130,9 @@ struct pg_handle_s {
   // Tranception
   __half* qkv2 = nullptr;
   float *tok_logp = nullptr, *slopes = nullptr;
+  // compact buffers for the pruned last layer (one row per sequence)
+  float* xc = nullptr;
+  __half *cabuf = nullptr, *cfbuf = nullptr;
 };
 
 namespace pg {
@@ -159,8 +162,10 @@ __global__ void row_select_kernel(const int32_t* positions, const int32_t* win_s
   sel[i] = tok - (win_start ? win_start[gp] : 0);
 }
 
+// `emit_rows` (device, [Bc]) = the one row per sequence the caller will read, or null when every row is needed. When given,
+// the last layer runs its attention-output / out_proj / LayerNorm / MLP for those rows only and leaves them in h->xc [Bc, d].
 int forward_rows(pg_handle h, const int32_t* tokens, int n_tokens, const int32_t* positions, const int32_t* win_start,
-                 int p_offset, int Bc, int T, cudaStream_t s) {
+                 int p_offset, int Bc, int T, cudaStream_t s, const int32_t* emit_rows = nullptr) {
   const pg_model_desc& D = h->desc;
   const int d = D.embed_dim, f = D.ffn_dim, np = h->np, nseg = (np == 2) ? 3 : 1;
   const int rows = Bc * T;
@@ -184,6 +189,32 @@ int forward_rows(pg_handle h, const int32_t* tokens, int n_tokens, const int32_t
     g.rot_cos = h->rot_cos; g.rot_sin = h->rot_sin; g.rot_T = T; g.rot_dim = d;
     { ProfScope ps(CAT_GEMM_QKV, s); rc = launch_gemm(g, s); }
     if (rc) return rc;
+    if (emit_rows && l == D.layers - 1) {
+      // exact pruning of the final layer: one query row per sequence from here on
+      const int64_t lda_c = static_cast<int64_t>(d) * np, ldf_c = static_cast<int64_t>(f) * np;
+      { ProfScope ps(CAT_ATTN, s, 2);
+        rc = launch_attn_single_query(h->qkv, static_cast<int64_t>(3 * d) * np, np == 2 ? 3 * d : 0, emit_rows, Bc, T, D.heads, h->cabuf,
+                                      lda_c, np == 2 ? d : 0, s);
+        if (!rc) rc = launch_gather_rows(h->x, emit_rows, Bc, T, d, h->xc, s); }
+      if (rc) return rc;
+      g = GemmLaunch{};
+      g.a = h->cabuf; g.lda = lda_c; g.w = L.wo; g.ldw = lda_c; g.bias = L.bo;
+      g.M = Bc; g.N = d; g.K = d; g.nseg = nseg; g.epi = 2; g.resid = h->xc; g.ldr = d;
+      { ProfScope ps(CAT_GEMM_OUT, s); rc = launch_gemm(g, s); }
+      if (rc) return rc;
+      { ProfScope ps(CAT_LN, s); rc = launch_layernorm_f16(h->xc, d, L.ln2g, L.ln2b, Bc, d, h->cabuf, lda_c, np == 2 ? d : 0, s); }
+      if (rc) return rc;
+      g = GemmLaunch{};
+      g.a = h->cabuf; g.lda = lda_c; g.w = L.w1; g.ldw = lda_c; g.bias = L.b1;
+      g.M = Bc; g.N = f; g.K = d; g.nseg = nseg; g.epi = 1; g.out = h->cfbuf; g.ldo = ldf_c; g.out_lo_off = np == 2 ? f : 0;
+      { ProfScope ps(CAT_GEMM_FC1, s); rc = launch_gemm(g, s); }
+      if (rc) return rc;
+      g = GemmLaunch{};
+      g.a = h->cfbuf; g.lda = ldf_c; g.w = L.w2; g.ldw = ldf_c; g.bias = L.b2;
+      g.M = Bc; g.N = d; g.K = f; g.nseg = nseg; g.epi = 2; g.resid = h->xc; g.ldr = d;
+      { ProfScope ps(CAT_GEMM_FC2, s); rc = launch_gemm(g, s); }
+      return rc;
+    }
     AttnLaunch a{};
     a.qkv = h->qkv; a.ld = static_cast<int64_t>(3 * d) * np; a.lo_off = np == 2 ? 3 * d : 0;
     a.out = h->abuf; a.ldo = static_cast<int64_t>(d) * np; a.out_lo_off = np == 2 ? d : 0;
@@ -366,6 +397,9 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
   A(&h->hs_a, static_cast<size_t>(h->head_cap) * d);
   A(&h->hs_b, static_cast<size_t>(h->head_cap) * d);
   A(&h->row_sel, h->head_cap);
+  A(&h->xc, static_cast<size_t>(h->head_cap) * d);
+  A(&h->cabuf, static_cast<size_t>(h->head_cap) * d * np);
+  A(&h->cfbuf, static_cast<size_t>(h->head_cap) * f * np);
   if (rc) {
     std::string m = h->err;
     pg_destroy(h);
@@ -514,12 +548,12 @@ int pg_masked_marginals(pg_handle h, const int32_t* tokens, int32_t n_tokens, co
   if (per > h->head_cap) per = h->head_cap;
   for (int p0 = 0; p0 < P; p0 += static_cast<int>(per)) {
     const int Bc = (P - p0) < per ? (P - p0) : static_cast<int>(per);
-    int rc = forward_rows(h, tokens, n_tokens, positions, win_start, p0, Bc, T, s);
+    row_select_kernel<<<(Bc + 255) / 256, 256, 0, s>>>(positions, win_start, out_row, p0, Bc, h->row_sel);
+    int rc = forward_rows(h, tokens, n_tokens, positions, win_start, p0, Bc, T, s, h->row_sel);
     if (rc) return fail(h, rc, tls_error());
     ProfScope ps(CAT_HEAD, s, 4);
-    row_select_kernel<<<(Bc + 255) / 256, 256, 0, s>>>(positions, win_start, out_row, p0, Bc, h->row_sel);
     HeadLaunch hl = head_args(h, T);
-    hl.row_in_seq = h->row_sel; hl.P = Bc; hl.all_rows = 0;
+    hl.x = h->xc; hl.P = Bc; hl.all_rows = 1;  // the pruned last layer left exactly the rows to emit, compacted
     hl.out = out_logprobs + static_cast<long long>(p0) * h->desc.vocab;
     rc = launch_head(hl, s);
     if (rc) return fail(h, rc, tls_error());

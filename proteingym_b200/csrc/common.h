@@ -99,6 +99,9 @@ int launch_attention_tc(const AttnLaunch& a, cudaStream_t s);  // tcgen05/TMEM a
 }  // namespace pg
 
 namespace pg {
+int launch_attn_single_query(const __half* qkv, int64_t ld, int64_t lo_off, const int32_t* row_sel, int B, int T, int heads,
+                             __half* out, int64_t ldo, int64_t out_lo_off, cudaStream_t s);
+int launch_gather_rows(const float* x, const int32_t* row_sel, int B, int T, int d, float* xc, cudaStream_t s);
 int launch_gather_embed(const int32_t* ids, const float* wte, long long rows, int d, int vocab, float* x, cudaStream_t s);
 int launch_qkv_conv(const __half* in, __half* out, int64_t ld, int64_t lo_off, int B, int T, int heads, const float* taps,
                     float qscale, cudaStream_t s);

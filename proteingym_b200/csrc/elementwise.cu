@@ -246,7 +246,99 @@ __global__ void score_kernel(const float* __restrict__ table, int n_rows, int vo
   out[m] = s;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Last-layer pruning (exact): only the masked row of each copy feeds the LM head, so in the final layer the attention
+// output, out_proj, LayerNorm and MLP are needed for ONE query row per sequence. K and V still come
+// from all rows. One warp per (sequence, head); fp32 SIMT arithmetic on the fp16 hi(+lo) q/k/v.
+__global__ void __launch_bounds__(128) attn_single_query_kernel(const __half* __restrict__ qkv, long long ld, long long lo_off,
+                                                                const int32_t* __restrict__ row_sel, int B, int T, int heads,
+                                                                __half* __restrict__ out, long long ldo, long long out_lo_off) {
+  const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (wid >= B * heads) return;
+  const int b = wid / heads, h = wid % heads, lane = threadIdx.x & 31;
+  const int d = heads * 64;
+  const __half* base = qkv + static_cast<long long>(b) * T * ld;
+  auto load64 = [&](const __half* p, float (&v)[64]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 hv = *reinterpret_cast<const uint4*>(p + c * 8);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&hv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h2[i]);
+        v[c * 8 + 2 * i] = f.x; v[c * 8 + 2 * i + 1] = f.y;
+      }
+      if (lo_off > 0) {
+        const uint4 lv = *reinterpret_cast<const uint4*>(p + lo_off + c * 8);
+        const __half2* l2 = reinterpret_cast<const __half2*>(&lv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(l2[i]);
+          v[c * 8 + 2 * i] += f.x; v[c * 8 + 2 * i + 1] += f.y;
+        }
+      }
+    }
+  };
+  float q[64];
+  load64(base + static_cast<long long>(row_sel[b]) * ld + h * 64, q);
+  float m = -INFINITY, l = 0.f, acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    float kv[64];
+    load64(base + static_cast<long long>(j) * ld + d + h * 64, kv);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) s = fmaf(q[i], kv[i], s);
+    const float mn = fmaxf(m, s);
+    const float corr = __expf(m - mn), pj = __expf(s - mn);
+    m = mn;
+    l = l * corr + pj;
+    load64(base + static_cast<long long>(j) * ld + 2 * d + h * 64, kv);
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = fmaf(acc[i], corr, pj * kv[i]);
+  }
+  const float mw = warp_max(m);
+  const float sc = (m == -INFINITY) ? 0.f : __expf(m - mw);  // lanes that saw no key (T < 32) contribute nothing
+  l = warp_sum(l * sc);
+  const float rl = 1.f / l;
+  __half* orow = out + static_cast<long long>(b) * ldo + h * 64;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) {
+    const float v = warp_sum(acc[i] * sc) * rl;
+    if (lane == (i & 31)) {
+      __half hi, lo;
+      split_hi_lo(v, hi, lo);
+      orow[i] = hi;
+      if (out_lo_off > 0) orow[out_lo_off + i] = lo;
+    }
+  }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_sel, int T, int d,
+                                   float* __restrict__ xc) {
+  const int b = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(x + (static_cast<long long>(b) * T + row_sel[b]) * d);
+  float4* dst = reinterpret_cast<float4*>(xc + static_cast<long long>(b) * d);
+  for (int j = threadIdx.x; j < d / 4; j += blockDim.x) dst[j] = src[j];
+}
+
 }  // namespace
+
+int launch_attn_single_query(const __half* qkv, int64_t ld, int64_t lo_off, const int32_t* row_sel, int B, int T, int heads,
+                             __half* out, int64_t ldo, int64_t out_lo_off, cudaStream_t s) {
+  if (B <= 0) return PG_OK;
+  attn_single_query_kernel<<<(B * heads + 3) / 4, 128, 0, s>>>(qkv, ld, lo_off, row_sel, B, T, heads, out, ldo, out_lo_off);
+  PG_CUDA_OK(cudaGetLastError());
+  return PG_OK;
+}
+
+int launch_gather_rows(const float* x, const int32_t* row_sel, int B, int T, int d, float* xc, cudaStream_t s) {
+  if (B <= 0) return PG_OK;
+  gather_rows_kernel<<<B, 128, 0, s>>>(x, row_sel, T, d, xc);
+  PG_CUDA_OK(cudaGetLastError());
+  return PG_OK;
+}
 
 int launch_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int rows, int d, __half* out,
                          int64_t ldo, int64_t lo_off, cudaStream_t s) {
