@@ -22,46 +22,46 @@ if __package__ in (None, ""):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+# (flags, kwargs) — the reference parser's option names, types, defaults, nargs and choices (checked one by one against a dump of
+# the reference's create_parser() in tests/golden/esm_cli_flags.json); help texts are ours.
+_FLAGS = [
+    (("--model_type",), dict(type=str, default="MSA_transformer", nargs="+", help="ESM1v | ESM1b | ESM2 (MSA_transformer is not handled here)")),
+    (("--model-location",), dict(type=str, nargs="+", help="one or more local fair-esm .pt checkpoints; one output column each")),
+    (("--sequence",), dict(type=str, help="wild-type sequence (filled from the mapping file when --dms_index is given)")),
+    (("--dms-input",), dict(type=pathlib.Path, help="DMS CSV, or the folder holding the DMS CSVs when --dms_index is given")),
+    (("--dms_index",), dict(type=int, help="row of the assay in --dms_mapping")),
+    (("--dms_mapping",), dict(type=str, help="reference file (DMS_substitutions.csv)")),
+    (("--mutation-col",), dict(type=str, default="mutant", help="column with mutants written like A24G or A24G:T30S")),
+    (("--dms-output",), dict(type=pathlib.Path, help="folder for <DMS_id>.csv")),
+    (("--offset-idx",), dict(type=int, default=1, help="position of the first residue in the mutant numbering")),
+    (("--scoring-strategy",), dict(type=str, default="wt-marginals", choices=["wt-marginals", "pseudo-ppl", "masked-marginals"], help="")),
+    (("--msa-path",), dict(type=pathlib.Path, help="(MSA Transformer only)")),
+    (("--msa-sampling-strategy",), dict(type=str, default="sequence-reweighting", help="(MSA Transformer only)")),
+    (("--msa-samples",), dict(type=int, default=400, help="(MSA Transformer only)")),
+    (("--msa-weights-folder",), dict(type=str, default=None, help="(MSA Transformer only)")),
+    (("--seeds",), dict(type=int, default=1, nargs="+", help="(MSA Transformer only)")),
+    (("--filter-msa",), dict(action="store_true", help="(MSA Transformer only)")),
+    (("--hhfilter-min-cov",), dict(type=int, default=75, help="(MSA Transformer only)")),
+    (("--hhfilter-max-seq-id",), dict(type=int, default=90, help="(MSA Transformer only)")),
+    (("--hhfilter-min-seq-id",), dict(type=int, default=0, help="(MSA Transformer only)")),
+    (("--path-to-hhfilter",), dict(type=str, default="/n/groups/marks/software/hhsuite/hhsuite-3.3.0", help="(MSA Transformer only)")),
+    (("--scoring-window",), dict(type=str, default="optimal", help="long sequences: optimal (1024-token window per position) | overlapping")),
+    (("--overwrite-prior-scores",), dict(action="store_true", help="accepted for compatibility")),
+    (("--target_seq",), dict(default=None, type=str, help="wild type when no mapping file is used")),
+    (("--weight_file_name",), dict(default=None, type=str, help="(MSA Transformer only)")),
+    (("--MSA_start",), dict(default=None, type=int, help="(MSA Transformer only)")),
+    (("--MSA_end",), dict(default=None, type=int, help="(MSA Transformer only)")),
+    (("--nogpu",), dict(action="store_true", help="rejected: this scorer is the GPU path")),
+]
+
+
 def create_parser():
-    """Flag surface of the reference parser (:100-238); defaults are identical."""
-    p = argparse.ArgumentParser(description="Label a deep mutational scan with predictions from an ensemble of ESM-1v models.")
-    p.add_argument("--model_type", type=str, help="MSA_transformer Vs ESM1v Vs ESM1b", default="MSA_transformer", nargs="+")
-    p.add_argument("--model-location", type=str, nargs="+",
-                   help="PyTorch model file OR name of pretrained model to download (see README for models)")
-    p.add_argument("--sequence", type=str, help="Base sequence to which mutations were applied")
-    p.add_argument("--dms-input", type=pathlib.Path, help="CSV file containing the deep mutational scan")
-    p.add_argument("--dms_index", type=int, help="Index of DMS in mapping file")
-    p.add_argument("--dms_mapping", type=str, help="Location of DMS_mapping")
-    p.add_argument("--mutation-col", type=str, default="mutant",
-                   help="column in the deep mutational scan labeling the mutation as 'AiB'")
-    p.add_argument("--dms-output", type=pathlib.Path,
-                   help="Output file containing the deep mutational scan along with predictions")
-    p.add_argument("--offset-idx", type=int, default=1, help="Offset of the mutation positions in `--mutation-col`")
-    p.add_argument("--scoring-strategy", type=str, default="wt-marginals",
-                   choices=["wt-marginals", "pseudo-ppl", "masked-marginals"], help="")
-    p.add_argument("--msa-path", type=pathlib.Path, help="path to MSA (required for MSA Transformer)")
-    p.add_argument("--msa-sampling-strategy", type=str, default="sequence-reweighting",
-                   help="Strategy to sample sequences from MSA [sequence-reweighting|random|first_x_rows]")
-    p.add_argument("--msa-samples", type=int, default=400, help="number of sequences to randomly sample from the MSA")
-    p.add_argument("--msa-weights-folder", type=str, default=None,
-                   help="Folder with weights to sample MSA sequences in 'sequence-reweighting' scheme")
-    p.add_argument("--seeds", type=int, default=1, help="Random seed used during training", nargs="+")
-    p.add_argument("--filter-msa", action="store_true", help="Whether to use hhfilter to filter input MSA before sampling")
-    p.add_argument("--hhfilter-min-cov", type=int, default=75, help="minimum coverage with query (%%)")
-    p.add_argument("--hhfilter-max-seq-id", type=int, default=90, help="maximum pairwise identity (%%)")
-    p.add_argument("--hhfilter-min-seq-id", type=int, default=0, help="minimum sequence identity with query (%%)")
-    p.add_argument("--path-to-hhfilter", type=str, default="/n/groups/marks/software/hhsuite/hhsuite-3.3.0",
-                   help="Path to hhfilter binaries")
-    p.add_argument("--scoring-window", type=str, default="optimal", help="Approach to handle long sequences [optimal|overlapping]")
-    p.add_argument("--overwrite-prior-scores", action="store_true", help="Whether to overwrite prior scores in the dataframe")
-    p.add_argument("--target_seq", default=None, type=str, help="WT sequence mutated in the assay")
-    p.add_argument("--weight_file_name", default=None, type=str)
-    p.add_argument("--MSA_start", default=None, type=int)
-    p.add_argument("--MSA_end", default=None, type=int)
-    p.add_argument("--nogpu", action="store_true", help="Do not use GPU even if available")
+    p = argparse.ArgumentParser(description="ESM masked-marginal / wt-marginal / pseudo-ppl DMS scoring on B200 (compute_fitness.py drop-in)")
+    for flags, kw in _FLAGS:
+        p.add_argument(*flags, **kw)
     # additive (not in the reference)
     p.add_argument("--precision", default="f16x3", choices=["f16x3", "f16"],
-                   help="tensor-core operand precision: f16x3 meets the 1e-3 parity bar (default); f16 is ~2x faster")
+                   help="tensor-core operand precision: f16x3 meets the 1e-3 parity bar (default); f16 is ~2.4x faster")
     p.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
     return p
 

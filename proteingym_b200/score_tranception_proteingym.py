@@ -16,34 +16,41 @@ if __package__ in (None, ""):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+# option names, types and defaults of the reference parser (score_tranception_proteingym.py:18-45); help texts are ours
+_FLAGS = [
+    ("--checkpoint", dict(type=str, help="HF checkpoint folder (config.json + pytorch_model.bin)")),
+    ("--model_framework", dict(default="pytorch", type=str, help="accepted for compatibility")),
+    ("--batch_size_inference", dict(default=20, type=int, help="accepted for compatibility (batching is sized by the workspace)")),
+    ("--DMS_reference_file_path", dict(default=None, type=str, help="reference file listing the assays")),
+    ("--DMS_index", dict(default=0, type=int, help="row of the assay in the reference file")),
+    ("--target_seq", dict(default=None, type=str, help="wild type when no reference file is used")),
+    ("--DMS_file_name", dict(default=None, type=str, help="assay CSV when no reference file is used")),
+    ("--MSA_filename", dict(default=None, type=str, help="a2m alignment of the wild type (retrieval)")),
+    ("--MSA_weight_file_name", dict(default=None, type=str, help="EVE sequence weights (not supported, see module docstring)")),
+    ("--MSA_start", dict(default=None, type=int, help="first position covered by the MSA, 1-based")),
+    ("--MSA_end", dict(default=None, type=int, help="last position covered by the MSA, 1-based")),
+    ("--DMS_data_folder", dict(type=str, help="folder with the assay CSVs")),
+    ("--output_scores_folder", dict(default="./", type=str, help="folder for <DMS_id>.csv")),
+    ("--deactivate_scoring_mirror", dict(action="store_true", help="score left-to-right only")),
+    ("--indel_mode", dict(action="store_true", help="rows are full mutated sequences (insertions / deletions)")),
+    ("--scoring_window", dict(default="optimal", type=str, help="optimal | sliding, for sequences longer than n_ctx - 2")),
+    ("--num_workers", dict(default=10, type=int, help="accepted for compatibility")),
+    ("--inference_time_retrieval", dict(action="store_true", help="fuse the MSA prior into the token log-probabilities")),
+    ("--retrieval_inference_weight", dict(default=0.6, type=float, help="alpha of the fusion")),
+    ("--MSA_folder", dict(default=".", type=str, help="folder with the MSAs")),
+    ("--MSA_weights_folder", dict(default=None, type=str, help="folder with EVE weights (not supported)")),
+    ("--clustal_omega_location", dict(default=None, type=str, help="(indel retrieval only; not supported)")),
+]
+
+
 def create_parser():
-    parser = argparse.ArgumentParser(description='Tranception scoring')
-    parser.add_argument('--checkpoint', type=str, help='Path of Tranception model checkpoint')
-    parser.add_argument('--model_framework', default='pytorch', type=str, help='Underlying framework [pytorch|JAX]')
-    parser.add_argument('--batch_size_inference', default=20, type=int, help='Batch size for inference')
-    parser.add_argument('--DMS_reference_file_path', default=None, type=str, help='Path to reference file with list of DMS to score')
-    parser.add_argument('--DMS_index', default=0, type=int, help='Index of DMS assay in reference file')
-    parser.add_argument('--target_seq', default=None, type=str, help='Full wild type sequence that is mutated in the DMS asssay')
-    parser.add_argument('--DMS_file_name', default=None, type=str, help='Name of DMS assay file')
-    parser.add_argument('--MSA_filename', default=None, type=str, help='Name of MSA (eg., a2m) file constructed on the wild type sequence')
-    parser.add_argument('--MSA_weight_file_name', default=None, type=str, help='Weight of sequences in the MSA (optional)')
-    parser.add_argument('--MSA_start', default=None, type=int, help='Sequence position that the MSA starts at (1-indexing)')
-    parser.add_argument('--MSA_end', default=None, type=int, help='Sequence position that the MSA ends at (1-indexing)')
-    parser.add_argument('--DMS_data_folder', type=str, help='Path to folder that contains all DMS assay datasets')
-    parser.add_argument('--output_scores_folder', default='./', type=str, help='Name of folder to write model scores to')
-    parser.add_argument('--deactivate_scoring_mirror', action='store_true', help='Whether to deactivate sequence scoring from both directions (Left->Right and Right->Left)')
-    parser.add_argument('--indel_mode', action='store_true', help='Flag to be used when scoring insertions and deletions. Otherwise assumes substitutions')
-    parser.add_argument('--scoring_window', default="optimal", type=str, help='Sequence window selection mode (when sequence length longer than model context size)')
-    parser.add_argument('--num_workers', default=10, type=int, help='Number of workers for model scoring data loader')
-    parser.add_argument('--inference_time_retrieval', action='store_true', help='Whether to perform inference-time retrieval')
-    parser.add_argument('--retrieval_inference_weight', default=0.6, type=float, help='Coefficient (alpha) used when aggregating autoregressive transformer and retrieval')
-    parser.add_argument('--MSA_folder', default='.', type=str, help='Path to MSA for neighborhood scoring')
-    parser.add_argument('--MSA_weights_folder', default=None, type=str, help='Path to MSA weights for neighborhood scoring')
-    parser.add_argument('--clustal_omega_location', default=None, type=str, help='Path to Clustal Omega (only needed with scoring indels with retrieval)')
+    parser = argparse.ArgumentParser(description="Tranception scoring on B200 (score_tranception_proteingym.py drop-in)")
+    for flag, kw in _FLAGS:
+        parser.add_argument(flag, **kw)
     # additive
-    parser.add_argument('--precision', default='f16x3', choices=['f16x3', 'f16'])
-    parser.add_argument('--device', default=0, type=int)
-    parser.add_argument('--MSA_log_prior_npy', default=None, type=str, help='precomputed [L_full, 25] log prior for --inference_time_retrieval')
+    parser.add_argument("--precision", default="f16x3", choices=["f16x3", "f16"])
+    parser.add_argument("--device", default=0, type=int)
+    parser.add_argument("--MSA_log_prior_npy", default=None, type=str, help="precomputed [L_full, 25] log prior for --inference_time_retrieval")
     return parser
 
 
