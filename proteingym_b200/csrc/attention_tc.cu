@@ -58,7 +58,7 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo_elem, float hi_elem) {  /
   return d;
 }
 
-template <int NP>
+template <int NP, bool ONLINE>
 __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
           if (++slot == NSLOT) { slot = 0; phase ^= 1; }
         };
         const int nkb = p.causal ? (qt + 1 < p.nkb ? qt + 1 : p.nkb) : p.nkb;  // QT == KT: the diagonal block is block qt
-        for (int j = 0; j < nkb; ++j) load_block(ck, j, 1);  // pass A: K hi only
+        if (!ONLINE)
+          for (int j = 0; j < nkb; ++j) load_block(ck, j, 1);  // pass A: K hi only
         load_block(ck, 0, NP);                                // pass B: K0, then (K_{j+1}, V_j) ...
         for (int j = 0; j < nkb; ++j) {
           if (j + 1 < nkb) load_block(ck, j + 1, NP);
@@ -184,7 +185,8 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
           if (++slot == NSLOT) { slot = 0; phase ^= 1; }
           ++sblk;
         };
-        for (int j = 0; j < nkb; ++j) issue_qk(j, false);  // pass A (row max only)
+        if (!ONLINE)
+          for (int j = 0; j < nkb; ++j) issue_qk(j, false);  // pass A (row max only)
         issue_qk(0, true);
         for (int j = 0; j < nkb; ++j) {
           if (j + 1 < nkb) issue_qk(j + 1, true);
@@ -238,6 +240,120 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
       // A warp whose 32 query rows all lie beyond T (the tail tile of T = 514 keeps 2 rows of 128) only keeps the barrier
       // protocol going: no TMEM loads, no exponentials, no P writes (its P rows feed O rows that are never stored).
       const bool live = qt * QT + wq * 32 < p.T;
+      float l = 0.f;
+      if (ONLINE) {
+        // ---- single pass, online softmax with lazy rescaling: the running maximum is only raised when a block exceeds it by
+        // more than 8 (log2 units), so P <= 2^8 and O / l in TMEM need a correction step only on those (rare) blocks ----
+        const float slope2 = slope * LOG2E;
+        float m_run = -INFINITY;  // log2 domain
+        __half* redh = reinterpret_cast<__half*>(red);  // [2 parities][2 halves][128 rows]; fp16 is enough for a stabiliser
+        for (int j = 0; j < nkb; ++j, ++sblk, ++pblk) {
+          const uint32_t buf = sblk & 1;
+          mbar_wait(&s_full[buf], (sblk >> 1) & 1);
+          tc_fence_after();
+          const int valid = p.T - j * KT - g * 64;
+          const int vrow = (p.causal && j == qt) ? min(valid, row + 1 - g * 64) : valid;
+          const float bias0 = slope2 * static_cast<float>(j * KT + g * 64);
+          const int ncols = live ? nkeys(j) - g * 64 : 0;
+          uint32_t r[2][32];
+          if (ncols > 0) tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL0 + buf * KT + g * 64, r[0]);
+          if (ncols > 32) tmem_ld_32x32b_x32(tmem_base + lane_addr + S_COL0 + buf * KT + g * 64 + 32, r[1]);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[buf]);
+          float scale = 1.f;
+          if (live) {
+            // (1) scores to the log2 domain (+ ALiBi, masks) and this thread's block maximum
+            float mloc = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              if (c * 32 < ncols) {
+                if (plain && valid - c * 32 >= 32) {
+                  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    const float t = __uint_as_float(r[c][i]) * LOG2E;
+                    r[c][i] = __float_as_uint(t);
+                    m4[i & 3] = fmaxf(m4[i & 3], t);
+                  }
+                  mloc = fmaxf(mloc, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    float t = fmaf(__uint_as_float(r[c][i]), LOG2E, fmaf(slope2, static_cast<float>(c * 32 + i), bias0));
+                    t = (c * 32 + i < vrow) ? t : -INFINITY;
+                    r[c][i] = __float_as_uint(t);
+                    mloc = fmaxf(mloc, t);
+                  }
+                }
+              }
+            }
+            // (2) agree on the block maximum with the thread holding the other 64 columns of this row (same lane, warp +-4)
+            const __half mh = __float2half_rn(mloc);
+            redh[(j & 1) * 256 + g * 128 + row] = mh;
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + wq) : "memory");
+            const float mblk = fmaxf(__half2float(mh), __half2float(redh[(j & 1) * 256 + (g ^ 1) * 128 + row]));
+            // (3) lazy rescale decision (identical in both threads of the row)
+            if (mblk > m_run + 8.f) {
+              scale = ex2_approx(m_run - mblk);  // 0 for the first block (m_run = -inf)
+              m_run = mblk;
+            }
+            // (4) P = 2^(t - m_run), row-sum
+            float lsum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              if (c * 32 < ncols) {
+                float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float e = ex2_approx(__uint_as_float(r[c][i]) - m_run);
+                  l4[i & 3] += e;
+                  r[c][i] = __float_as_uint(e);
+                }
+                lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+              }
+            }
+            l = fmaf(l, scale, lsum);
+          }
+          mbar_wait(p_empty, (pblk & 1) ^ 1);  // PV of the previous block has completed: O is stable, P is free
+          if (j > 0 && live && __any_sync(0xffffffffu, scale != 1.f)) {
+            tc_fence_after();
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_addr + O_COL + g * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * scale);
+            tmem_st_32x32b_x32(tmem_base + lane_addr + O_COL + g * 32, o);
+            tmem_st_wait();
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int q8 = 0; q8 < 4; ++q8) {
+              if (c * 32 + q8 * 8 < ncols) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float x0 = __uint_as_float(r[c][q8 * 8 + 2 * u]), x1 = __uint_as_float(r[c][q8 * 8 + 2 * u + 1]);
+                  hi[u] = cvt_f16x2(x0, x1);
+                  if (NP == 2) {
+                    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
+                    lo[u] = cvt_f16x2(x0 - hf.x, x1 - hf.y);
+                  }
+                }
+                uint8_t* dst = prow + (((c * 4 + q8) ^ sw) << 4);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                if (NP == 2) *reinterpret_cast<uint4*>(dst + 2 * TILE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
+            }
+          }
+          fence_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full);
+        }
+      } else {
       // ---- pass A: row max over this thread's columns ----
       float m = -INFINITY;
       for (int j = 0; j < nkb; ++j, ++sblk) {
@@ -273,7 +389,6 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
       asm volatile("bar.sync 1, 256;" ::: "memory");
       m = fmaxf(m, red[(g ^ 1) * 128 + row]);
       const float m2 = m * LOG2E;
-      float l = 0.f;
       // ---- pass B: P = exp(S - max) ----
       const float slope2 = slope * LOG2E;
       for (int j = 0; j < nkb; ++j, ++sblk, ++pblk) {
@@ -339,6 +454,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
+      }
       }
       // ---- epilogue: O / l -> fp16 hi[/lo]; this thread owns 32 of the 64 head-dim columns ----
       asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read the pass-A maxima
@@ -413,19 +529,22 @@ int launch_attention_tc(const AttnLaunch& a, cudaStream_t s) {
   if (rc) return rc;
   const long long nitems = static_cast<long long>(a.B) * a.heads * p.nqt;
   const int grid = nitems < num_sms() ? static_cast<int>(nitems) : num_sms();
-  static bool set1 = false, set2 = false;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<1>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<1>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::TOTAL));
+    attr_set = true;
+  }
+  // PG_ATTN_TWO_PASS=1 selects the exact two-pass softmax variant (kept for cross-checking); default is the single-pass kernel.
+  static const bool two_pass = getenv("PG_ATTN_TWO_PASS") != nullptr;
   if (np == 1) {
-    if (!set1) {
-      PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<1>::TOTAL));
-      set1 = true;
-    }
-    attn_tc_kernel<1><<<grid, 384, Smem<1>::TOTAL, s>>>(tm, p);
+    if (two_pass) attn_tc_kernel<1, false><<<grid, 384, Smem<1>::TOTAL, s>>>(tm, p);
+    else attn_tc_kernel<1, true><<<grid, 384, Smem<1>::TOTAL, s>>>(tm, p);
   } else {
-    if (!set2) {
-      PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::TOTAL));
-      set2 = true;
-    }
-    attn_tc_kernel<2><<<grid, 384, Smem<2>::TOTAL, s>>>(tm, p);
+    if (two_pass) attn_tc_kernel<2, false><<<grid, 384, Smem<2>::TOTAL, s>>>(tm, p);
+    else attn_tc_kernel<2, true><<<grid, 384, Smem<2>::TOTAL, s>>>(tm, p);
   }
   PG_CUDA_OK(cudaGetLastError());
   if (split_tail) {
