@@ -1,4 +1,5 @@
 // C-ABI of libpgscore.so (include/pgscore.h): model handle, weight repacking, and the batched masked-marginal forward.
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -270,7 +271,8 @@ int forward_tranception(pg_handle h, const int32_t* ids, int B, int T, cudaStrea
     a.B = B; a.T = T; a.heads = D.heads; a.nseg = nseg; a.causal = 1; a.alibi_slopes = h->slopes;
     // causal + ALiBi: the mma.sync kernel is currently the faster of the two here (622 vs 837 ms on the L=512 bench, f16x3);
     // the tcgen05 kernel's causal path is correct (tests) but its masked/biased softmax loop is instruction-bound.
-    { ProfScope ps(CAT_ATTN, s); rc = launch_attention(a, s); }
+    { static const bool use_mma = getenv("PG_TRANCEPTION_ATTN_MMA") != nullptr;
+      ProfScope ps(CAT_ATTN, s); rc = use_mma ? launch_attention(a, s) : launch_attention_tc(a, s); }
     if (rc) return rc;
     g = GemmLaunch{};
     g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.wo; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.bo;

@@ -278,6 +278,15 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
                     m4[i & 3] = fmaxf(m4[i & 3], t);
                   }
                   mloc = fmaxf(mloc, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+                } else if (vrow - c * 32 >= 32) {  // ALiBi, every column of this chunk visible to this row: no masks
+                  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    const float t = fmaf(__uint_as_float(r[c][i]), LOG2E, fmaf(slope2, static_cast<float>(c * 32 + i), bias0));
+                    r[c][i] = __float_as_uint(t);
+                    m4[i & 3] = fmaxf(m4[i & 3], t);
+                  }
+                  mloc = fmaxf(mloc, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
                 } else {
 #pragma unroll
                   for (int i = 0; i < 32; ++i) {

@@ -12,7 +12,9 @@ st = {k[len("transformer."):]: v for k, v in synth.make_tranception_state(arch, 
 cfg = {"n_embd": arch.embed_dim, "n_head": arch.heads, "n_layer": arch.layers, "n_ctx": arch.n_ctx, "n_inner": arch.ffn_dim, "vocab_size": 25}
 lib = _lib.load()
 cases = [("subs_L512_1000", 512, 1000, False), ("indels_L62_2000", 62, 2000, True), ("subs_L1500_windowed_300", 1500, 300, False)]
-for precision in ("f16x3", "f16"):
+if os.environ.get("PG_BENCH_CASES"): cases = [c for c in cases if c[0] in os.environ["PG_BENCH_CASES"].split(",")]
+PRECS = os.environ.get("PG_BENCH_PRECS", "f16x3,f16").split(",")
+for precision in PRECS:
     sc = TranceptionScorer(cfg, st, precision=precision)
     for name, L, n, indel in cases:
         seq = synth.random_protein(L, 7)
