@@ -26,7 +26,7 @@ constexpr int QT = 128, KT = 128;
 constexpr uint32_t TILE = 16384;  // 128 rows x 64 fp16
 constexpr int NSLOT = 4;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t S_COL0 = 0, O_COL = 256;
+constexpr uint32_t S_COL0 = 0, O_COL = 256, P_COL = 320, PLO_COL = 384;  // TMEM columns (P: fp16 pairs, 64 columns per plane)
 
 template <int NP>
 struct Smem {
@@ -58,7 +58,7 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo_elem, float hi_elem) {  /
   return d;
 }
 
-template <int NP, bool ONLINE>
+template <int NP, bool ONLINE, bool PTMEM>
 __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -200,15 +200,25 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
           const int nks = nkeys(j) >> 4;
           for (int ks = 0; ks < nks; ++ks) {
             // A: P[128 x 16 keys] inside 64-key swizzle atoms of 16 KiB; B: V[16 keys x 64] = 2 KiB further per step
-            const uint32_t pa = p_addr + (ks >> 2) * TILE + (ks & 3) * 32;
-            const uint64_t ph = make_desc_sw128(pa, 1024);
             const uint64_t vh = make_desc_sw128(v_addr + ks * 2048, 1024, 1024);
-            umma_f16(tmem_o, ph, vh, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-            if (NP == 2) {
-              const uint64_t pl = make_desc_sw128(pa + 2 * TILE, 1024);
-              const uint64_t vl = make_desc_sw128(v_addr + TILE + ks * 2048, 1024, 1024);
-              umma_f16(tmem_o, pl, vh, idesc_o, 1);
-              umma_f16(tmem_o, ph, vl, idesc_o, 1);
+            if (PTMEM) {
+              // A = P straight from TMEM (128 lanes x 16 fp16 = 8 packed columns per k-step): no smem round trip, no proxy fence
+              umma_f16_ts(tmem_o, tmem_base + P_COL + ks * 8, vh, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+              if (NP == 2) {
+                const uint64_t vl = make_desc_sw128(v_addr + TILE + ks * 2048, 1024, 1024);
+                umma_f16_ts(tmem_o, tmem_base + PLO_COL + ks * 8, vh, idesc_o, 1);
+                umma_f16_ts(tmem_o, tmem_base + P_COL + ks * 8, vl, idesc_o, 1);
+              }
+            } else {
+              const uint32_t pa = p_addr + (ks >> 2) * TILE + (ks & 3) * 32;
+              const uint64_t ph = make_desc_sw128(pa, 1024);
+              umma_f16(tmem_o, ph, vh, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+              if (NP == 2) {
+                const uint64_t pl = make_desc_sw128(pa + 2 * TILE, 1024);
+                const uint64_t vl = make_desc_sw128(v_addr + TILE + ks * 2048, 1024, 1024);
+                umma_f16(tmem_o, pl, vh, idesc_o, 1);
+                umma_f16(tmem_o, ph, vl, idesc_o, 1);
+              }
             }
           }
           umma_commit(&kv_empty[slot]);
@@ -336,28 +346,49 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
             tmem_st_32x32b_x32(tmem_base + lane_addr + O_COL + g * 32, o);
             tmem_st_wait();
           }
+          if (PTMEM) {
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < 2; ++c) {
+              if (c * 32 < ncols) {
+                uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int q8 = 0; q8 < 4; ++q8) {
-              if (c * 32 + q8 * 8 < ncols) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float x0 = __uint_as_float(r[c][q8 * 8 + 2 * u]), x1 = __uint_as_float(r[c][q8 * 8 + 2 * u + 1]);
+                for (int u = 0; u < 16; ++u) {
+                  const float x0 = __uint_as_float(r[c][2 * u]), x1 = __uint_as_float(r[c][2 * u + 1]);
                   hi[u] = cvt_f16x2(x0, x1);
                   if (NP == 2) {
                     const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
                     lo[u] = cvt_f16x2(x0 - hf.x, x1 - hf.y);
                   }
                 }
-                uint8_t* dst = prow + (((c * 4 + q8) ^ sw) << 4);
-                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                if (NP == 2) *reinterpret_cast<uint4*>(dst + 2 * TILE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                tmem_st_32x32b_x16(tmem_base + lane_addr + P_COL + g * 32 + c * 16, hi);
+                if (NP == 2) tmem_st_32x32b_x16(tmem_base + lane_addr + PLO_COL + g * 32 + c * 16, lo);
               }
             }
-          }
+            tmem_st_wait();
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+  #pragma unroll
+              for (int q8 = 0; q8 < 4; ++q8) {
+                if (c * 32 + q8 * 8 < ncols) {
+                  uint32_t hi[4], lo[4];
+  #pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float x0 = __uint_as_float(r[c][q8 * 8 + 2 * u]), x1 = __uint_as_float(r[c][q8 * 8 + 2 * u + 1]);
+                    hi[u] = cvt_f16x2(x0, x1);
+                    if (NP == 2) {
+                      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
+                      lo[u] = cvt_f16x2(x0 - hf.x, x1 - hf.y);
+                    }
+                  }
+                  uint8_t* dst = prow + (((c * 4 + q8) ^ sw) << 4);
+                  *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  if (NP == 2) *reinterpret_cast<uint4*>(dst + 2 * TILE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+              }
+            }
           fence_async_smem();
+          }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(p_full);
@@ -544,20 +575,26 @@ int launch_attention_tc(const AttnLaunch& a, cudaStream_t s) {
   const int grid = nitems < num_sms() ? static_cast<int>(nitems) : num_sms();
   static bool attr_set = false;
   if (!attr_set) {
-    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<1>::TOTAL));
-    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<1>::TOTAL));
-    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::TOTAL));
-    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<1>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<1>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<1>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::TOTAL));
     attr_set = true;
   }
   // PG_ATTN_TWO_PASS=1 selects the exact two-pass softmax variant (kept for cross-checking); default is the single-pass kernel.
   static const bool two_pass = getenv("PG_ATTN_TWO_PASS") != nullptr;
+  // PG_ATTN_P_SMEM=1: hand P to the PV MMA through swizzled shared memory instead of TMEM (the first working variant).
+  static const bool p_smem = getenv("PG_ATTN_P_SMEM") != nullptr;
   if (np == 1) {
-    if (two_pass) attn_tc_kernel<1, false><<<grid, 384, Smem<1>::TOTAL, s>>>(tm, p);
-    else attn_tc_kernel<1, true><<<grid, 384, Smem<1>::TOTAL, s>>>(tm, p);
+    if (two_pass) attn_tc_kernel<1, false, false><<<grid, 384, Smem<1>::TOTAL, s>>>(tm, p);
+    else if (p_smem) attn_tc_kernel<1, true, false><<<grid, 384, Smem<1>::TOTAL, s>>>(tm, p);
+    else attn_tc_kernel<1, true, true><<<grid, 384, Smem<1>::TOTAL, s>>>(tm, p);
   } else {
-    if (two_pass) attn_tc_kernel<2, false><<<grid, 384, Smem<2>::TOTAL, s>>>(tm, p);
-    else attn_tc_kernel<2, true><<<grid, 384, Smem<2>::TOTAL, s>>>(tm, p);
+    if (two_pass) attn_tc_kernel<2, false, false><<<grid, 384, Smem<2>::TOTAL, s>>>(tm, p);
+    else if (p_smem) attn_tc_kernel<2, true, false><<<grid, 384, Smem<2>::TOTAL, s>>>(tm, p);
+    else attn_tc_kernel<2, true, true><<<grid, 384, Smem<2>::TOTAL, s>>>(tm, p);
   }
   PG_CUDA_OK(cudaGetLastError());
   if (split_tail) {
