@@ -6,8 +6,9 @@
 //   * two softmax warpgroups (4 warps each, thread = one query row x 64 keys: no cross-thread max exchange needed),
 //   * the MMA warp interleaves the two tiles' QK^T / PV issues, so one tile's tensor work hides the other's softmax,
 //   * both tiles consume the same K / V blocks from one TMA ring (half the L2->smem traffic per query row).
-// Key blocks are 64 wide so that Q(2 tiles) + ring + P(2 tiles) fit in shared memory even with hi/lo planes (192 KiB).
-// TMEM: per tile two 64-column S buffers + a 64-column O accumulator (384 of 512 columns).
+// Key blocks are 64 wide so that both tiles' S, O and P fit in the 512 TMEM columns even with hi/lo planes.
+// TMEM: per tile two 64-column S buffers, a 64-column O accumulator and P as packed fp16 pairs (32 columns hi + 32 lo): 256 columns per
+// tile, all 512 in use. P reaches the PV MMA through TMEM (TS-form tcgen05.mma), so shared memory only holds Q and the K/V ring.
 #include <cstdlib>
 
 #include "common.h"
@@ -20,15 +21,14 @@ namespace {
 constexpr int QT = 128, KB = 64;
 constexpr uint32_t QTILE = 16384;  // 128 rows x 64 fp16
 constexpr uint32_t KTILE = 8192;   // 64 rows x 64 fp16
-constexpr int NSLOT = 4;
+constexpr int NSLOT = 8;
 constexpr uint32_t TMEM_COLS = 512;
 
 template <int NP>
 struct Smem2 {
   static constexpr uint32_t Q = 0;                                 // [2 tiles][NP]
   static constexpr uint32_t KV = 2 * NP * QTILE;                   // [NSLOT][NP]
-  static constexpr uint32_t P = KV + NSLOT * NP * KTILE;           // [2 tiles][NP] 128 x 64 keys
-  static constexpr uint32_t BAR = P + 2 * NP * QTILE;
+  static constexpr uint32_t BAR = KV + NSLOT * NP * KTILE;
   static constexpr uint32_t TOTAL = BAR + 512 + 1024;
 };
 
@@ -61,7 +61,6 @@ __global__ void __launch_bounds__(384, 1) attn_tc2_kernel(const __grid_constant_
   using L = Smem2<NP>;
   uint8_t* sQ = smem + L::Q;
   uint8_t* sKV = smem + L::KV;
-  uint8_t* sP = smem + L::P;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
@@ -177,7 +176,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc2_kernel(const __grid_constant_
               mbar_wait(&s_empty[t * 2 + buf], ((sblk[t] >> 1) & 1) ^ 1);
               tc_fence_after();
               const uint32_t q_addr = smem_u32(sQ + t * NP * QTILE);
-              const uint32_t tmem_s = tmem_base + t * 192 + buf * 64;
+              const uint32_t tmem_s = tmem_base + t * 256 + buf * 64;
               const uint64_t qh = make_desc_sw128(q_addr, 1024), kh = make_desc_sw128(k_addr, 1024);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_s, qh + 2 * ks, kh + 2 * ks, idesc_s, ks > 0);
@@ -205,17 +204,15 @@ __global__ void __launch_bounds__(384, 1) attn_tc2_kernel(const __grid_constant_
               mbar_wait(&p_full[t], pblk[t] & 1);
               if (jj == 0) mbar_wait(&o_empty[t], (oitem[t] & 1) ^ 1);
               tc_fence_after();
-              const uint32_t p_addr = smem_u32(sP + t * NP * QTILE);
-              const uint32_t tmem_o = tmem_base + t * 192 + 128;
+              const uint32_t tmem_o = tmem_base + t * 256 + 128;
+              const uint32_t tmem_p = tmem_base + t * 256 + 192;  // P hi: 32 packed columns (64 keys); lo at +32
               for (int ks = 0; ks < nks; ++ks) {
-                const uint64_t ph = make_desc_sw128(p_addr + ks * 32, 1024);
                 const uint64_t vh = make_desc_sw128(v_addr + ks * 2048, 1024, 1024);
-                umma_f16(tmem_o, ph, vh, idesc_o, (jj > 0 || ks > 0) ? 1u : 0u);
+                umma_f16_ts(tmem_o, tmem_p + ks * 8, vh, idesc_o, (jj > 0 || ks > 0) ? 1u : 0u);  // A = P from TMEM
                 if (NP == 2) {
-                  const uint64_t pl = make_desc_sw128(p_addr + QTILE + ks * 32, 1024);
                   const uint64_t vl = make_desc_sw128(v_addr + KTILE + ks * 2048, 1024, 1024);
-                  umma_f16(tmem_o, pl, vh, idesc_o, 1);
-                  umma_f16(tmem_o, ph, vl, idesc_o, 1);
+                  umma_f16_ts(tmem_o, tmem_p + 32 + ks * 8, vh, idesc_o, 1);
+                  umma_f16_ts(tmem_o, tmem_p + ks * 8, vl, idesc_o, 1);
                 }
               }
               umma_commit(&p_empty[t]);
@@ -239,9 +236,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc2_kernel(const __grid_constant_
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     constexpr float LOG2E = 1.4426950408889634f;
     uint32_t sblk = 0, pblk = 0, oitem = 0;
-    uint8_t* prow = sP + t * NP * QTILE + row * 128;
-    const int sw = row & 7;
-    const uint32_t tmem_t = tmem_base + t * 192 + lane_addr;
+    const uint32_t tmem_t = tmem_base + t * 256 + lane_addr;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int pi = item % p.npairs, bh = item / p.npairs;
       const int h = bh % p.heads, b = bh / p.heads;
@@ -340,26 +335,22 @@ __global__ void __launch_bounds__(384, 1) attn_tc2_kernel(const __grid_constant_
         }
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+          if (c * 32 < ncols) {
+            uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int q8 = 0; q8 < 4; ++q8) {
-            if (c * 32 + q8 * 8 < ncols) {
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float x0 = __uint_as_float(r[c][q8 * 8 + 2 * u]), x1 = __uint_as_float(r[c][q8 * 8 + 2 * u + 1]);
-                hi[u] = cvt2(x0, x1);
-                if (NP == 2) {
-                  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
-                  lo[u] = cvt2(x0 - hf.x, x1 - hf.y);
-                }
+            for (int u = 0; u < 16; ++u) {
+              const float x0 = __uint_as_float(r[c][2 * u]), x1 = __uint_as_float(r[c][2 * u + 1]);
+              hi[u] = cvt2(x0, x1);
+              if (NP == 2) {
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
+                lo[u] = cvt2(x0 - hf.x, x1 - hf.y);
               }
-              uint8_t* dst = prow + (((c * 4 + q8) ^ sw) << 4);
-              *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              if (NP == 2) *reinterpret_cast<uint4*>(dst + QTILE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
+            tmem_st_32x32b_x16(tmem_t + 192 + c * 16, hi);
+            if (NP == 2) tmem_st_32x32b_x16(tmem_t + 224 + c * 16, lo);
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);

@@ -137,7 +137,7 @@ def stage_attn_perf():
     for nseg in (1, 3):
         np_ = 2 if nseg == 3 else 1
         qkv = (torch.randn(B * T, 3 * d * np_, device="cuda") * 0.5).half(); out = torch.empty(B * T, d * np_, device="cuda", dtype=torch.float16)
-        for impl in (1, 2):
+        for impl in (1, 2, 3):
             a = _lib.PgAttnArgs(); a.qkv = qkv.data_ptr(); a.ld = 3 * d * np_; a.lo_off = 3 * d if nseg == 3 else 0
             a.out = out.data_ptr(); a.ldo = d * np_; a.out_lo_off = d if nseg == 3 else 0
             a.B, a.T, a.heads, a.nseg, a.causal, a.impl = B, T, H, nseg, 0, impl
