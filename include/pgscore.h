@@ -95,6 +95,34 @@ int pg_forward_logprobs(pg_handle h, const int32_t* tokens, int32_t n_tokens, in
 int pg_ar_loglik(pg_handle h, const int32_t* ids, const int32_t* lens, int32_t B, int32_t T, const float* log_prior,
                  const int32_t* prior_row, float alpha, float* out_sum_logp, pg_stream stream);
 
+/* Retrieval fusion arguments of pg_ar_loglik_fused — the per-position mixing the reference does inside forward():
+ *   Tranception   (tranception/model_pytorch.py:806-830):  fused = (1-alpha)*logp + alpha*log_prior            on ALL columns
+ *   TranceptEVE   (trancepteve/model_pytorch.py:1100-1116): fused = (1-beta)*((1-alpha)*logp + alpha*log_prior) + beta*log_prior2
+ *                                                          on the amino-acid columns (>= 5) only
+ * The host does the slice / flip index arithmetic and hands the kernel one table row index per token row:
+ *   prior_row  [B, T] int32: row of log_prior for (b, t); -1 = no fusion; -2 = keep only the (1-alpha) factor (the reference's
+ *              fallback for non-focus columns that its coordinate arithmetic places outside the MSA, :1131-1133)
+ *   prior_row2 [B, T] int32: row of log_prior2 (EVE) or -1 (= two-way fusion with log_prior only, :1129-1130)
+ *   first_col  fusion applies to vocabulary columns >= first_col (0 Tranception, 5 TranceptEVE)
+ *   out_logprobs optional [B, T, vocab] fp32: the fused log-probabilities of every column for t < len-1 (what
+ *              get_transformer_log_softmax, trancepteve/model_pytorch.py:821-874, returns; used for prior recalibration)
+ * All pointers are device pointers; tables are [rows, vocab] fp32. */
+typedef struct pg_ar_fusion {
+  const float* log_prior;
+  const int32_t* prior_row;
+  float alpha;
+  const float* log_prior2;
+  const int32_t* prior_row2;
+  float beta;
+  int32_t first_col;
+  float* out_logprobs;
+} pg_ar_fusion;
+
+/* pg_ar_loglik with the full fusion argument block (f may be NULL = no retrieval). pg_ar_loglik(h, ..., log_prior, prior_row,
+ * alpha, ...) is the same call with only the first prior set and first_col = 0. */
+int pg_ar_loglik_fused(pg_handle h, const int32_t* ids, const int32_t* lens, int32_t B, int32_t T, const pg_ar_fusion* f,
+                       float* out_sum_logp, pg_stream stream);
+
 /* Replaces label_row over the whole DMS frame (compute_fitness.py:240-250, :505-514):
  *   score[m] = sum_{s in [row_offsets[m], row_offsets[m+1])} table[site_row[s], site_mt[s]] - table[site_row[s], site_wt[s]]
  * table [n_rows, vocab] fp32; site_* int32 CSR arrays (device); out_scores [M] fp32. Fixed summation order per mutant. */

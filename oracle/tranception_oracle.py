@@ -127,6 +127,33 @@ def sequence_logprob(st, seq, layers, heads, ln_eps=1e-5, dtype=torch.float32, l
     return lp.gather(1, labels[:, None]).sum().item()
 
 
+def fused_logprob_rows(st, seq, layers, heads, ln_eps=1e-5, log_prior=None, prior_row=None, alpha=0.0, log_prior2=None, prior_row2=None,
+                       beta=0.0, first_col=0, dtype=torch.float32):
+    """CPU statement of what ``pg_ar_loglik_fused`` must return for one unpadded sequence, following the semantics written in
+    include/pgscore.h (pg_ar_fusion): log-softmax rows [len + 1, V] with, per predicted position t and vocabulary column
+    v >= first_col, prior_row[t] >= 0 -> (1-alpha)*lp + alpha*log_prior[prior_row[t], v], then if prior_row2[t] >= 0
+    -> (1-beta)*that + beta*log_prior2[prior_row2[t], v]; prior_row[t] == -2 -> (1-alpha)*lp. Returns (rows, sum of label terms).
+    The mixing formulas are TranceptEVE's (trancepteve/model_pytorch.py:1113-1116, :1129-1133) in float32."""
+    ids = torch.tensor([tokenize(seq)], dtype=torch.int64)
+    with torch.no_grad():
+        lp = torch.log_softmax(forward(st, ids, layers, heads, ln_eps, dtype)[0, :-1], dim=-1).float()
+    fused = lp.clone()
+    if prior_row is not None:
+        P1 = torch.as_tensor(log_prior, dtype=torch.float32)
+        P2 = torch.as_tensor(log_prior2, dtype=torch.float32) if log_prior2 is not None else None
+        for t in range(lp.shape[0]):
+            pr = int(prior_row[t])
+            if pr >= 0:
+                m = (1 - alpha) * lp[t, first_col:] + alpha * P1[pr, first_col:]
+                if P2 is not None and int(prior_row2[t]) >= 0:
+                    m = (1 - beta) * m + beta * P2[int(prior_row2[t]), first_col:]
+                fused[t, first_col:] = m
+            elif pr == -2:
+                fused[t, first_col:] = (1 - alpha) * lp[t, first_col:]
+    labels = ids[0, 1:]
+    return fused.numpy(), float(fused.gather(1, labels[:, None]).sum())
+
+
 def get_mutated_sequence(focus_seq, mutant, start_idx=1):
     """scoring_utils.py:16-31."""
     s = list(focus_seq)

@@ -36,6 +36,12 @@ class PgAttnArgs(C.Structure):
                 ("causal", C.c_int32), ("alibi_slopes", C.c_void_p), ("impl", C.c_int32)]
 
 
+class PgArFusion(C.Structure):
+    _fields_ = [("log_prior", C.c_void_p), ("prior_row", C.c_void_p), ("alpha", C.c_float),
+                ("log_prior2", C.c_void_p), ("prior_row2", C.c_void_p), ("beta", C.c_float),
+                ("first_col", C.c_int32), ("out_logprobs", C.c_void_p)]
+
+
 # every symbol include/pgscore.h declares, with its ctypes signature
 SIGNATURES = {
     "pg_abi_version": (C.c_int, []),
@@ -51,6 +57,8 @@ SIGNATURES = {
                                    C.c_int32, C.c_void_p, C.c_void_p]),
     "pg_ar_loglik": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                C.c_void_p]),
+    "pg_ar_loglik_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(PgArFusion), C.c_void_p,
+                                     C.c_void_p]),
     "pg_gemm": (C.c_int, [C.POINTER(PgGemmArgs), C.c_void_p]),
     "pg_layernorm_f16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_int64, C.c_int64, C.c_void_p]),

@@ -312,7 +312,7 @@ using namespace pg;
 
 extern "C" {
 
-int pg_abi_version(void) { return 1; }
+int pg_abi_version(void) { return 2; }
 
 long long pg_launch_count(void) {
   std::lock_guard<std::mutex> lk(prof_mu());
@@ -590,15 +590,24 @@ int pg_forward_logprobs(pg_handle h, const int32_t* tokens, int32_t n_tokens, in
   return PG_OK;
 }
 
-int pg_ar_loglik(pg_handle h, const int32_t* ids, const int32_t* lens, int32_t B, int32_t T, const float* log_prior,
-                 const int32_t* prior_row, float alpha, float* out_sum_logp, pg_stream stream) {
+int pg_ar_loglik_fused(pg_handle h, const int32_t* ids, const int32_t* lens, int32_t B, int32_t T, const pg_ar_fusion* f,
+                       float* out_sum_logp, pg_stream stream) {
   if (!h) return set_error(PG_ERR_ARG, "pg_ar_loglik: null handle");
   if (!h->loaded) return fail(h, PG_ERR_STATE, "pg_ar_loglik: weights not loaded");
   if (h->desc.arch != PG_ARCH_TRANCEPTION) return fail(h, PG_ERR_STATE, "pg_ar_loglik: handle is not a Tranception model");
   if (B < 0 || T <= 0) return fail(h, PG_ERR_ARG, "pg_ar_loglik: bad B/T");
   if (B == 0) return PG_OK;
   if (!ids || !lens || !out_sum_logp) return fail(h, PG_ERR_ARG, "pg_ar_loglik: null buffer");
-  if ((log_prior == nullptr) != (prior_row == nullptr)) return fail(h, PG_ERR_ARG, "pg_ar_loglik: log_prior and prior_row go together");
+  ArFusion base;
+  if (f) {
+    if ((f->log_prior == nullptr) != (f->prior_row == nullptr)) return fail(h, PG_ERR_ARG, "pg_ar_loglik: log_prior and prior_row go together");
+    if ((f->log_prior2 == nullptr) != (f->prior_row2 == nullptr)) return fail(h, PG_ERR_ARG, "pg_ar_loglik: log_prior2 and prior_row2 go together");
+    if (f->log_prior2 && !f->log_prior) return fail(h, PG_ERR_ARG, "pg_ar_loglik: the second prior needs the first (it is fused inside the MSA overlap)");
+    if (f->first_col < 0 || f->first_col > h->desc.vocab) return fail(h, PG_ERR_ARG, "pg_ar_loglik: first_col outside the vocabulary");
+    base.log_prior = f->log_prior; base.prior_row = f->prior_row; base.alpha = f->alpha;
+    base.log_prior2 = f->log_prior2; base.prior_row2 = f->prior_row2; base.beta = f->beta;
+    base.first_col = f->first_col; base.out_logprobs = f->out_logprobs;
+  }
   if (T > h->desc.max_positions) return fail(h, PG_ERR_ARG, "pg_ar_loglik: sequence longer than n_ctx");
   if (T > h->max_rows) return fail(h, PG_ERR_ARG, "pg_ar_loglik: sequence longer than workspace");
   PG_CUDA_OK(cudaSetDevice(h->desc.device));
@@ -606,15 +615,27 @@ int pg_ar_loglik(pg_handle h, const int32_t* ids, const int32_t* lens, int32_t B
   const long long per = h->max_rows / T;
   for (int b0 = 0; b0 < B; b0 += static_cast<int>(per)) {
     const int Bc = (B - b0) < per ? (B - b0) : static_cast<int>(per);
-    const int32_t* idc = ids + static_cast<long long>(b0) * T;
+    const long long off = static_cast<long long>(b0) * T;
+    const int32_t* idc = ids + off;
     int rc = forward_tranception(h, idc, Bc, T, s);
     if (rc) return fail(h, rc, tls_error());
     ProfScope ps(CAT_HEAD, s, 2);
-    rc = launch_ar_head(h->x, h->desc.embed_dim, Bc, T, h->desc.vocab, idc, lens + b0, h->lnag, h->lnab, h->embed, log_prior,
-                        prior_row ? prior_row + static_cast<long long>(b0) * T : nullptr, alpha, h->tok_logp, out_sum_logp + b0, s);
+    ArFusion fc = base;
+    if (fc.prior_row) fc.prior_row += off;
+    if (fc.prior_row2) fc.prior_row2 += off;
+    if (fc.out_logprobs) fc.out_logprobs += off * h->desc.vocab;
+    rc = launch_ar_head(h->x, h->desc.embed_dim, Bc, T, h->desc.vocab, idc, lens + b0, h->lnag, h->lnab, h->embed, fc, h->tok_logp,
+                        out_sum_logp + b0, s);
     if (rc) return fail(h, rc, tls_error());
   }
   return PG_OK;
+}
+
+int pg_ar_loglik(pg_handle h, const int32_t* ids, const int32_t* lens, int32_t B, int32_t T, const float* log_prior,
+                 const int32_t* prior_row, float alpha, float* out_sum_logp, pg_stream stream) {
+  pg_ar_fusion f = {};
+  f.log_prior = log_prior; f.prior_row = prior_row; f.alpha = alpha;
+  return pg_ar_loglik_fused(h, ids, lens, B, T, &f, out_sum_logp, stream);
 }
 
 int pg_score_mutants(const float* table, int32_t n_rows, int32_t vocab, const int32_t* site_row, const int32_t* site_wt,

@@ -106,7 +106,13 @@ int launch_gather_rows(const float* x, const int32_t* row_sel, int B, int T, int
 int launch_gather_embed(const int32_t* ids, const float* wte, long long rows, int d, int vocab, float* x, cudaStream_t s);
 int launch_qkv_conv(const __half* in, __half* out, int64_t ld, int64_t lo_off, int B, int T, int heads, const float* taps,
                     float qscale, cudaStream_t s);
+// Retrieval-prior fusion arguments of the autoregressive head (device pointers; see pg_ar_fusion in include/pgscore.h).
+struct ArFusion {
+  const float* log_prior = nullptr; const int32_t* prior_row = nullptr; float alpha = 0.f;
+  const float* log_prior2 = nullptr; const int32_t* prior_row2 = nullptr; float beta = 0.f;
+  int first_col = 0;
+  float* out_logprobs = nullptr;
+};
 int launch_ar_head(const float* x, int d, int B, int T, int vocab, const int32_t* ids, const int32_t* lens, const float* lnf_g,
-                   const float* lnf_b, const float* wte, const float* log_prior, const int32_t* prior_row, float alpha,
-                   float* tok_logp, float* out_sum, cudaStream_t s);
+                   const float* lnf_b, const float* wte, const ArFusion& fusion, float* tok_logp, float* out_sum, cudaStream_t s);
 }  // namespace pg

@@ -141,9 +141,26 @@ struct ArHeadParams {
   const float* x; int d; int T; int vocab;
   const int32_t* ids; const int32_t* lens;
   const float* lnf_g; const float* lnf_b; const float* wte;
-  const float* log_prior; const int32_t* prior_row; float alpha;
+  ArFusion f;
   float* tok_logp;  // [B*T]
 };
+
+// Retrieval fusion of one log-probability (Tranception model_pytorch.py:806-830; TranceptEVE model_pytorch.py:1100-1116, and the
+// non-focus-column fallbacks of :1118-1133 which the host encodes in the row indices): v = vocabulary column, r = token row.
+__device__ __forceinline__ float fuse_logp(const ArFusion& f, int vocab, long long r, int v, float lp) {
+  if (!f.prior_row || v < f.first_col) return lp;
+  const int pr = f.prior_row[r];
+  if (pr >= 0) {
+    float m = (1.f - f.alpha) * lp + f.alpha * f.log_prior[static_cast<long long>(pr) * vocab + v];
+    if (f.prior_row2) {
+      const int pr2 = f.prior_row2[r];
+      if (pr2 >= 0) m = (1.f - f.beta) * m + f.beta * f.log_prior2[static_cast<long long>(pr2) * vocab + v];
+    }
+    return m;
+  }
+  if (pr == -2) return (1.f - f.alpha) * lp;
+  return lp;
+}
 
 // One block (128 threads) per token row r = (b, t): log p(ids[b, t+1] | ids[b, <=t]); 0 for t >= len-1.
 __global__ void ar_head_kernel(ArHeadParams p) {
@@ -186,14 +203,12 @@ __global__ void ar_head_kernel(ArHeadParams p) {
     float se = 0.f;
     for (int v = lane; v < p.vocab; v += 32) se += expf(logits[v] - m);
     se = warp_sum_t(se);
+    const float lse = m + logf(se);
+    if (p.f.out_logprobs)
+      for (int v = lane; v < p.vocab; v += 32) p.f.out_logprobs[r * p.vocab + v] = fuse_logp(p.f, p.vocab, r, v, logits[v] - lse);
     if (lane == 0) {
       const int label = p.ids[r + 1];
-      float lp = logits[label] - (m + logf(se));
-      if (p.log_prior && p.prior_row) {
-        const int pr = p.prior_row[r];
-        if (pr >= 0) lp = (1.f - p.alpha) * lp + p.alpha * p.log_prior[static_cast<long long>(pr) * p.vocab + label];
-      }
-      p.tok_logp[r] = lp;
+      p.tok_logp[r] = fuse_logp(p.f, p.vocab, r, label, logits[label] - lse);
     }
   }
 }
@@ -231,10 +246,9 @@ int launch_qkv_conv(const __half* in, __half* out, int64_t ld, int64_t lo_off, i
 }
 
 int launch_ar_head(const float* x, int d, int B, int T, int vocab, const int32_t* ids, const int32_t* lens, const float* lnf_g,
-                   const float* lnf_b, const float* wte, const float* log_prior, const int32_t* prior_row, float alpha,
-                   float* tok_logp, float* out_sum, cudaStream_t s) {
+                   const float* lnf_b, const float* wte, const ArFusion& fusion, float* tok_logp, float* out_sum, cudaStream_t s) {
   if (B <= 0 || T <= 0) return PG_OK;
-  ArHeadParams p{x, d, T, vocab, ids, lens, lnf_g, lnf_b, wte, log_prior, prior_row, alpha, tok_logp};
+  ArHeadParams p{x, d, T, vocab, ids, lens, lnf_g, lnf_b, wte, fusion, tok_logp};
   ar_head_kernel<<<static_cast<unsigned>(static_cast<long long>(B) * T), 128, (d + vocab) * sizeof(float), s>>>(p);
   seq_sum_kernel<<<(B + 3) / 4, 128, 0, s>>>(tok_logp, lens, B, T, out_sum);
   PG_CUDA_OK(cudaGetLastError());

@@ -1,0 +1,128 @@
+"""EVE log prior for TranceptEVE (trancepteve/model_pytorch.py:940-1001): the once-per-protein pre-step that turns trained EVE
+VAE checkpoints into an ``EVE_log_prior`` [L_full, 25] table (-inf outside the MSA's focus columns and on the 5 special tokens).
+
+This is not part of the scoring hot path and is cached on disk exactly where the reference caches it
+(``<EVE model folder>/log_prior/<model name>_<num samples>_log_space``, a pickled tensor), so a cache written by either
+implementation is read by the other. When there is no cache the Monte-Carlo average over the Bayesian decoder is computed here
+with plain tensor algebra on the scorer's device, drawing from a ``torch.Generator`` seeded like the reference (VAE_model.py:37
+``torch.manual_seed(random_seed)``, seed 42) in the reference's draw order (latent, then per decoder layer weight -> bias,
+output weight -> bias, output convolution, [sparsity], temperature), so that with the same torch build and device type the samples
+are the same numbers. torch's generator is used on purpose: stream-for-stream agreement with the reference's sampling is only
+possible through it; the arithmetic is restated, not imported.
+
+State-dict keys / shapes: VAE_encoder.py:40-52, VAE_decoder.py:47-108."""
+from __future__ import annotations
+
+import json
+import os
+import pickle
+
+import numpy as np
+import torch
+
+ALPHABET = "ACDEFGHIKLMNPQRSTVWY"
+_ACT = {"relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, "elu": torch.nn.functional.elu, "linear": lambda x: x}
+
+
+def encode_focus(st: dict, enc: dict, x: torch.Tensor):
+    """VAE_MLP_encoder.forward (VAE_encoder.py:66-87): x [B, L, 20] one-hot -> (z_mean, z_log_var)."""
+    B, L, A = x.shape
+    if enc.get("convolve_input"):
+        x = torch.einsum("bla,ca->bcl", x, st["encoder.input_convolution.weight"][:, :, 0]).reshape(B, -1)
+    else:
+        x = x.reshape(B, L * A)
+    act = _ACT[enc["nonlinear_activation"]]
+    for k in range(len(enc["hidden_layers_sizes"])):
+        x = act(x @ st[f"encoder.hidden_layers.{k}.weight"].T + st[f"encoder.hidden_layers.{k}.bias"])
+    return (x @ st["encoder.fc_mean.weight"].T + st["encoder.fc_mean.bias"],
+            x @ st["encoder.fc_log_var.weight"].T + st["encoder.fc_log_var.bias"])
+
+
+def _draw(mean: torch.Tensor, log_var: torch.Tensor, g: torch.Generator) -> torch.Tensor:
+    eps = torch.randn(mean.shape, generator=g, device=mean.device, dtype=mean.dtype)
+    return torch.exp(0.5 * log_var) * eps + mean
+
+
+def decode_sample(st: dict, dec: dict, z: torch.Tensor, seq_len: int, g: torch.Generator) -> torch.Tensor:
+    """One pass of VAE_Bayesian_MLP_decoder.forward in eval mode (VAE_decoder.py:118-169) -> log-softmax [B, L, 20]."""
+    A = len(ALPHABET)
+    H = dec["hidden_layers_sizes"]
+    x = z
+    for k in range(len(H)):
+        w = _draw(st[f"decoder.hidden_layers_mean.{k}.weight"], st[f"decoder.hidden_layers_log_var.{k}.weight"], g)
+        b = _draw(st[f"decoder.hidden_layers_mean.{k}.bias"], st[f"decoder.hidden_layers_log_var.{k}.bias"], g)
+        act = _ACT[dec["first_hidden_nonlinearity"] if k < len(H) - 1 else dec["last_hidden_nonlinearity"]]
+        x = act(x @ w.T + b)
+    w_out = _draw(st["decoder.last_hidden_layer_weight_mean"], st["decoder.last_hidden_layer_weight_log_var"], g)
+    b_out = _draw(st["decoder.last_hidden_layer_bias_mean"], st["decoder.last_hidden_layer_bias_log_var"], g)
+    if dec["convolve_output"]:
+        C = dec["convolution_output_depth"]
+        conv = _draw(st["decoder.output_convolution_mean.weight"], st["decoder.output_convolution_log_var.weight"], g)
+        # the reference reinterprets the buffers (no transposes): [C*L, H] read as [L*H, C], [A, C, 1] read as [C, A]
+        w_out = w_out.reshape(seq_len * H[-1], C) @ conv.reshape(C, A)
+    if dec.get("include_sparsity"):
+        tiles = dec["num_tiles_sparsity"]
+        sp = _draw(st["decoder.sparsity_weight_mean"], st["decoder.sparsity_weight_log_var"], g)
+        sp = torch.sigmoid(sp.repeat(tiles, 1)).unsqueeze(2)
+        w_out = w_out.reshape(H[-1], seq_len, A) * sp
+    w_out = w_out.reshape(seq_len * A, H[-1])
+    x = x @ w_out.T + b_out
+    if dec["include_temperature_scaler"]:
+        t = _draw(st["decoder.temperature_scaler_mean"], st["decoder.temperature_scaler_log_var"], g)
+        x = torch.log(1.0 + torch.exp(t)) * x
+    return torch.log_softmax(x.reshape(z.shape[0], seq_len, A), dim=-1)
+
+
+def eve_log_prior_single(state: dict, params: dict, focus_seq_trimmed, focus_cols, full_sequence_len: int, MSA_start: int,
+                         num_samples: int = 10, device="cuda", seed: int = 42) -> torch.Tensor:
+    """get_EVE_log_prior_single (model_pytorch.py:969-1001) for the wild type: [full_sequence_len, 25] float32 on ``device``."""
+    dev = torch.device(device)
+    st = {k: v.to(dev, torch.float32) for k, v in state.items()}
+    L, A = len(focus_seq_trimmed), len(ALPHABET)
+    x = torch.zeros((1, L, A), dtype=torch.float32, device=dev)
+    for j, ch in enumerate(focus_seq_trimmed):
+        k = ALPHABET.find(ch)
+        if k >= 0:
+            x[0, j, k] = 1.0
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    mu, log_var = encode_focus(st, params["encoder_parameters"], x)
+    recon = 0
+    for _ in range(num_samples):
+        z = _draw(mu, log_var, g)
+        recon = recon + decode_sample(st, params["decoder_parameters"], z, L, g)
+    recon = recon / num_samples
+    prior = torch.full((full_sequence_len, A + 5), -np.inf, dtype=torch.float32, device=dev)
+    rows = torch.tensor([MSA_start + c for c in focus_cols], dtype=torch.long, device=dev)
+    prior[rows, 5:] = recon[0]
+    return prior
+
+
+def cache_location(EVE_model_path: str, num_samples: int) -> str:
+    parts = EVE_model_path.split("/")
+    return "/".join(parts[:-1]) + os.sep + "log_prior" + os.sep + "_".join([parts[-1], str(num_samples), "log_space"])
+
+
+def eve_log_prior(EVE_model_paths, EVE_model_parameters_location: str, msa, full_sequence_len: int, MSA_start: int,
+                  EVE_num_samples_log_proba: int = 10, device="cuda") -> torch.Tensor:
+    """get_EVE_models_and_log_prior (model_pytorch.py:940-967): ensemble mean of the per-model priors, each read from / written to
+    the reference's cache location. ``msa`` is the MSAProcessing of the retrieved alignment (focus columns, trimmed focus sequence)."""
+    params = json.load(open(EVE_model_parameters_location))
+    total = 0
+    for path in EVE_model_paths:
+        loc = cache_location(path, EVE_num_samples_log_proba)
+        os.makedirs(os.path.dirname(loc), exist_ok=True)
+        if not os.path.exists(loc):
+            print("Computing EVE log prior")
+            ck = torch.load(path, map_location="cpu")
+            single = eve_log_prior_single(ck["model_state_dict"], params, msa.focus_seq_trimmed, msa.focus_cols, full_sequence_len, MSA_start,
+                                          EVE_num_samples_log_proba, device)
+            with open(loc, "wb") as fh:
+                pickle.dump(single.cpu(), fh)
+        else:
+            print("Loading EVE log prior from disk")
+            with open(loc, "rb") as fh:
+                single = pickle.load(fh)
+            single = torch.as_tensor(single)
+        total = total + single.to(device)
+    return total / len(EVE_model_paths)

@@ -6,8 +6,8 @@
   * ``cluster_weights``   -> EVE-style sequence weights 1/|cluster| (proteingym/utils/weights.py:13-53 ``calc_weights_fast``),
     the O(N^2 L) pairwise identity count in ``pg_msa_cluster_neighbors`` (numba on CPU in the reference).
 
-Not reproduced: ``MSA_processing`` (utils/msa_utils.py:24-255: focus-column / fragment filtering and the name->weight map
-read from a ``.npy``); callers that have such weights pass them as a ``{sequence name: weight}`` dict."""
+``MSA_processing`` (focus-column / fragment filtering, the name->weight map read from or written to a ``.npy``) and the
+reference-signature ``get_msa_prior`` live in msa_processing.py; here weights arrive as a ``{sequence name: weight}`` dict."""
 from __future__ import annotations
 
 from collections import defaultdict
@@ -45,9 +45,8 @@ def encode(seqs, unknown=255) -> np.ndarray:
     return lut[arr]
 
 
-def msa_prior(msa: dict, MSA_start: int, MSA_end: int, len_target_seq: int, weights: dict | None = None, filter_MSA: bool = True,
-              device: int = 0) -> np.ndarray:
-    """get_msa_prior(..., retrieval_aggregation_mode="aggregate_substitution") -> float64 [len_target_seq, 25]."""
+def _select(msa: dict, weights: dict | None, filter_MSA: bool):
+    """Sequences get_msa_prior keeps (hamming filter, then those that have a weight) -> (names, tokens [N, L], weights [N])."""
     names = list(msa.keys())
     tok = encode([msa[n] for n in names])
     if filter_MSA:  # hamming similarity to the first sequence over its in-vocabulary positions (msa_utils.py:84-92)
@@ -58,12 +57,25 @@ def msa_prior(msa: dict, MSA_start: int, MSA_end: int, len_target_seq: int, weig
         names = [n for n, k in zip(names, keep) if k]
         tok = tok[keep]
     if weights is not None:  # sequences without a weight are dropped (msa_utils.py:103-110)
-        keep = np.array([n in weights for n in names])
+        keep = np.array([n in weights for n in names], dtype=bool)
         tok = tok[keep]
         names = [n for n, k in zip(names, keep) if k]
         w = np.array([weights[n] for n in names], dtype=np.float64)
     else:
         w = np.ones(len(names), dtype=np.float64)
+    return names, tok, w
+
+
+def filtered_depth(msa: dict, weights: dict | None = None, filter_MSA: bool = True) -> int:
+    """``processed_MSA_depth`` of the TranceptEVE get_msa_prior (trancepteve/utils/msa_utils.py:117)."""
+    return len(_select(msa, weights, filter_MSA)[0])
+
+
+def msa_prior(msa: dict, MSA_start: int, MSA_end: int, len_target_seq: int, weights: dict | None = None, filter_MSA: bool = True,
+              device: int = 0, return_depth: bool = False):
+    """get_msa_prior(..., retrieval_aggregation_mode="aggregate_substitution") -> float64 [len_target_seq, 25]
+    (and the number of sequences that went into it when ``return_depth``)."""
+    names, tok, w = _select(msa, weights, filter_MSA)
     Lm = MSA_end - MSA_start
     cols = np.full((len(names), Lm), 255, dtype=np.uint8)  # one_hots has MSA_end-MSA_start columns; sequences fill from column 0
     n = min(Lm, tok.shape[1])
@@ -79,7 +91,7 @@ def msa_prior(msa: dict, MSA_start: int, MSA_end: int, len_target_seq: int, weig
                                 torch.cuda.current_stream(dev).cuda_stream))
     prior = np.zeros((len_target_seq, VOCAB_SIZE))
     prior[MSA_start:MSA_end, :] = out.cpu().numpy()
-    return prior
+    return (prior, len(names)) if return_depth else prior
 
 
 def msa_log_prior(msa_file: str, MSA_start: int, MSA_end: int, len_target_seq: int, weights: dict | None = None, device: int = 0):

@@ -1,8 +1,8 @@
 """Drop-in for ``proteingym/baselines/tranception/score_tranception_proteingym.py`` (same flags, same output CSV:
 ``mutated_sequence, avg_score_L_to_R, avg_score_R_to_L, avg_score``; reference lines :18-45 flags, :57-77 DMS resolution,
-:105-122 scoring + CSV). Inference-time retrieval for substitutions builds the unweighted MSA prior on the GPU (msa_prior.py, utils/msa_utils.py:63-138);
-EVE sequence-weight files (MSA_processing) are not reproduced: pass a precomputed ``[L_full, 25]`` log-prior with ``--MSA_log_prior_npy``.
-Additive flags: --precision, --device, --MSA_log_prior_npy."""
+:105-122 scoring + CSV). Inference-time retrieval for substitutions builds the MSA prior on the GPU (msa_processing.get_msa_prior =
+utils/msa_utils.py:63-138), with EVE-style sequence weights read from ``--MSA_weights_folder`` through the MSA_processing mirror when
+given. Additive flags: --precision, --device, --MSA_log_prior_npy (a precomputed ``[L_full, 25]`` log prior)."""
 from __future__ import annotations
 
 import argparse
@@ -26,7 +26,7 @@ _FLAGS = [
     ("--target_seq", dict(default=None, type=str, help="wild type when no reference file is used")),
     ("--DMS_file_name", dict(default=None, type=str, help="assay CSV when no reference file is used")),
     ("--MSA_filename", dict(default=None, type=str, help="a2m alignment of the wild type (retrieval)")),
-    ("--MSA_weight_file_name", dict(default=None, type=str, help="EVE sequence weights (not supported, see module docstring)")),
+    ("--MSA_weight_file_name", dict(default=None, type=str, help="EVE sequence weights (.npy) inside --MSA_weights_folder")),
     ("--MSA_start", dict(default=None, type=int, help="first position covered by the MSA, 1-based")),
     ("--MSA_end", dict(default=None, type=int, help="last position covered by the MSA, 1-based")),
     ("--DMS_data_folder", dict(type=str, help="folder with the assay CSVs")),
@@ -38,7 +38,7 @@ _FLAGS = [
     ("--inference_time_retrieval", dict(action="store_true", help="fuse the MSA prior into the token log-probabilities")),
     ("--retrieval_inference_weight", dict(default=0.6, type=float, help="alpha of the fusion")),
     ("--MSA_folder", dict(default=".", type=str, help="folder with the MSAs")),
-    ("--MSA_weights_folder", dict(default=None, type=str, help="folder with EVE weights (not supported)")),
+    ("--MSA_weights_folder", dict(default=None, type=str, help="folder with the EVE sequence-weight files")),
     ("--clustal_omega_location", dict(default=None, type=str, help="(indel retrieval only; not supported)")),
 ]
 
@@ -81,15 +81,17 @@ def main(argv=None):
         if args.MSA_log_prior_npy:
             log_prior = np.load(args.MSA_log_prior_npy)
         else:
-            if args.MSA_weights_folder is not None:
-                raise NotImplementedError("EVE sequence-weight files need MSA_processing (not reproduced); pass --MSA_log_prior_npy "
-                                          "or omit --MSA_weights_folder for the unweighted prior")
-            from proteingym_b200.msa_prior import msa_log_prior
+            from proteingym_b200.msa_processing import get_msa_prior
             if args.DMS_reference_file_path:
                 msa_file = args.MSA_folder + os.sep + mapping["MSA_filename"][args.DMS_index]
+                wfile = args.MSA_weights_folder + os.sep + mapping["weight_file_name"][sel].values[0] if args.MSA_weights_folder else None
             else:
                 msa_file = args.MSA_folder + os.sep + args.MSA_filename
-            log_prior = msa_log_prior(msa_file, MSA_start, MSA_end, len(target_seq), device=args.device)  # model_pytorch.py:660-671
+                wfile = args.MSA_weights_folder + os.sep + args.MSA_weight_file_name if args.MSA_weights_folder is not None else None
+            prior = get_msa_prior(msa_file, wfile, MSA_start, MSA_end, len(target_seq), verbose=True, return_depth=False,
+                                  device=args.device)  # model_pytorch.py:660-671
+            with np.errstate(divide="ignore"):
+                log_prior = np.log(prior).astype(np.float32)
     config, state = load_tranception_checkpoint(args.checkpoint)
     scorer = TranceptionScorer(config, state, precision=args.precision, device=args.device)
     if not os.path.isdir(args.output_scores_folder):

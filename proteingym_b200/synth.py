@@ -277,21 +277,72 @@ def random_indels(seq: str, n: int, seed: int, max_len: int = 4):
     return sorted(out)
 
 
-def synthetic_msa(target_seq: str, n: int, seed: int, sub_rate=(0.05, 0.9), gap_rate=0.1):
-    """name -> aligned sequence (a2m-like, upper case, '-' gaps, occasional 'X'); first entry is the target itself."""
+def synthetic_msa(target_seq: str, n: int, seed: int, sub_rate=(0.05, 0.9), gap_rate=0.1, gappy_cols=(), gappy_rate=0.6):
+    """name -> aligned sequence (a2m-like, upper case, '-' gaps, occasional 'X'); first entry is the target itself.
+    ``gappy_cols`` get gaps at ``gappy_rate`` instead (columns that fall below a focus-column occupancy threshold)."""
     rng = np.random.RandomState(seed)
     msa = {">target/1-%d" % len(target_seq): target_seq}
+    gappy = set(gappy_cols)
     for i in range(n - 1):
         r = rng.uniform(*sub_rate)
         s = list(target_seq)
         for j in range(len(s)):
             u = rng.rand()
-            if u < gap_rate:
+            if u < (gappy_rate if j in gappy else gap_rate):
                 s[j] = "-"
             elif u < gap_rate + r:
                 s[j] = AA20[rng.randint(0, 20)] if rng.rand() > 0.02 else "X"
         msa[">seq%d" % i] = "".join(s)
     return msa
+
+
+# EVE VAE (trancepteve/EVE/VAE_model.py) at toy width: same keys as utils/eve_model_default_params.json
+EVE_TINY_PARAMS = {
+    "encoder_parameters": {"hidden_layers_sizes": [48, 32, 24], "z_dim": 8, "convolve_input": False, "convolution_input_depth": 40,
+                           "nonlinear_activation": "relu", "dropout_proba": 0.0},
+    "decoder_parameters": {"hidden_layers_sizes": [24, 32, 50], "z_dim": 8, "bayesian_decoder": True, "first_hidden_nonlinearity": "relu",
+                           "last_hidden_nonlinearity": "relu", "dropout_proba": 0.1, "convolve_output": True, "convolution_output_depth": 10,
+                           "include_temperature_scaler": True, "include_sparsity": False, "num_tiles_sparsity": 0, "logit_sparsity_p": 0},
+}
+
+
+def make_eve_state(seq_len: int, params: dict = None, seed: int = 0, log_var: float = -4.0) -> dict:
+    """Seeded ``model_state_dict`` of the reference's EVE ``VAE_model`` (MLP encoder + Bayesian MLP decoder with 1x1 output
+    convolution and temperature scaler; key names/shapes as VAE_encoder.py:40-52, VAE_decoder.py:47-108). ``log_var`` sets every
+    weight-posterior log-variance (the reference initialises them to -10; a larger value makes the sampling noise visible)."""
+    params = params or EVE_TINY_PARAMS
+    g = torch.Generator().manual_seed(seed)
+    A = 20
+    enc, dec = params["encoder_parameters"], params["decoder_parameters"]
+
+    def lin(o, i):
+        return torch.randn((o, i), generator=g) / math.sqrt(i), 0.1 + 0.05 * torch.randn(o, generator=g)
+
+    st = {}
+    sizes = [A * seq_len] + list(enc["hidden_layers_sizes"])
+    for k in range(len(sizes) - 1):
+        st[f"encoder.hidden_layers.{k}.weight"], st[f"encoder.hidden_layers.{k}.bias"] = lin(sizes[k + 1], sizes[k])
+    st["encoder.fc_mean.weight"], st["encoder.fc_mean.bias"] = lin(enc["z_dim"], sizes[-1])
+    w, _ = lin(enc["z_dim"], sizes[-1])
+    st["encoder.fc_log_var.weight"], st["encoder.fc_log_var.bias"] = 0.1 * w, torch.full((enc["z_dim"],), -2.0)
+    H = dec["hidden_layers_sizes"]
+    C = dec["convolution_output_depth"] if dec["convolve_output"] else A
+    st["decoder.last_hidden_layer_weight_mean"] = torch.randn((C * seq_len, H[-1]), generator=g) * math.sqrt(2.0 / (C * seq_len + H[-1]))
+    st["decoder.last_hidden_layer_weight_log_var"] = torch.full((C * seq_len, H[-1]), log_var)
+    st["decoder.last_hidden_layer_bias_mean"] = 0.1 + 0.3 * torch.randn(A * seq_len, generator=g)
+    st["decoder.last_hidden_layer_bias_log_var"] = torch.full((A * seq_len,), log_var)
+    if dec["include_temperature_scaler"]:
+        st["decoder.temperature_scaler_mean"] = torch.ones(1) * 2.0
+        st["decoder.temperature_scaler_log_var"] = torch.full((1,), log_var)
+    dsz = [dec["z_dim"]] + list(H)
+    for k in range(len(H)):
+        st[f"decoder.hidden_layers_mean.{k}.weight"], st[f"decoder.hidden_layers_mean.{k}.bias"] = lin(dsz[k + 1], dsz[k])
+        st[f"decoder.hidden_layers_log_var.{k}.weight"] = torch.full((dsz[k + 1], dsz[k]), log_var)
+        st[f"decoder.hidden_layers_log_var.{k}.bias"] = torch.full((dsz[k + 1],), log_var)
+    if dec["convolve_output"]:
+        st["decoder.output_convolution_mean.weight"] = torch.randn((A, C, 1), generator=g) / math.sqrt(C) * 3.0
+        st["decoder.output_convolution_log_var.weight"] = torch.full((A, C, 1), log_var)
+    return st
 
 
 def write_a2m(path: str, msa: dict, width: int = 60):

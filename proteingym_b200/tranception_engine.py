@@ -90,6 +90,39 @@ def replace_ambiguous(seq: str) -> str:
     return seq
 
 
+def prior_rows(prow, prow2, ws, we, msa_start, msa_end, flip, nonfocus=None):
+    """Index arithmetic of the retrieval fusion for one sequence slice [ws, we) of the full protein (Tranception
+    model_pytorch.py:811-830; TranceptEVE model_pytorch.py:1085-1133): fill ``prow`` (and ``prow2`` for the EVE table) with the prior
+    row to mix into each predicted position, in the encoding pg_ar_fusion documents. Position a0+i of the slice takes row lo+i
+    (left-to-right) or hi-1-i (``flip``: the slice of the prior is reversed with the sequence).
+
+    ``nonfocus`` (bool per prior row, TranceptEVE with a focus-column threshold < 1): rows where the EVE prior is -inf. The reference
+    finds them after fusion, converts their position ix back to protein coordinates as ix + ws — also for flipped sequences, where
+    that is not the position's true coordinate — and re-fuses them with the MSA prior alone, taking row (ix + ws) - lo of the
+    (possibly reversed) prior slice, or with nothing but the (1 - alpha) factor when ix + ws falls outside the MSA."""
+    lo, hi = max(ws, msa_start), min(we, msa_end)
+    if not (msa_start < we and msa_end > ws) or hi <= lo:
+        return
+    n = hi - lo
+    a0 = max(0, we - msa_end) if flip else max(0, msa_start - ws)
+    rows = np.arange(hi - 1, lo - 1, -1) if flip else np.arange(lo, hi)
+    prow[a0:a0 + n] = rows
+    if prow2 is None:
+        return
+    prow2[a0:a0 + n] = rows
+    if nonfocus is None:
+        return
+    for i in np.nonzero(nonfocus[rows])[0]:
+        ix = a0 + int(i)
+        full = ix + ws
+        prow2[ix] = -1
+        if msa_start <= full < msa_end:
+            k = full - lo
+            prow[ix] = (hi - 1 - k) if flip else (lo + k)
+        else:
+            prow[ix] = -2
+
+
 class TranceptionScorer:
     def __init__(self, config: dict, state: dict, precision: str = "f16x3", device: int = 0, max_rows: int = 0):
         if not torch.cuda.is_available():
@@ -142,21 +175,31 @@ class TranceptionScorer:
             pass
 
     # ------------------------------------------------------------------------------------------------------------
-    def sequence_logprobs(self, seqs, prior=None, windows=None, flip=False, alpha=0.6, msa_start=0, msa_end=None, chunk_rows=1 << 17):
+    def sequence_logprobs(self, seqs, prior=None, windows=None, flip=False, alpha=0.6, msa_start=0, msa_end=None, chunk_rows=1 << 17,
+                          prior2=None, beta=0.0, first_col=0, nonfocus_fallback=False, return_rows=False):
         """sum_t log p(tok_{t+1} | tok_<=t) of ``[CLS] s [SEP]`` for every string in ``seqs`` (float32 numpy).
         ``prior`` ([L_full, vocab] log-probabilities) with per-sequence ``windows`` [(start, end)] enables the retrieval
-        fusion of model_pytorch.py:806-830; ``flip`` marks right-to-left scoring (the strings are already reversed)."""
+        fusion of model_pytorch.py:806-830; ``flip`` marks right-to-left scoring (the strings are already reversed).
+        ``prior2`` / ``beta`` / ``first_col`` / ``nonfocus_fallback``: the TranceptEVE three-way fusion (see ``prior_rows``).
+        ``return_rows``: also return, per sequence, the fused log-probabilities [len(s) + 1, vocab] of every predicted position."""
         n = len(seqs)
         out = np.zeros(n, dtype=np.float32)
+        rows_out = [None] * n
         if n == 0:
-            return out
+            return (out, rows_out) if return_rows else out
         order = np.argsort([len(s) for s in seqs], kind="stable")
-        d_prior = torch.from_numpy(np.ascontiguousarray(prior, dtype=np.float32)).to(self.device) if prior is not None else None
+
+        def dev32(a):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device) if a is not None else None
+
+        d_prior, d_prior2 = dev32(prior), dev32(prior2)
         msa_end = (prior.shape[0] if msa_end is None else msa_end) if prior is not None else None
+        nonfocus = None
+        if prior2 is not None and nonfocus_fallback and beta > 0:  # rows whose EVE prior is -inf drag the fused value to -inf (:1118)
+            nonfocus = np.asarray(prior2)[:, 5:].min(axis=1) == -np.inf
         stream = torch.cuda.current_stream(self.device).cuda_stream
         i = 0
         while i < n:
-            T = len(seqs[order[min(n - 1, i)]]) + 2
             # grow the chunk while the padded row count stays within budget (sequences are sorted by length)
             j = i
             while j < n and (j - i + 1) * (len(seqs[order[j]]) + 2) <= chunk_rows:
@@ -167,31 +210,33 @@ class TranceptionScorer:
             ids = np.full((len(idx), T), PAD, dtype=np.int32)
             lens = np.zeros(len(idx), dtype=np.int32)
             prow = np.full((len(idx), T), -1, dtype=np.int32) if prior is not None else None
+            prow2 = np.full((len(idx), T), -1, dtype=np.int32) if prior2 is not None else None
             for r, k in enumerate(idx):
                 t = tokenize(replace_ambiguous(seqs[k]))
                 ids[r, :len(t)] = t
                 lens[r] = len(t)
                 if prior is not None:
-                    ws, we = windows[k]
-                    lo, hi = max(ws, msa_start), min(we, msa_end)
-                    if hi > lo:
-                        if flip:
-                            a0 = max(0, we - msa_end)
-                            prow[r, a0:a0 + hi - lo] = np.arange(hi - 1, lo - 1, -1)
-                        else:
-                            a0 = max(0, msa_start - ws)
-                            prow[r, a0:a0 + hi - lo] = np.arange(lo, hi)
+                    prior_rows(prow[r], prow2[r] if prow2 is not None else None, windows[k][0], windows[k][1], msa_start, msa_end, flip, nonfocus)
             d_ids = torch.from_numpy(ids).to(self.device)
             d_lens = torch.from_numpy(lens).to(self.device)
             d_prow = torch.from_numpy(prow).to(self.device) if prow is not None else None
+            d_prow2 = torch.from_numpy(prow2).to(self.device) if prow2 is not None else None
             d_out = torch.empty(len(idx), dtype=torch.float32, device=self.device)
-            _lib.check(self.lib.pg_ar_loglik(self.handle, d_ids.data_ptr(), d_lens.data_ptr(), len(idx), T,
-                                             d_prior.data_ptr() if d_prior is not None else None,
-                                             d_prow.data_ptr() if d_prow is not None else None, float(alpha), d_out.data_ptr(), stream),
-                       self.handle)
+            d_rows = torch.zeros((len(idx), T, self.vocab), dtype=torch.float32, device=self.device) if return_rows else None
+            f = _lib.PgArFusion(log_prior=d_prior.data_ptr() if d_prior is not None else None,
+                                prior_row=d_prow.data_ptr() if d_prow is not None else None, alpha=float(alpha),
+                                log_prior2=d_prior2.data_ptr() if d_prior2 is not None else None,
+                                prior_row2=d_prow2.data_ptr() if d_prow2 is not None else None, beta=float(beta),
+                                first_col=int(first_col), out_logprobs=d_rows.data_ptr() if d_rows is not None else None)
+            _lib.check(self.lib.pg_ar_loglik_fused(self.handle, d_ids.data_ptr(), d_lens.data_ptr(), len(idx), T, C.byref(f),
+                                                   d_out.data_ptr(), stream), self.handle)
             out[idx] = d_out.cpu().numpy()
+            if return_rows:
+                h_rows = d_rows.cpu().numpy()
+                for r, k in enumerate(idx):
+                    rows_out[k] = h_rows[r, :lens[r] - 1]
             i = j
-        return out
+        return (out, rows_out) if return_rows else out
 
     # ------------------------------------------------------------------------------------------------------------
     @staticmethod

@@ -1,0 +1,183 @@
+"""GPU (-m gpu): the retrieval / TranceptEVE rows end to end through the C-ABI (pg_ar_loglik_fused, pg_msa_prior,
+pg_msa_cluster_neighbors) against outputs of the reference's UNMODIFIED TrancepteveLMHeadModel / TranceptionLMHeadModel classes
+(tests/golden/trancepteve_*, tests/golden/tranception_retrieval; oracle/gen_golden_trancepteve.py). Score tolerance 1e-3 abs."""
+import json
+import os
+import pickle
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from conftest import GOLDEN
+from trancepteve_cases import CASES, make_inputs
+
+from proteingym_b200 import eve_prior, synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _setup(name, tmp_path, with_weights=True, with_cache=True):
+    """Files of a case as the reference's launcher would find them: MSA, weights .npy, Tranception checkpoint folder, EVE
+    checkpoints (+ the per-model log-prior caches holding the reference's own samples)."""
+    case = CASES[name]
+    meta = json.load(open(os.path.join(GOLDEN, name, "meta.json")))
+    gd = os.path.join(GOLDEN, name)
+    inp = make_inputs(case, str(tmp_path), weights_file=os.path.join(gd, "msa_weights.npy") if with_weights else None)
+    ck = str(tmp_path / "ckpt")
+    synth.write_tranception_checkpoint(ck, inp["arch"], meta["tranception_seed"])
+    paths = []
+    for i, sd in enumerate(case["eve_seeds"]):
+        pth = os.path.join(inp["eve_dir"], f"TARGET_msa_seed_{sd}")
+        torch.save({"model_state_dict": synth.make_eve_state(meta["focus_seq_len"], seed=100 + sd)}, pth)
+        paths.append(pth)
+        if with_cache:
+            loc = eve_prior.cache_location(pth, case["n_samples"])
+            os.makedirs(os.path.dirname(loc), exist_ok=True)
+            with open(loc, "wb") as fh:
+                pickle.dump(torch.from_numpy(np.load(os.path.join(gd, f"eve_log_prior_model{i}.npy"))), fh)
+    return case, meta, gd, inp, ck, paths
+
+
+def _scorer(case, meta, inp, ck, paths, precision="f16x3"):
+    from proteingym_b200.tranception_engine import load_tranception_checkpoint
+    from proteingym_b200.trancepteve_engine import TranceptEVEScorer
+    config, state = load_tranception_checkpoint(ck)
+    return TranceptEVEScorer(config, state, full_target_seq=meta["target_seq"], inference_time_retrieval_type=case["kind"],
+                             retrieval_aggregation_mode="aggregate_substitution", MSA_filename=inp["msa_file"],
+                             MSA_weight_file_name=inp["weights_file"], MSA_start=case["msa"][0], MSA_end=case["msa"][1],
+                             MSA_threshold_sequence_frac_gaps=case["seq_thr"], MSA_threshold_focus_cols_frac_gaps=case["col_thr"],
+                             EVE_model_paths=paths or None, EVE_num_samples_log_proba=case["n_samples"],
+                             EVE_model_parameters_location=inp["params_file"], MSA_recalibrate_probas=case["msa_recal"],
+                             EVE_recalibrate_probas=case["eve_recal"], precision=precision, max_rows=32768)
+
+
+def _same_prior(mine, want, tol):
+    mine, want = np.asarray(mine), np.asarray(want)
+    assert np.array_equal(np.isfinite(mine), np.isfinite(want))
+    assert np.abs(np.nan_to_num(mine, neginf=0) - np.nan_to_num(want, neginf=0)).max() < tol
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_trancepteve_constructor_recalibration_and_scores(name, tmp_path):
+    case, meta, gd, inp, ck, paths = _setup(name, tmp_path)
+    sc = _scorer(case, meta, inp, ck, paths)
+    assert (sc.MSA_processed_depth, sc.EVE_processed_depth) == (meta["MSA_processed_depth"], meta["EVE_processed_depth"])
+    assert (sc.retrieval_inference_MSA_weight, sc.retrieval_inference_EVE_weight) == \
+        (meta["retrieval_inference_MSA_weight"], meta["retrieval_inference_EVE_weight"])
+    _same_prior(sc.MSA_log_prior, np.load(os.path.join(gd, "msa_log_prior_init.npy")), 1e-5)   # pg_msa_prior (fp64) + weights by name
+    if case["kind"] == "TranceptEVE":
+        _same_prior(sc.EVE_log_prior, np.load(os.path.join(gd, "eve_log_prior_init.npy")), 1e-6)  # ensemble mean of the caches
+    rows, labels = sc.get_transformer_log_softmax(meta["target_seq"])                          # out_logprobs of the fused call
+    assert list(labels) == meta["wt_shift_labels"]
+    assert np.abs(rows.numpy() - np.load(os.path.join(gd, "wt_log_softmax_msa_fused.npy"))).max() < TOL
+    got = sc.score_mutants(inp["dms"], meta["target_seq"])
+    ref = pd.read_csv(os.path.join(gd, "reference_scores.csv"))
+    assert list(got.columns) == list(ref.columns) and list(got["mutated_sequence"]) == list(ref["mutated_sequence"])
+    assert list(got["mutant"]) == list(ref["mutant"])
+    for c in ("avg_score_L_to_R", "avg_score_R_to_L", "avg_score"):
+        assert np.abs(got[c].to_numpy(dtype=np.float64) - ref[c].to_numpy(dtype=np.float64)).max() < TOL, c
+    _same_prior(sc.MSA_log_prior, np.load(os.path.join(gd, "msa_log_prior_final.npy")), 5e-3)   # after recalibration
+    if case["kind"] == "TranceptEVE":
+        _same_prior(sc.EVE_log_prior, np.load(os.path.join(gd, "eve_log_prior_final.npy")), 5e-3)
+    sc.close()
+
+
+def test_fast_precision_keeps_ranking(tmp_path):
+    from scipy.stats import spearmanr
+    case, meta, gd, inp, ck, paths = _setup("trancepteve_subs", tmp_path)
+    sc = _scorer(case, meta, inp, ck, paths, precision="f16")
+    got = sc.score_mutants(inp["dms"], meta["target_seq"])
+    sc.close()
+    ref = pd.read_csv(os.path.join(gd, "reference_scores.csv"))
+    assert np.abs(got["avg_score"].values - ref["avg_score"].values).max() < 2e-2
+    assert spearmanr(got["avg_score"].values, ref["avg_score"].values).correlation > 0.999
+
+
+@pytest.mark.parametrize("name", ["trancepteve_subs", "trancepteve_nonfocus"])
+def test_sequence_weights_computed_on_gpu_match_reference(name, tmp_path):
+    """No readable weights file -> MSAProcessing computes 1/|cluster| with pg_msa_cluster_neighbors and saves it; the reference's
+    numpy loop wrote tests/golden/<case>/msa_weights.npy (same sequence order)."""
+    from proteingym_b200.msa_processing import MSAProcessing
+    case = CASES[name]
+    inp = make_inputs(case, str(tmp_path))
+    open(inp["weights_file"], "wb").close()
+    m = MSAProcessing(inp["msa_file"], weights_location=inp["weights_file"], threshold_sequence_frac_gaps=case["seq_thr"],
+                      threshold_focus_cols_frac_gaps=case["col_thr"])
+    want = np.load(os.path.join(GOLDEN, name, "msa_weights.npy"))
+    assert m.weights.shape == want.shape and np.abs(m.weights - want).max() < 1e-12
+    assert np.array_equal(np.load(inp["weights_file"]), m.weights) and abs(m.Neff - want.sum()) < 1e-9
+
+
+def test_eve_prior_on_device_matches_host_arithmetic(tmp_path):
+    """The sampler's tensor algebra on the GPU against the same function on the CPU, with the posterior variances switched off
+    (log-variance -80) so the two generators' different streams cannot matter; plus the stochastic run's support and scale."""
+    L = 23
+    focus = list(synth.random_protein(L, 3))
+    cols = list(range(L))
+    st0 = synth.make_eve_state(L, seed=7, log_var=-80.0)
+    st0["encoder.fc_log_var.bias"] = torch.full_like(st0["encoder.fc_log_var.bias"], -80.0)
+    st0["encoder.fc_log_var.weight"] = torch.zeros_like(st0["encoder.fc_log_var.weight"])
+    a = eve_prior.eve_log_prior_single(st0, synth.EVE_TINY_PARAMS, focus, cols, L + 4, 2, 3, device="cpu")
+    b = eve_prior.eve_log_prior_single(st0, synth.EVE_TINY_PARAMS, focus, cols, L + 4, 2, 3, device="cuda").cpu()
+    assert torch.equal(torch.isfinite(a), torch.isfinite(b))
+    fin = torch.isfinite(a)
+    assert (a[fin] - b[fin]).abs().max() < 1e-4
+    assert torch.isinf(b[:2]).all() and torch.isinf(b[2 + L:]).all() and torch.isinf(b[:, :5]).all()
+    st1 = synth.make_eve_state(L, seed=7)
+    c = eve_prior.eve_log_prior_single(st1, synth.EVE_TINY_PARAMS, focus, cols, L + 4, 2, 3000, device="cuda").cpu()
+    d = eve_prior.eve_log_prior_single(st1, synth.EVE_TINY_PARAMS, focus, cols, L + 4, 2, 3000, device="cpu")
+    assert torch.equal(torch.isfinite(c), torch.isfinite(d)) and (c[fin] - d[fin]).abs().mean() < 0.2  # Monte-Carlo agreement (3000 draws; two streams differ by ~0.08)
+
+
+def test_cli_end_to_end(tmp_path, monkeypatch):
+    """score_trancepteve.py drop-in, manual-fields mode: CSV columns / rows / values as the reference's, coefficient log appended."""
+    from proteingym_b200 import score_trancepteve
+    name = "trancepteve_subs"
+    case, meta, gd, inp, ck, paths = _setup(name, tmp_path)
+    dms_dir, out_dir = tmp_path / "dms", tmp_path / "out"
+    dms_dir.mkdir()
+    inp["dms"].to_csv(dms_dir / "ASSAY1.csv", index=False)
+    monkeypatch.chdir(tmp_path)
+    score_trancepteve.main([
+        "--checkpoint", ck, "--target_seq", meta["target_seq"], "--DMS_file_name", "ASSAY1.csv", "--DMS_data_folder", str(dms_dir),
+        "--output_scores_folder", str(out_dir), "--inference_time_retrieval_type", "TranceptEVE", "--MSA_folder", str(tmp_path),
+        "--MSA_filename", "TARGET_msa.a2m", "--MSA_weights_folder", str(tmp_path), "--MSA_weight_file_name", "TARGET_weights.npy",
+        "--MSA_start", str(case["msa"][0] + 1), "--MSA_end", str(case["msa"][1]), "--MSA_threshold_sequence_frac_gaps", str(case["seq_thr"]),
+        "--MSA_threshold_focus_cols_frac_gaps", str(case["col_thr"]), "--EVE_model_folder", inp["eve_dir"], "--EVE_seeds", "0",
+        "--EVE_num_samples_log_proba", str(case["n_samples"]), "--EVE_model_parameters_location", inp["params_file"],
+        "--EVE_recalibrate_probas"])
+    got = pd.read_csv(out_dir / "ASSAY1.csv")
+    ref = pd.read_csv(os.path.join(gd, "reference_scores.csv"))
+    assert list(got.columns) == list(ref.columns) and list(got["mutant"]) == list(ref["mutant"])
+    assert np.abs(got["avg_score"].values - ref["avg_score"].values).max() < TOL
+    log = (tmp_path / "TranceptEVE_aggregation_coefficients_log").read_text().splitlines()
+    assert log[0].startswith("DMS_id,num_mutants_scored") and log[1].split(",")[:2] == ["ASSAY1", str(len(ref))]
+    assert log[1].split(",")[-2:] == [str(meta["retrieval_inference_MSA_weight"]), str(meta["retrieval_inference_EVE_weight"])]
+
+
+def test_tranception_cli_retrieval_with_sequence_weights(tmp_path):
+    """score_tranception_proteingym.py --inference_time_retrieval with an EVE weights file, against the reference's real
+    TranceptionLMHeadModel (tests/golden/tranception_retrieval): weighted MSA prior on the GPU + alpha = 0.6 fusion on all columns."""
+    from proteingym_b200 import score_tranception_proteingym
+    gd = os.path.join(GOLDEN, "tranception_retrieval")
+    meta = json.load(open(os.path.join(gd, "meta.json")))
+    case = meta["case"]
+    inp = make_inputs(case, str(tmp_path), weights_file=os.path.join(gd, "msa_weights.npy"))
+    ck = str(tmp_path / "ckpt")
+    synth.write_tranception_checkpoint(ck, inp["arch"], meta["tranception_seed"])
+    dms_dir, out_dir = tmp_path / "dms", tmp_path / "out"
+    dms_dir.mkdir()
+    inp["dms"].to_csv(dms_dir / "ASSAY2.csv", index=False)
+    score_tranception_proteingym.main([
+        "--checkpoint", ck, "--target_seq", meta["target_seq"], "--DMS_file_name", "ASSAY2.csv", "--DMS_data_folder", str(dms_dir),
+        "--output_scores_folder", str(out_dir), "--inference_time_retrieval", "--MSA_folder", str(tmp_path), "--MSA_filename", "TARGET_msa.a2m",
+        "--MSA_weights_folder", str(tmp_path), "--MSA_weight_file_name", "TARGET_weights.npy", "--MSA_start", str(case["msa"][0] + 1),
+        "--MSA_end", str(case["msa"][1])])
+    got = pd.read_csv(out_dir / "ASSAY2.csv")
+    ref = pd.read_csv(os.path.join(gd, "reference_scores.csv"))
+    assert list(got.columns) == list(ref.columns) and list(got["mutated_sequence"]) == list(ref["mutated_sequence"])
+    for c in ("avg_score_L_to_R", "avg_score_R_to_L", "avg_score"):
+        assert np.abs(got[c].values - ref[c].values).max() < TOL, c

@@ -1,12 +1,16 @@
 """CPU: the oracle restatement (oracle/esm_oracle.py) against golden vectors produced by the UNMODIFIED reference
 (oracle/gen_golden.py ran /root/reference's compute_fitness.main + fair-esm modules on the same seeded checkpoints)."""
+import json
+import os
+
 import numpy as np
 import pandas as pd
 import pytest
 import torch
 
-from conftest import GOLDEN_SMALL, GOLDEN_WINDOW, load_golden
+from conftest import GOLDEN, GOLDEN_SMALL, GOLDEN_WINDOW, load_golden
 from oracle import esm_oracle as O
+from proteingym_b200 import synth
 
 
 def _kind(arch):
@@ -127,3 +131,24 @@ def test_msa_prior_and_weights_oracle_match_reference():
     g = np.load(os.path.join(GOLDEN, "msa_weights_reference.npz"))
     w = TO.cluster_weights(g["matrix"].astype(np.int64), meta["identity_threshold"])
     assert np.array_equal(w, g["weights"]) and w[5] == 0
+
+
+def test_tranception_oracle_retrieval_vs_real_reference_class(tmp_path):
+    """tests/golden/tranception_retrieval comes from the reference's real TranceptionLMHeadModel (oracle/gen_golden_trancepteve.py
+    tranception): weighted MSA log prior fused with alpha = 0.6 on every vocabulary column (model_pytorch.py:806-830)."""
+    from trancepteve_cases import make_inputs
+    from oracle import tranception_oracle as TO
+    gd = os.path.join(GOLDEN, "tranception_retrieval")
+    meta = json.load(open(os.path.join(gd, "meta.json")))
+    case = meta["case"]
+    a = case["arch"]
+    arch = synth.TranceptionArch(a[0], a[1], a[2], a[3], n_ctx=a[4])
+    st = synth.make_tranception_state(arch, meta["tranception_seed"])
+    inp = make_inputs(case, str(tmp_path))
+    lp = torch.tensor(np.load(os.path.join(gd, "msa_log_prior.npy")))
+    out = TO.score_mutants(st, inp["dms"], meta["target_seq"], arch.layers, arch.heads, n_ctx=arch.n_ctx, log_prior=lp, alpha=0.6,
+                           msa_start=case["msa"][0], msa_end=case["msa"][1])
+    ref = pd.read_csv(os.path.join(gd, "reference_scores.csv"))
+    assert list(out.mutated_sequence) == list(ref.mutated_sequence)
+    for c in ("avg_score_L_to_R", "avg_score_R_to_L", "avg_score"):
+        assert np.abs(out[c].values - ref[c].values).max() < 2e-5, c
