@@ -193,32 +193,41 @@ class EsmScorer:
                      windowed=len(tok) > model_window)
         return host, sizes
 
-    def run_assay(self, host: torch.Tensor, sizes: dict, dev: torch.Tensor | None = None) -> torch.Tensor:
+    def run_assay(self, host: torch.Tensor, sizes: dict, dev: torch.Tensor | None = None, shard=None) -> torch.Tensor:
         """Device half: (optional H2D of the packed int32 block) -> masked-marginal rows -> mutant scores [M] (device).
-        Pass ``dev`` to reuse an already-resident copy of ``host`` (bench's HBM-resident leg)."""
+        Pass ``dev`` to reuse an already-resident copy of ``host`` (bench's HBM-resident leg). ``shard = (rank, world)`` with an
+        initialised torch.distributed group: this rank computes only its contiguous chunk of the P masked positions and the
+        [P, vocab] table is completed by one all-gather (position partitioning of a single assay)."""
         if dev is None:
             dev = host.to(self.device, non_blocking=True)
         n, P, T, S, M = sizes["n_tokens"], sizes["P"], sizes["T"], sizes["S"], sizes["M"]
         o = [0, n, n + P, n + 2 * P, n + 2 * P + S, n + 2 * P + 2 * S, n + 2 * P + 3 * S]
         tok, pos, st, trow, wt, mt, offs = (dev[o[i]:(o[i + 1] if i + 1 < len(o) else None)] for i in range(7))
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        table = torch.empty((max(P, 1), self.config.vocab), dtype=torch.float32, device=self.device)
+        lo, hi, rows = 0, P, max(P, 1)
+        if shard is not None:
+            from . import sharding
+            lo, hi, chunk = sharding.position_chunk(P, shard[1], shard[0])
+            rows = max(shard[1] * chunk, 1)
+        table = torch.empty((rows, self.config.vocab), dtype=torch.float32, device=self.device)
         scores = torch.empty((M,), dtype=torch.float32, device=self.device)
-        if P:
-            _lib.check(self.lib.pg_masked_marginals(self.handle, tok.data_ptr(), n, pos.data_ptr(),
-                                                    st.data_ptr() if sizes["windowed"] else None, None, P, T,
-                                                    table.data_ptr(), stream), self.handle)
+        if hi > lo:
+            _lib.check(self.lib.pg_masked_marginals(self.handle, tok.data_ptr(), n, pos[lo:].data_ptr(),
+                                                    st[lo:].data_ptr() if sizes["windowed"] else None, None, hi - lo, T,
+                                                    table[lo:].data_ptr(), stream), self.handle)
+        if shard is not None:
+            sharding.all_gather_rows(table, chunk)
         if M:
             _lib.check(self.lib.pg_score_mutants(table.data_ptr(), P, self.config.vocab, trow.data_ptr(), wt.data_ptr(),
                                                  mt.data_ptr(), offs.data_ptr(), M, scores.data_ptr(), stream))
         self._keepalive3 = (dev, table)
         return scores
 
-    def score_assay(self, sequence: str, mutants, offset_idx: int = 1, model_window: int = 1024) -> np.ndarray:
+    def score_assay(self, sequence: str, mutants, offset_idx: int = 1, model_window: int = 1024, shard=None) -> np.ndarray:
         """Public one-call API: WT sequence + mutant strings in, per-mutant scores (host float32) out — what
-        compute_fitness.py:486-514 does for one checkpoint."""
+        compute_fitness.py:486-514 does for one checkpoint. ``shard``: see run_assay (every rank returns all the scores)."""
         host, sizes = self.prepare_assay(sequence, mutants, offset_idx, model_window)
-        scores = self.run_assay(host, sizes)
+        scores = self.run_assay(host, sizes, shard=shard)
         out = torch.empty(scores.shape, dtype=torch.float32).pin_memory()
         out.copy_(scores, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

@@ -6,9 +6,12 @@ GPUs of one box. Replaces the SLURM-array pattern of scripts/scoring_DMS_zero_sh
         --model-location ckpt1.pt ckpt2.pt ... --model_type ESM1v --dms_mapping reference_files/DMS_substitutions.csv \\
         --dms-input DMS_ProteinGym_substitutions --dms-output out/
 
-Weights are read on rank 0 and NCCL-broadcast; assays are assigned by LPT on the analytic cost (sharding.assay_cost); each
-rank writes the CSVs of its own assays (same files compute_fitness.py would write); rank 0 gathers a (assay, seconds,
-mutants) summary. No collective runs on the data path."""
+Weights are read on rank 0 and NCCL-broadcast. ``--partition assays`` (default when there are at least as many assays as
+GPUs): assays are assigned by LPT on the analytic cost (sharding.assay_cost); each rank writes the CSVs of its own assays (same
+files compute_fitness.py would write); no collective runs on the data path. ``--partition positions`` (default otherwise — few big
+assays, single-assay latency): all ranks work on every assay, each on a contiguous chunk of its masked positions, and one
+all-gather of the [P, 33] log-prob rows (<= 135 KB) completes the table; rank 0 writes the CSVs. Scores are bit-identical in both
+modes and for any world size. Rank 0 gathers an (assay, seconds, mutants) summary."""
 from __future__ import annotations
 
 import argparse
@@ -37,6 +40,8 @@ def main(argv=None):
     ap.add_argument("--mutation-col", default="mutant")
     ap.add_argument("--precision", default="f16x3", choices=["f16x3", "f16"])
     ap.add_argument("--indices", type=int, nargs="*", default=None, help="subset of dms_index values (default: all rows)")
+    ap.add_argument("--partition", default="auto", choices=["auto", "assays", "positions"],
+                    help="what is split across GPUs: whole assays (LPT) or the masked positions of each assay")
     a = ap.parse_args(argv)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -59,7 +64,8 @@ def main(argv=None):
             conf, name = box
             state = sharding.broadcast_state(state, src=0, device=torch.device("cuda", local))
         costs = [sharding.assay_cost(len(str(mapping["target_seq"][i])), conf.layers, conf.embed_dim, conf.ffn_dim) for i in idx]
-        mine = [idx[j] for j in sharding.lpt_assign(costs, world)[rank]]
+        by_pos = world > 1 and (a.partition == "positions" or (a.partition == "auto" and len(idx) < world))
+        mine = list(idx) if by_pos else [idx[j] for j in sharding.lpt_assign(costs, world)[rank]]
         scorer = EsmScorer(conf, state, precision=a.precision, device=local)
         del state
         for i in mine:
@@ -70,10 +76,13 @@ def main(argv=None):
             if i not in frames:
                 frames[i] = pd.read_csv(os.path.join(a.dms_input, row["DMS_filename"]))
             t0 = time.time()
-            frames[i][name] = scorer.score_assay(seq, list(frames[i][col]), off).astype(np.float64)
-            summary[(i, name)] = (time.time() - t0, len(frames[i]))
+            frames[i][name] = scorer.score_assay(seq, list(frames[i][col]), off, shard=(rank, world) if by_pos else None).astype(np.float64)
+            if not by_pos or rank == 0:
+                summary[(i, name)] = (time.time() - t0, len(frames[i]))
         scorer.close()
     for i, df in frames.items():
+        if by_pos and rank != 0:  # every rank holds the same scores; one writer
+            continue
         if "ESM1v" in a.model_type:
             names = [os.path.basename(c).split(".")[0] for c in a.model_location]
             df["Ensemble_ESM1v"] = sum(df[n] for n in names) / len(names)

@@ -27,6 +27,30 @@ def lpt_assign(costs, world: int):
     return out
 
 
+def position_chunk(P: int, world: int, rank: int):
+    """Secondary partitioning: the P masked positions of ONE assay in contiguous chunks of ceil(P / world) rows.
+    Returns (lo, hi, chunk). Equal chunk size keeps the all-gather a single fixed-size collective; the last ranks may get fewer
+    (or no) rows. Rows are computed independently of how they are batched, so scores are bit-identical for any world size."""
+    chunk = (P + world - 1) // world if P > 0 else 0
+    lo = min(P, rank * chunk)
+    return lo, min(P, lo + chunk), chunk
+
+
+def all_gather_rows(full: torch.Tensor, chunk: int, group=None) -> torch.Tensor:
+    """``full`` [world * chunk, V]: this rank has written its rows at [rank * chunk, ...). After the call every rank holds every
+    chunk (the only data-path collective of the position-partitioned mode: <= 135 KB per assay). Returns ``full``."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if chunk == 0 or world == 1:
+        return full
+    views = [full[r * chunk:(r + 1) * chunk] for r in range(world)]
+    try:
+        dist.all_gather_into_tensor(full, views[rank].clone(), group=group)
+    except (RuntimeError, NotImplementedError):  # backends without the flat variant
+        dist.all_gather(views, views[rank].clone(), group=group)
+    return full
+
+
 def broadcast_state(state: dict | None, src: int = 0, device=None) -> dict:
     """Rank ``src`` holds ``state`` (name -> fp32 tensor); every rank returns an identical copy on ``device``."""
     import torch.distributed as dist

@@ -61,3 +61,42 @@ def test_lpt_balances_real_length_distribution():
         assert max(loads) / (sum(loads) / world) < 1.05  # within 5% of perfect balance
     assert sharding.lpt_assign([], 4) == [[], [], [], []]
     assert sharding.lpt_assign([3.0], 2) == [[0], []]
+
+
+def _worker_rows(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for P in (0, 1, 5, 8, 33):
+        lo, hi, chunk = sharding.position_chunk(P, world, rank)
+        full = torch.full((max(world * chunk, 1), 3), float("nan"))
+        for r in range(lo, hi):
+            full[r] = torch.tensor([r, 2.0 * r, -1.0 * r])
+        sharding.all_gather_rows(full, chunk)
+        want = torch.stack([torch.tensor([r, 2.0 * r, -1.0 * r]) for r in range(P)]) if P else torch.zeros((0, 3))
+        ok = ok and torch.equal(full[:P], want)
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_position_partition_chunks_and_row_gather_world2():
+    """Secondary partitioning of one assay: contiguous position chunks + one all-gather of the log-prob rows."""
+    for P, world in ((0, 4), (1, 4), (512, 8), (513, 8), (7, 8), (1022, 3)):
+        spans = [sharding.position_chunk(P, world, r) for r in range(world)]
+        assert all(c == spans[0][2] for _, _, c in spans)
+        covered = [i for lo, hi, _ in spans for i in range(lo, hi)]
+        assert covered == list(range(P))                      # disjoint, ordered, complete
+        assert all(hi - lo <= spans[0][2] for lo, hi, _ in spans)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_rows, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)

@@ -4,6 +4,7 @@
 Tolerances: per-mutant score |diff| <= 1e-3 in parity mode (f16x3) — north_star's bar; the single-pass f16 mode is only
 held to Spearman >= 0.999 and a loose absolute bound."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -467,3 +468,18 @@ def test_boundary_lengths_vs_oracle(L):
     sc.close()
     ref = O.masked_marginal_table(O.load_state(st, "esm1v", torch.float64), seq, "esm1v", 1, 1, dtype=torch.float64, positions=pos)
     assert np.abs(got[pos] - ref[pos].numpy()).max() < 2e-4
+
+
+def test_position_partition_two_gpus_bit_identical():
+    """Secondary partitioning: one assay's masked positions split over 2 GPUs + one all-gather of the rows gives,
+    bit for bit, the single-GPU scores. Needs 2 devices (skipped on the 1-GPU box; runs under `gpurun --gpus 2`)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29671", os.path.join(root, "scripts", "check_position_partition.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "bit_identical=True" in r.stdout
