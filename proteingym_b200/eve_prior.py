@@ -10,6 +10,15 @@ output weight -> bias, output convolution, [sparsity], temperature), so that wit
 are the same numbers. torch's generator is used on purpose: stream-for-stream agreement with the reference's sampling is only
 possible through it; the arithmetic is restated, not imported.
 
+For the sample counts the reference's launcher asks for (``EVE_num_samples_log_proba=200000``,
+scripts/scoring_DMS_zero_shot/scoring_TranceptEVE_substitutions.sh) drawing every decoder weight per sample is 40 M normals and
+320 MB of parameter traffic per sample for a 500-residue protein. ``sampler="local"`` draws from the SAME distribution without
+materialising weights (local reparameterisation): with independent Gaussian weight posteriors, a Bayesian linear layer's
+pre-activations given its input h are independent Gaussians N(mu_W h + mu_b, sigma_W^2 (h*h) + sigma_b^2), and the output layer's
+double reinterpretation + 1x1 convolution reduces (when alphabet | last hidden size) to one dot product per logit between a
+contiguous 1/alphabet slice of the output weights and y[j, c] = sum_a h[j*A + a] conv[c, a]. Thousands of samples then go through a
+handful of dense GEMMs per batch. ``sampler="auto"`` keeps the stream-exact path up to 2000 samples and switches to ``local`` above.
+
 State-dict keys / shapes: VAE_encoder.py:40-52, VAE_decoder.py:47-108."""
 from __future__ import annotations
 
@@ -73,9 +82,49 @@ def decode_sample(st: dict, dec: dict, z: torch.Tensor, seq_len: int, g: torch.G
     return torch.log_softmax(x.reshape(z.shape[0], seq_len, A), dim=-1)
 
 
+def local_sampling_supported(dec: dict) -> bool:
+    return bool(dec["convolve_output"]) and not dec.get("include_sparsity") and dec["hidden_layers_sizes"][-1] % len(ALPHABET) == 0
+
+
+def decode_batch_local(st: dict, dec: dict, z: torch.Tensor, seq_len: int, g: torch.Generator) -> torch.Tensor:
+    """``S`` decoder passes at once, each with its own weight draw, by sampling pre-activations instead of weights (see the module
+    docstring). z [S, z_dim] -> log-softmax [S, L, 20]. Same distribution as ``decode_sample`` applied to each row of z."""
+    A = len(ALPHABET)
+    H = dec["hidden_layers_sizes"]
+    S = z.shape[0]
+
+    def randn(*shape):
+        return torch.randn(shape, generator=g, device=z.device, dtype=z.dtype)
+
+    def bayes_linear(x, wm, wlv, bm, blv):
+        mean = x @ wm.T + bm
+        var = (x * x) @ torch.exp(wlv).T + torch.exp(blv)
+        return mean + torch.sqrt(var) * randn(*mean.shape)
+
+    x = z
+    for k in range(len(H)):
+        act = _ACT[dec["first_hidden_nonlinearity"] if k < len(H) - 1 else dec["last_hidden_nonlinearity"]]
+        x = act(bayes_linear(x, st[f"decoder.hidden_layers_mean.{k}.weight"], st[f"decoder.hidden_layers_log_var.{k}.weight"],
+                             st[f"decoder.hidden_layers_mean.{k}.bias"], st[f"decoder.hidden_layers_log_var.{k}.bias"]))
+    C = dec["convolution_output_depth"]
+    J = H[-1] // A
+    cm, clv = st["decoder.output_convolution_mean.weight"].reshape(C, A), st["decoder.output_convolution_log_var.weight"].reshape(C, A)
+    conv = cm + torch.exp(0.5 * clv) * randn(S, C, A)                      # the small 1x1-convolution weights are drawn directly
+    y = torch.einsum("sja,sca->sjc", x.reshape(S, J, A), conv).reshape(S, J * C)
+    wm = st["decoder.last_hidden_layer_weight_mean"].reshape(seq_len * A, J * C)   # logit q reads the q-th contiguous slice
+    wv = torch.exp(st["decoder.last_hidden_layer_weight_log_var"]).reshape(seq_len * A, J * C)
+    out = (y @ wm.T + st["decoder.last_hidden_layer_bias_mean"]) + torch.sqrt(
+        (y * y) @ wv.T + torch.exp(st["decoder.last_hidden_layer_bias_log_var"])) * randn(S, seq_len * A)
+    if dec["include_temperature_scaler"]:
+        t = st["decoder.temperature_scaler_mean"] + torch.exp(0.5 * st["decoder.temperature_scaler_log_var"]) * randn(S, 1)
+        out = torch.log(1.0 + torch.exp(t)) * out
+    return torch.log_softmax(out.reshape(S, seq_len, A), dim=-1)
+
+
 def eve_log_prior_single(state: dict, params: dict, focus_seq_trimmed, focus_cols, full_sequence_len: int, MSA_start: int,
-                         num_samples: int = 10, device="cuda", seed: int = 42) -> torch.Tensor:
-    """get_EVE_log_prior_single (model_pytorch.py:969-1001) for the wild type: [full_sequence_len, 25] float32 on ``device``."""
+                         num_samples: int = 10, device="cuda", seed: int = 42, sampler: str = "auto", batch: int = 2048) -> torch.Tensor:
+    """get_EVE_log_prior_single (model_pytorch.py:969-1001) for the wild type: [full_sequence_len, 25] float32 on ``device``.
+    ``sampler``: "stream" (reference's draw order), "local" (same distribution, batched; module docstring) or "auto"."""
     dev = torch.device(device)
     st = {k: v.to(dev, torch.float32) for k, v in state.items()}
     L, A = len(focus_seq_trimmed), len(ALPHABET)
@@ -87,11 +136,28 @@ def eve_log_prior_single(state: dict, params: dict, focus_seq_trimmed, focus_col
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
     mu, log_var = encode_focus(st, params["encoder_parameters"], x)
-    recon = 0
-    for _ in range(num_samples):
-        z = _draw(mu, log_var, g)
-        recon = recon + decode_sample(st, params["decoder_parameters"], z, L, g)
-    recon = recon / num_samples
+    dec = params["decoder_parameters"]
+    if sampler == "auto":
+        sampler = "local" if num_samples > 2000 and local_sampling_supported(dec) else "stream"
+    if sampler == "local":
+        if not local_sampling_supported(dec):
+            raise ValueError("local sampling needs convolve_output, no sparsity and alphabet | last hidden size")
+        recon = torch.zeros((1, L, A), dtype=torch.float64, device=dev)
+        done = 0
+        while done < num_samples:
+            S = min(batch, num_samples - done)
+            z = mu + torch.exp(0.5 * log_var) * torch.randn((S, mu.shape[1]), generator=g, device=dev, dtype=mu.dtype)
+            recon += decode_batch_local(st, dec, z, L, g).sum(dim=0, keepdim=True, dtype=torch.float64)
+            done += S
+        recon = (recon / num_samples).float()
+    elif sampler == "stream":
+        recon = 0
+        for _ in range(num_samples):
+            z = _draw(mu, log_var, g)
+            recon = recon + decode_sample(st, dec, z, L, g)
+        recon = recon / num_samples
+    else:
+        raise ValueError(sampler)
     prior = torch.full((full_sequence_len, A + 5), -np.inf, dtype=torch.float32, device=dev)
     rows = torch.tensor([MSA_start + c for c in focus_cols], dtype=torch.long, device=dev)
     prior[rows, 5:] = recon[0]
@@ -104,7 +170,7 @@ def cache_location(EVE_model_path: str, num_samples: int) -> str:
 
 
 def eve_log_prior(EVE_model_paths, EVE_model_parameters_location: str, msa, full_sequence_len: int, MSA_start: int,
-                  EVE_num_samples_log_proba: int = 10, device="cuda") -> torch.Tensor:
+                  EVE_num_samples_log_proba: int = 10, device="cuda", sampler: str = "auto") -> torch.Tensor:
     """get_EVE_models_and_log_prior (model_pytorch.py:940-967): ensemble mean of the per-model priors, each read from / written to
     the reference's cache location. ``msa`` is the MSAProcessing of the retrieved alignment (focus columns, trimmed focus sequence)."""
     params = json.load(open(EVE_model_parameters_location))
@@ -116,7 +182,7 @@ def eve_log_prior(EVE_model_paths, EVE_model_parameters_location: str, msa, full
             print("Computing EVE log prior")
             ck = torch.load(path, map_location="cpu")
             single = eve_log_prior_single(ck["model_state_dict"], params, msa.focus_seq_trimmed, msa.focus_cols, full_sequence_len, MSA_start,
-                                          EVE_num_samples_log_proba, device)
+                                          EVE_num_samples_log_proba, device, sampler=sampler)
             with open(loc, "wb") as fh:
                 pickle.dump(single.cpu(), fh)
         else:

@@ -1,7 +1,8 @@
 """Drop-in for ``proteingym/baselines/trancepteve/score_trancepteve.py`` (flags :19-61, assay / MSA / EVE resolution :75-156, scoring
 and CSV :176-190, coefficient log :201-208). Output: ``<output_scores_folder>/<DMS_id>.csv`` with ``mutated_sequence,
 avg_score_L_to_R, avg_score_R_to_L, avg_score, mutant``. Retrieval for indels (Clustal Omega re-alignment) is not reproduced.
-Additive flags: --precision, --device."""
+Additive flags: --precision, --device, --EVE_sampler (how a missing EVE log-prior cache is computed: the reference's weight-by-weight
+draw order, or the same distribution through batched local reparameterisation — eve_prior.py)."""
 from __future__ import annotations
 
 import argparse
@@ -58,6 +59,7 @@ def create_parser():
         parser.add_argument(flag, **kw)
     parser.add_argument("--precision", default="f16x3", choices=["f16x3", "f16"])
     parser.add_argument("--device", default=0, type=int)
+    parser.add_argument("--EVE_sampler", default="auto", choices=["auto", "stream", "local"])
     return parser
 
 
@@ -123,7 +125,7 @@ def main(argv=None):
             kw.update(MSA_recalibrate_probas=False, EVE_recalibrate_probas=True)
     config, state = load_tranception_checkpoint(args.checkpoint)
     scorer = TranceptEVEScorer(config, state, full_target_seq=target_seq, scoring_window=args.scoring_window, precision=args.precision,
-                               device=args.device, **kw)
+                               device=args.device, EVE_sampler=args.EVE_sampler, **kw)
     if not os.path.isdir(args.output_scores_folder):
         os.mkdir(args.output_scores_folder)
     DMS_data = pd.read_csv(args.DMS_data_folder + os.sep + DMS_file_name, low_memory=False)

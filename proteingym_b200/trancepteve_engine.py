@@ -63,7 +63,8 @@ class TranceptEVEScorer(TranceptionScorer):
                  MSA_threshold_sequence_frac_gaps=None, MSA_threshold_focus_cols_frac_gaps=None, EVE_model_paths=None,
                  EVE_num_samples_log_proba=10, EVE_model_parameters_location=None, MSA_recalibrate_probas=False,
                  EVE_recalibrate_probas=True, retrieval_weights_manual=False, retrieval_inference_MSA_weight=0.5,
-                 retrieval_inference_EVE_weight=0.5, scoring_window="optimal", precision="f16x3", device=0, max_rows=0):
+                 retrieval_inference_EVE_weight=0.5, scoring_window="optimal", precision="f16x3", device=0, max_rows=0,
+                 EVE_sampler="auto"):
         super().__init__(config, state, precision=precision, device=device, max_rows=max_rows)
         self.full_target_seq = full_target_seq
         self.full_protein_length = len(full_target_seq)
@@ -101,7 +102,7 @@ class TranceptEVEScorer(TranceptionScorer):
                                          threshold_focus_cols_frac_gaps=MSA_threshold_focus_cols_frac_gaps, device=dev)
             self.EVE_log_prior = eve_prior.eve_log_prior(EVE_model_paths, EVE_model_parameters_location, self.EVE_MSA,
                                                          self.full_protein_length, MSA_start, EVE_num_samples_log_proba,
-                                                         device=self.device).cpu()
+                                                         device=self.device, sampler=EVE_sampler).cpu()
             self.EVE_processed_depth = len(self.EVE_MSA.seq_name_to_sequence.keys())
         self.retrieval_inference_MSA_weight, self.retrieval_inference_EVE_weight = retrieval_weights(
             inference_time_retrieval_type, retrieval_aggregation_mode, self.MSA_processed_depth, self.EVE_processed_depth,

@@ -80,6 +80,35 @@ def test_eve_log_prior_matches_reference_sampling(name, tmp_path):
     assert np.array_equal(np.nan_to_num(again, neginf=0), np.nan_to_num(got, neginf=0))
 
 
+def test_local_reparameterisation_sampler_has_the_reference_distribution():
+    """eve_prior's batched sampler draws pre-activations instead of weights. Same distribution as the reference's weight-by-weight
+    sampling: identical when the posterior variances vanish, and Monte-Carlo averages that agree as closely as two independent
+    streams of the reference-order sampler agree with each other."""
+    import copy
+    P = copy.deepcopy(synth.EVE_TINY_PARAMS)
+    P["decoder_parameters"]["hidden_layers_sizes"] = [24, 32, 60]   # alphabet | last hidden size
+    assert eve_prior.local_sampling_supported(P["decoder_parameters"]) and not eve_prior.local_sampling_supported(synth.EVE_TINY_PARAMS["decoder_parameters"])
+    L = 9
+    focus, cols = list(synth.random_protein(L, 3)), list(range(L))
+    st0 = synth.make_eve_state(L, P, seed=7, log_var=-80.0)
+    st0["encoder.fc_log_var.bias"].fill_(-80.0)
+    st0["encoder.fc_log_var.weight"].zero_()
+    run = lambda st, n, how, seed=42: eve_prior.eve_log_prior_single(st, P, focus, cols, L, 0, n, device="cpu", sampler=how, seed=seed)  # noqa: E731
+    a, b = run(st0, 3, "stream"), run(st0, 3, "local")
+    fin = torch.isfinite(a)
+    assert torch.equal(fin, torch.isfinite(b)) and (a[fin] - b[fin]).abs().max() < 1e-5
+    st = synth.make_eve_state(L, P, seed=7, log_var=-3.0)
+    n = 4000
+    s1, s2, l1 = run(st, n, "stream"), run(st, n, "stream", 7), run(st, n, "local")
+    big = run(st, 400000, "local", 11)                      # a near-exact answer is cheap with the batched sampler
+    noise = (s1[fin] - s2[fin]).abs().mean().item()
+    assert noise > 1e-3                                      # the sampling matters at this variance
+    assert (l1[fin] - s1[fin]).abs().mean().item() < 1.5 * noise
+    assert (s1[fin] - big[fin]).abs().mean().item() < noise and (l1[fin] - big[fin]).abs().mean().item() < noise
+    with pytest.raises(ValueError):
+        eve_prior.eve_log_prior_single(st, synth.EVE_TINY_PARAMS, focus, cols, L, 0, 3, device="cpu", sampler="local")
+
+
 def test_retrieval_weight_ladder():
     """Depth thresholds of the constructor (trancepteve/model_pytorch.py:720-763)."""
     f = lambda m, e: retrieval_weights("TranceptEVE", "aggregate_substitution", m, e)  # noqa: E731
