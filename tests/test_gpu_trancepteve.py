@@ -181,3 +181,60 @@ def test_tranception_cli_retrieval_with_sequence_weights(tmp_path):
     assert list(got.columns) == list(ref.columns) and list(got["mutated_sequence"]) == list(ref["mutated_sequence"])
     for c in ("avg_score_L_to_R", "avg_score_R_to_L", "avg_score"):
         assert np.abs(got[c].values - ref[c].values).max() < TOL, c
+
+
+def test_true_size_trancepteve_fusion_properties():
+    """Tranception-L architecture (36 x 1280, 20 heads) with synthetic [L, 25] MSA / EVE log priors. No CPU
+    oracle at this size; the fused head is checked through properties: (1) zero weights reproduce the plain scores bit for bit,
+    (2) every emitted row is a normalised distribution and the label terms add up to the returned sum, (3) the fused sums equal the
+    three-way mixture evaluated on the host from the unfused rows and the prior-row indices — left-to-right and flipped, window
+    partially overlapping the MSA range, non-focus rows included."""
+    from proteingym_b200.tranception_engine import TranceptionScorer, prior_rows, tokenize
+    arch = synth.TRANCEPTION_L
+    st = synth.make_tranception_state(arch, 0)
+    cfg = {"n_embd": arch.embed_dim, "n_head": arch.heads, "n_layer": arch.layers, "n_ctx": arch.n_ctx, "n_inner": arch.ffn_dim,
+           "vocab_size": arch.vocab, "layer_norm_epsilon": arch.ln_eps, "activation_function": "squared_relu"}
+    sc = TranceptionScorer(cfg, {k[len("transformer."):]: v for k, v in st.items() if k.startswith("transformer.")}, max_rows=16384)
+    rng = np.random.RandomState(0)
+    Lfull = 400
+    full = synth.random_protein(Lfull, 4)
+    msa_lp = np.log(rng.dirichlet(np.ones(25), size=Lfull)).astype(np.float32)
+    eve_lp = np.full((Lfull, 25), -np.inf, dtype=np.float32)
+    eve_lp[:, 5:] = np.log(rng.dirichlet(np.ones(20), size=Lfull)).astype(np.float32)
+    nonfocus_rows = [70, 71, 150, 333]
+    eve_lp[nonfocus_rows, 5:] = -np.inf
+    windows = [(0, 300), (100, 400), (50, 200)]
+    seqs = [full[a:b] for a, b in windows]
+    msa_start, msa_end, alpha, beta = 60, 350, 0.3, 0.6
+    plain, rows = sc.sequence_logprobs(seqs, return_rows=True)
+    for r, s in zip(rows, seqs):
+        assert r.shape == (len(s) + 1, 25) and np.abs(np.log(np.exp(r.astype(np.float64)).sum(-1))).max() < 1e-4
+        lab = np.asarray(tokenize(s)[1:])
+        assert abs(r[np.arange(len(lab)), lab].astype(np.float64).sum() - plain[seqs.index(s)]) < 2e-3
+    kw = dict(windows=windows, prior=msa_lp, msa_start=msa_start, msa_end=msa_end, prior2=eve_lp, first_col=5, nonfocus_fallback=True)
+    zero = sc.sequence_logprobs(seqs, alpha=0.0, beta=0.0, **{**kw, "prior2": np.where(np.isfinite(eve_lp), eve_lp, 0).astype(np.float32)})
+    assert np.array_equal(zero, plain)
+    for flip in (False, True):
+        strings = [s[::-1] for s in seqs] if flip else seqs
+        base, rws = sc.sequence_logprobs(strings, return_rows=True)
+        got = sc.sequence_logprobs(strings, alpha=alpha, beta=beta, flip=flip, **kw)
+        nonfocus = eve_lp[:, 5:].min(axis=1) == -np.inf
+        for k, s in enumerate(strings):
+            T = len(s) + 2
+            p1, p2 = np.full(T, -1, np.int32), np.full(T, -1, np.int32)
+            prior_rows(p1, p2, windows[k][0], windows[k][1], msa_start, msa_end, flip, nonfocus)
+            lab = np.asarray(tokenize(s)[1:])
+            want = 0.0
+            for t, v in enumerate(lab):
+                lp = np.float32(rws[k][t, v])
+                if v >= 5 and p1[t] >= 0:
+                    m = np.float32(1 - alpha) * lp + np.float32(alpha) * msa_lp[p1[t], v]
+                    if p2[t] >= 0:
+                        m = np.float32(1 - beta) * m + np.float32(beta) * eve_lp[p2[t], v]
+                    lp = m
+                elif v >= 5 and p1[t] == -2:
+                    lp = np.float32(1 - alpha) * lp
+                want += float(lp)
+            assert np.isfinite(got[k]) and abs(got[k] - want) < 2e-3 * max(1.0, abs(want) / 100), (flip, k, got[k], want)
+        assert (np.abs(got - base) > 1.0).all()  # the priors really moved the scores
+    sc.close()
