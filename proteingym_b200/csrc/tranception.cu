@@ -82,58 +82,75 @@ __global__ void qkv_conv_kernel(const __half* __restrict__ in, __half* __restric
   for (int o = 0; o < 7; ++o)
 #pragma unroll
     for (int i = 0; i < 8; ++i) win[o][i] = 0.f;
-  auto load_row = [&](int t, float (&v)[8]) {
-    const __half* src = in + (row0 + t) * ld + c0;
-    const uint4 hv = *reinterpret_cast<const uint4*>(src);
+  auto decode = [&](const uint4& hv, const uint4& lv, float (&v)[8]) {
     const __half2* h2 = reinterpret_cast<const __half2*>(&hv);
+    const __half2* l2 = reinterpret_cast<const __half2*>(&lv);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 f = __half22float2(h2[i]);
       v[2 * i] = f.x; v[2 * i + 1] = f.y;
-    }
-    if (lo_off > 0) {
-      const uint4 lv = *reinterpret_cast<const uint4*>(src + lo_off);
-      const __half2* l2 = reinterpret_cast<const __half2*>(&lv);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(l2[i]);
-        v[2 * i] += f.x; v[2 * i + 1] += f.y;
+      if (lo_off > 0) {
+        const float2 e = __half22float2(l2[i]);
+        v[2 * i] += e.x; v[2 * i + 1] += e.y;
       }
     }
   };
-  // prime the window with the klen-1 rows before the block (zeros before the start of the sequence)
+  auto fetch = [&](int t, uint4& hv, uint4& lv) {
+    const __half* src = in + (row0 + t) * ld + c0;
+    hv = *reinterpret_cast<const uint4*>(src);
+    if (lo_off > 0) lv = *reinterpret_cast<const uint4*>(src + lo_off);
+  };
+  // prime the window with the klen-1 rows before the block (zeros before the start of the sequence): all loads first
+  {
+    uint4 hv[6], lv[6];
 #pragma unroll
-  for (int o = 1; o < 7; ++o)
-    if (o < klen && t0 - o >= 0) load_row(t0 - o, win[o]);
+    for (int o = 1; o < 7; ++o)
+      if (o < klen && t0 - o >= 0) fetch(t0 - o, hv[o - 1], lv[o - 1]);
+#pragma unroll
+    for (int o = 1; o < 7; ++o)
+      if (o < klen && t0 - o >= 0) decode(hv[o - 1], lv[o - 1], win[o]);
+  }
+  // CONV_LD rows are requested before any of them is consumed: the kernel is HBM-bound and a thread that waits for one 16-byte
+  // load per step leaves the memory system idle (measured 3.5x off the copy roofline before this batching)
+  constexpr int CONV_LD = 4;
 #pragma unroll 1
-  for (int tt = 0; tt < CONV_TB; ++tt) {
-    const int t = t0 + tt;
-    if (t >= T) break;
-    load_row(t, win[0]);
-    float acc[8];
+  for (int tt0 = 0; tt0 < CONV_TB; tt0 += CONV_LD) {
+    if (t0 + tt0 >= T) break;
+    uint4 hv[CONV_LD], lv[CONV_LD];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float a = tap[i][7];
+    for (int u = 0; u < CONV_LD; ++u)
+      if (t0 + tt0 + u < T) fetch(t0 + tt0 + u, hv[u], lv[u]);
 #pragma unroll
-      for (int o = 0; o < 7; ++o) a = fmaf(tap[i][o], win[o][i], a);  // taps beyond klen are zero
-      acc[i] = a * sc;
+    for (int u = 0; u < CONV_LD; ++u) {
+      const int t = t0 + tt0 + u;
+      if (t < T) {
+        decode(hv[u], lv[u], win[0]);
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a = tap[i][7];
+#pragma unroll
+          for (int o = 0; o < 7; ++o) a = fmaf(tap[i][o], win[o][i], a);  // taps beyond klen are zero
+          acc[i] = a * sc;
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half h0, l0, h1, l1;
+          split_hi_lo(acc[2 * i], h0, l0);
+          split_hi_lo(acc[2 * i + 1], h1, l1);
+          hi[i] = pack_h2(h0, h1);
+          lo[i] = pack_h2(l0, l1);
+        }
+        __half* dst = out + (row0 + t) * ld + c0;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (lo_off > 0) *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+        for (int o = 6; o > 0; --o)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) win[o][i] = win[o - 1][i];
+      }
     }
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __half h0, l0, h1, l1;
-      split_hi_lo(acc[2 * i], h0, l0);
-      split_hi_lo(acc[2 * i + 1], h1, l1);
-      hi[i] = pack_h2(h0, h1);
-      lo[i] = pack_h2(l0, l1);
-    }
-    __half* dst = out + (row0 + t) * ld + c0;
-    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    if (lo_off > 0) *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-#pragma unroll
-    for (int o = 6; o > 0; --o)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) win[o][i] = win[o - 1][i];
   }
 }
 
