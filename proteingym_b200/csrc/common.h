@@ -97,6 +97,7 @@ int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
                      uint32_t box_cols);
 int launch_attention_tc(const AttnLaunch& a, cudaStream_t s);   // tcgen05/TMEM attention; dispatches to the tile-pair kernel by default
 int launch_attention_tc2(const AttnLaunch& a, cudaStream_t s);  // two query tiles in flight per CTA (attention_tc2.cu)
+int launch_attention_tc3(const AttnLaunch& a, cudaStream_t s);  // P stored in place over S, three-slot TMEM ring (attention_tc3.cu)
 }  // namespace pg
 
 namespace pg {
