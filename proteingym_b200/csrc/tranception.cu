@@ -5,6 +5,8 @@
 //   ar_head_kernel        ln_f -> tied lm_head (no bias) -> log_softmax -> optional retrieval-prior fusion -> log p(next token)
 //                         (model_pytorch.py:612, :783, :806-830; utils/scoring_utils.py:121-128)
 //   seq_sum_kernel        per-sequence sum over the real (non-pad) predicted tokens, fixed order
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -154,6 +156,89 @@ __global__ void qkv_conv_kernel(const __half* __restrict__ in, __half* __restric
   }
 }
 
+// v2 of the depthwise conv (PG_CONV_V2=1): the block stages a [CV_T + 6 rows] x [CV_C channels] tile (hi and lo planes) in shared
+// memory with cp.async — every byte of the tile is in flight at once, independent of the arithmetic — then each thread walks down
+// time for ONE channel pair with a 7-deep register window (16 tap registers instead of 64, so several blocks fit per SM). One warp =
+// the 64 channels of one head, hence uniform in its conv group. Same FMA order as qkv_conv_kernel: bit-identical results.
+constexpr int CV_T = 64;
+constexpr int CV_C = 256;
+template <int NP>
+__global__ void __launch_bounds__(128) qkv_conv2_kernel(const __half* __restrict__ in, __half* __restrict__ out, long long ld,
+                                                        long long lo_off, int T, int heads, const float* __restrict__ taps, float qscale) {
+  extern __shared__ __align__(16) uint8_t cv_smem[];
+  constexpr int ROWS = CV_T + 6;
+  constexpr int ROWB = CV_C * 2;                      // bytes per staged row and plane
+  const int c0 = blockIdx.x * CV_C, t0 = blockIdx.y * CV_T, b = blockIdx.z;
+  const long long row0 = static_cast<long long>(b) * T;
+  const uint32_t sbase = smem_u32(cv_smem);
+  // ---- stage: rows t0-6 .. t0+CV_T-1 (zero-filled outside [0, T)), 32 16-byte chunks per row and plane ----
+  for (int id = threadIdx.x; id < NP * ROWS * (ROWB / 16); id += blockDim.x) {
+    const int ch = id % (ROWB / 16);
+    const int r = (id / (ROWB / 16)) % ROWS;
+    const int pl = id / ((ROWB / 16) * ROWS);
+    const int t = t0 - 6 + r;
+    const bool ok = t >= 0 && t < T;
+    const __half* g = in + (ok ? (row0 + t) * ld + c0 + ch * 8 + pl * lo_off : 0);
+    cp_async_16(sbase + (pl * ROWS + r) * ROWB + ch * 16, g, ok ? 16u : 0u);
+  }
+  cp_async_commit();
+  // ---- this thread's channel pair: taps while the tile is in flight ----
+  const int c = c0 + 2 * threadIdx.x;
+  const int d = heads * 64;
+  const int which = c / d, head = (c % d) / 64, chn = c % 64;
+  const int group = head / (heads / 4);
+  float tap[2][8];
+  {
+    const float4* tp4 = reinterpret_cast<const float4*>(taps + ((static_cast<long long>(which) * 4 + group) * 64 + chn) * 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float4 a = __ldg(tp4 + 2 * i), bq = __ldg(tp4 + 2 * i + 1);
+      tap[i][0] = a.x; tap[i][1] = a.y; tap[i][2] = a.z; tap[i][3] = a.w;
+      tap[i][4] = bq.x; tap[i][5] = bq.y; tap[i][6] = bq.z; tap[i][7] = bq.w;
+    }
+  }
+  const float sc = which == 0 ? qscale : 1.f;
+  cp_async_wait<0>();
+  __syncthreads();
+  auto rd = [&](int r, float (&v)[2]) {
+    const __half2 hv = *reinterpret_cast<const __half2*>(cv_smem + r * ROWB + threadIdx.x * 4);
+    const float2 f = __half22float2(hv);
+    v[0] = f.x; v[1] = f.y;
+    if (NP == 2) {
+      const __half2 lv = *reinterpret_cast<const __half2*>(cv_smem + (ROWS + r) * ROWB + threadIdx.x * 4);
+      const float2 e = __half22float2(lv);
+      v[0] += e.x; v[1] += e.y;
+    }
+  };
+  float win[7][2];  // win[o] = input row t - o
+#pragma unroll
+  for (int o = 1; o < 7; ++o) rd(6 - o, win[o]);     // staged row index of time t0 - o is 6 - o
+  const int nt = (T - t0) < CV_T ? (T - t0) : CV_T;
+#pragma unroll 4
+  for (int tt = 0; tt < nt; ++tt) {
+    rd(6 + tt, win[0]);
+    float acc[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float a = tap[i][7];
+#pragma unroll
+      for (int o = 0; o < 7; ++o) a = fmaf(tap[i][o], win[o][i], a);  // taps beyond the group's kernel length are zero
+      acc[i] = a * sc;
+    }
+    __half h0, l0, h1, l1;
+    split_hi_lo(acc[0], h0, l0);
+    split_hi_lo(acc[1], h1, l1);
+    __half* dst = out + (row0 + t0 + tt) * ld + c;
+    *reinterpret_cast<uint32_t*>(dst) = pack_h2(h0, h1);
+    if (NP == 2) *reinterpret_cast<uint32_t*>(dst + lo_off) = pack_h2(l0, l1);
+#pragma unroll
+    for (int o = 6; o > 0; --o) {
+      win[o][0] = win[o - 1][0];
+      win[o][1] = win[o - 1][1];
+    }
+  }
+}
+
 struct ArHeadParams {
   const float* x; int d; int T; int vocab;
   const int32_t* ids; const int32_t* lens;
@@ -257,6 +342,21 @@ int launch_qkv_conv(const __half* in, __half* out, int64_t ld, int64_t lo_off, i
   const long long n = static_cast<long long>(B) * ((T + CONV_TB - 1) / CONV_TB) * (3 * heads * 64 / 8);
   if (n <= 0) return PG_OK;
   if (heads % 4) return set_error(PG_ERR_ARG, "qkv_conv: heads must be a multiple of 4");
+  static const bool v2 = getenv("PG_CONV_V2") && getenv("PG_CONV_V2")[0] == '1';
+  if (v2 && B <= 65535) {
+    const dim3 grid(3 * heads * 64 / CV_C, (T + CV_T - 1) / CV_T, B);
+    const int np = lo_off > 0 ? 2 : 1;
+    const int smem = np * (CV_T + 6) * CV_C * 2;
+    static bool attr = false;
+    if (!attr) {
+      PG_CUDA_OK(cudaFuncSetAttribute(qkv_conv2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (CV_T + 6) * CV_C * 2));
+      attr = true;
+    }
+    if (np == 2) qkv_conv2_kernel<2><<<grid, 128, smem, s>>>(in, out, ld, lo_off, T, heads, taps, qscale);
+    else qkv_conv2_kernel<1><<<grid, 128, smem, s>>>(in, out, ld, lo_off, T, heads, taps, qscale);
+    PG_CUDA_OK(cudaGetLastError());
+    return PG_OK;
+  }
   qkv_conv_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(in, out, ld, lo_off, B, T, heads, taps, qscale);
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;
