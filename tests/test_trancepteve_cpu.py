@@ -208,6 +208,6 @@ def test_cli_flag_surface_matches_reference(tag):
                         "type": getattr(a.type, "__name__", str(a.type)), "choices": list(a.choices) if a.choices else None,
                         "const": str(a.const)}
     ref = json.load(open(os.path.join(GOLDEN, tag + "_cli_flags.json")))
-    assert set(mine) - set(ref) <= {"precision", "device", "MSA_log_prior_npy"} and not set(ref) - set(mine)
+    assert set(mine) - set(ref) <= {"precision", "device", "MSA_log_prior_npy", "EVE_sampler"} and not set(ref) - set(mine)
     for k, v in ref.items():
         assert mine[k] == v, k
