@@ -163,7 +163,7 @@ typedef struct {
   void* out; int64_t ldo; int64_t out_lo_off;
   int32_t B, T, heads, nseg;
   int32_t causal; const float* alibi_slopes; /* NULL = none */
-  int32_t impl; /* 0 = auto (tcgen05 kernel), 1 = mma.sync kernel, 2 = tcgen05 kernel, 3 = tcgen05 tile-pair kernel (experimental), 4 = tcgen05 kernel with P in place over S (experimental) */
+  int32_t impl; /* 0 = auto (what the model uses: 4 unless PG_ATTN_INPLACE=0), 1 = mma.sync kernel, 2 = tcgen05 kernel with P in its own TMEM columns, 3 = tcgen05 tile-pair kernel (experimental), 4 = tcgen05 kernel with P in place over S */
 } pg_attn_args;
 int pg_attention(const pg_attn_args* args, pg_stream stream);
 

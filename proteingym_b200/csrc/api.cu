@@ -674,7 +674,8 @@ int pg_attention(const pg_attn_args* a, pg_stream stream) {
   ProfScope ps(CAT_OTHER, static_cast<cudaStream_t>(stream));
   if (a->impl == 3) return launch_attention_tc2(l, static_cast<cudaStream_t>(stream));
   if (a->impl == 4) return launch_attention_tc3(l, static_cast<cudaStream_t>(stream));
-  if (a->impl == 2 || a->impl == 0) return launch_attention_tc(l, static_cast<cudaStream_t>(stream));
+  if (a->impl == 0) return launch_attention_tc(l, static_cast<cudaStream_t>(stream));   // the model's default dispatch
+  if (a->impl == 2) return launch_attention_tc_own(l, static_cast<cudaStream_t>(stream));
   return launch_attention(l, static_cast<cudaStream_t>(stream));
 }
 

@@ -543,15 +543,22 @@ __global__ void __launch_bounds__(384, 1) attn_tc_kernel(const __grid_constant__
 
 }  // namespace
 
+// The model's dispatch (pg_attention impl 0): which tcgen05 kernel runs.
 int launch_attention_tc(const AttnLaunch& a, cudaStream_t s) {
   if (a.B <= 0 || a.T <= 0) return PG_OK;
-  // PG_ATTN_PAIR=1 selects the tile-pair ("ping-pong") kernel of attention_tc2.cu. Measured on B200 it is on par in f16
-  // (0.689 vs 0.699 ms, B=128 T=514 H=20) and slower in f16x3 (1.084 vs 0.949 ms), so this one-tile-per-CTA kernel stays default.
+  // PG_ATTN_PAIR=1 selects the tile-pair ("ping-pong") kernel of attention_tc2.cu (on par in f16, slower in f16x3).
   static const bool pair = getenv("PG_ATTN_PAIR") && getenv("PG_ATTN_PAIR")[0] == '1';
   if (pair) return launch_attention_tc2(a, s);
-  // PG_ATTN_INPLACE=1 selects attention_tc3.cu (P stored in place over S, three-slot TMEM ring, no wait for the previous PV).
-  static const bool inplace = getenv("PG_ATTN_INPLACE") && getenv("PG_ATTN_INPLACE")[0] == '1';
+  // Default: attention_tc3.cu (P stored in place over S, three-slot TMEM ring, no wait for the previous PV): equal in f16, +4.5 % in
+  // f16x3 (B=128, T=514, H=20: 0.868 vs 0.907 ms). PG_ATTN_INPLACE=0 keeps this file's kernel (P in its own TMEM columns).
+  static const bool inplace = !(getenv("PG_ATTN_INPLACE") && getenv("PG_ATTN_INPLACE")[0] == '0');
   if (inplace && a.q_begin == 0) return launch_attention_tc3(a, s);
+  return launch_attention_tc_own(a, s);
+}
+
+// This file's kernel (pg_attention impl 2).
+int launch_attention_tc_own(const AttnLaunch& a, cudaStream_t s) {
+  if (a.B <= 0 || a.T <= 0) return PG_OK;
   if (a.nseg != 1 && a.nseg != 3) return set_error(PG_ERR_ARG, "attention: nseg must be 1 or 3");
   if (a.ld % 8 || a.lo_off % 8 || a.ldo % 8 || a.out_lo_off % 8 || (reinterpret_cast<uintptr_t>(a.out) & 15))
     return set_error(PG_ERR_ARG, "attention_tc: pitches must be multiples of 8 elements and out 16-byte aligned");

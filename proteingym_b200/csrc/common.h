@@ -95,7 +95,8 @@ namespace pg {
 // 2D fp16 row-major tensor map [rows, cols] (pitch ld elements), box [box_rows, box_cols], SWIZZLE_128B, OOB -> 0.
 int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                      uint32_t box_cols);
-int launch_attention_tc(const AttnLaunch& a, cudaStream_t s);   // tcgen05/TMEM attention; dispatches to the tile-pair kernel by default
+int launch_attention_tc(const AttnLaunch& a, cudaStream_t s);      // tcgen05/TMEM attention: the model's dispatch (default attention_tc3.cu)
+int launch_attention_tc_own(const AttnLaunch& a, cudaStream_t s);  // attention_tc.cu's kernel (P in its own TMEM columns)
 int launch_attention_tc2(const AttnLaunch& a, cudaStream_t s);  // two query tiles in flight per CTA (attention_tc2.cu)
 int launch_attention_tc3(const AttnLaunch& a, cudaStream_t s);  // P stored in place over S, three-slot TMEM ring (attention_tc3.cu)
 }  // namespace pg

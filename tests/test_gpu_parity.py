@@ -116,7 +116,7 @@ def test_layernorm_matches_fp64(rows, d):
 @pytest.mark.parametrize("B,T,H,nseg,causal", [(2, 64, 2, 1, 0), (3, 100, 2, 1, 0), (2, 514, 4, 1, 0), (1, 1024, 2, 1, 0),
                                                (1, 1, 1, 1, 0), (2, 3, 1, 3, 0), (3, 100, 2, 3, 0), (2, 514, 4, 3, 0),
                                                (2, 130, 2, 1, 1), (2, 130, 2, 3, 1), (2, 514, 4, 1, 1), (1, 1024, 2, 3, 1)])
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3, 4])
 def test_attention_matches_fp64(B, T, H, nseg, causal, impl):
     slopes = None
     lib = _lib.load()
