@@ -1,16 +1,18 @@
 // K4 — tcgen05/TMEM fused multi-head self-attention (bidirectional, or causal + ALiBi for Tranception), head_dim 64.
 // Reference arithmetic: esm/multihead_attention.py:357 (QK^T), :379 (fp32 softmax), :387 (PV); q pre-scaled / pre-rotated.
+// This file's kernel keeps P in its OWN TMEM columns (or, PG_ATTN_P_SMEM=1, in swizzled shared memory); the model's default since
+// the end of round 1 is attention_tc3.cu (P in place over S). launch_attention_tc() below is the dispatch both go through.
 //
 // One persistent CTA per SM (384 threads); work item = (sequence, head, 128-query tile):
 //   warp 0     TMA producer: Q tile (128x64) and a ring of 128-key K / V tiles (SWIZZLE_128B), in MMA consumption order
 //   warp 1     MMA issuer (one thread):  S = Q K^T  (tcgen05.mma M128 N<=128 K16, K-major B)  -> TMEM S[2] (fp32)
-//                                         O += P V   (A = P from swizzled smem, B = V MN-major)   -> TMEM O (128x64 fp32)
+//                                         O += P V   (A = P from TMEM, TS form; B = V MN-major)  -> TMEM O (128x64 fp32)
 //   warp 2     TMEM allocator
-//   warps 4-11 softmax: thread = (query row, 64-key half) (tcgen05.ld 32x32b), exp2 in fp32, P -> fp16 (hi[, lo]) -> smem
+//   warps 4-11 softmax: thread = (query row, 64-key half) (tcgen05.ld 32x32b), exp2 in fp32, P -> fp16 (hi[, lo]) -> tcgen05.st
 //
-// Softmax is exact two-pass instead of online rescaling: pass A runs QK^T (hi*hi only) just to get each row's max,
-// pass B recomputes S, forms P = exp(S - max) and accumulates O directly in TMEM — no O correction step, and the
-// tensor pipe has headroom because the kernel is exp-throughput bound (16 MUFU/clk/SM) in single-pass mode.
+// Softmax (template ONLINE): single pass with lazy rescaling — the running row maximum is raised only when a block exceeds it by
+// more than 8 (log2 units), so O in TMEM is corrected only on those rare blocks. ONLINE = false (PG_ATTN_TWO_PASS=1) is the exact
+// two-pass variant kept for cross-checks: pass A runs QK^T (hi*hi only) for the row maxima, pass B recomputes S and accumulates.
 // NP == 2 (f16x3 parity mode): Q,K,V arrive as hi|lo planes, S = QhKh + QlKh + QhKl, O = PhVh + PlVh + PhVl.
 // Roofline: tensor/MUFU bound; algorithmic FLOPs = 4*T^2*64 per (sequence, head).
 #include <cstdlib>
