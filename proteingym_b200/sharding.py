@@ -4,7 +4,6 @@ cost, per-assay score vectors are gathered once at the end. Works on any torch.d
 gloo in the CPU tests)."""
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 
