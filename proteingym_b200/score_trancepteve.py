@@ -68,6 +68,8 @@ def main(argv=None):
     from proteingym_b200.trancepteve_engine import TranceptEVEScorer
     args = create_parser().parse_args(argv)
     print(args)
+    from proteingym_b200.score_tranception_proteingym import _finish_distributed, _init_distributed
+    rank, world = _init_distributed(args)
     retrieval = args.inference_time_retrieval_type is not None
     kw = {}
     if args.DMS_reference_file_path:
@@ -126,7 +128,9 @@ def main(argv=None):
     config, state = load_tranception_checkpoint(args.checkpoint)
     scorer = TranceptEVEScorer(config, state, full_target_seq=target_seq, scoring_window=args.scoring_window, precision=args.precision,
                                device=args.device, EVE_sampler=args.EVE_sampler, **kw)
-    if not os.path.isdir(args.output_scores_folder):
+    if world > 1:
+        scorer.shard = (rank, world)
+    if rank == 0 and not os.path.isdir(args.output_scores_folder):
         os.mkdir(args.output_scores_folder)
     DMS_data = pd.read_csv(args.DMS_data_folder + os.sep + DMS_file_name, low_memory=False)
     all_scores = scorer.score_mutants(DMS_data=DMS_data, target_seq=target_seq, scoring_mirror=not args.deactivate_scoring_mirror,
@@ -134,6 +138,10 @@ def main(argv=None):
                                       indel_mode=args.indel_mode)
     if len(all_scores) > 0 and args.clinvar_scoring:
         all_scores = pd.merge(all_scores, DMS_data, how="left", on="mutant")
+    if rank != 0:  # every rank holds the complete scores; one writer
+        scorer.close()
+        _finish_distributed(world)
+        return
     all_scores.to_csv(args.output_scores_folder + os.sep + DMS_id + ".csv", index=False)
     log_name = "ClinVar_scoring_Tranception_20221130" if args.clinvar_scoring else "TranceptEVE_aggregation_coefficients_log"
     with open(log_name, "a+") as fh:  # the reference appends one line per assay to this file in the working directory
@@ -142,6 +150,7 @@ def main(argv=None):
         fh.write(",".join(str(x) for x in [DMS_id, len(all_scores), len(all_scores.dropna()), scorer.MSA_processed_depth, scorer.EVE_processed_depth,
                                            scorer.retrieval_inference_MSA_weight, scorer.retrieval_inference_EVE_weight]) + "\n")
     scorer.close()
+    _finish_distributed(world)
 
 
 if __name__ == "__main__":

@@ -2,7 +2,8 @@
 ``mutated_sequence, avg_score_L_to_R, avg_score_R_to_L, avg_score``; reference lines :18-45 flags, :57-77 DMS resolution,
 :105-122 scoring + CSV). Inference-time retrieval for substitutions builds the MSA prior on the GPU (msa_processing.get_msa_prior =
 utils/msa_utils.py:63-138), with EVE-style sequence weights read from ``--MSA_weights_folder`` through the MSA_processing mirror when
-given. Additive flags: --precision, --device, --MSA_log_prior_npy (a precomputed ``[L_full, 25]`` log prior)."""
+given. Additive flags: --precision, --device, --MSA_log_prior_npy (a precomputed ``[L_full, 25]`` log prior). Launched with torchrun
+(``--nproc-per-node N``) the assay's sequence rows are split over N GPUs (see ``_init_distributed``)."""
 from __future__ import annotations
 
 import argparse
@@ -54,9 +55,33 @@ def create_parser():
     return parser
 
 
+def _init_distributed(args):
+    """Under torchrun (WORLD_SIZE > 1) the sequence rows of the assay are split over the GPUs of the box: one process
+    per GPU, NCCL, device = LOCAL_RANK; every rank ends with the full score vector, rank 0 writes the CSV. Single process: (0, 1)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    args.device = local
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank(), world
+
+
+def _finish_distributed(world):
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
 def main(argv=None):
     from proteingym_b200.tranception_engine import TranceptionScorer, load_tranception_checkpoint
     args = create_parser().parse_args(argv)
+    rank, world = _init_distributed(args)
     MSA_start = MSA_end = None
     if args.DMS_reference_file_path:
         mapping = pd.read_csv(args.DMS_reference_file_path)
@@ -94,14 +119,18 @@ def main(argv=None):
                 log_prior = np.log(prior).astype(np.float32)
     config, state = load_tranception_checkpoint(args.checkpoint)
     scorer = TranceptionScorer(config, state, precision=args.precision, device=args.device)
-    if not os.path.isdir(args.output_scores_folder):
+    if world > 1:
+        scorer.shard = (rank, world)
+    if rank == 0 and not os.path.isdir(args.output_scores_folder):
         os.mkdir(args.output_scores_folder)
     DMS_data = pd.read_csv(args.DMS_data_folder + os.sep + DMS_file_name, low_memory=False)
     all_scores = scorer.score_mutants(DMS_data=DMS_data, target_seq=target_seq, scoring_mirror=not args.deactivate_scoring_mirror,
                                       indel_mode=args.indel_mode, scoring_window=args.scoring_window, log_prior=log_prior,
                                       retrieval_inference_weight=args.retrieval_inference_weight, MSA_start=MSA_start or 0, MSA_end=MSA_end)
-    all_scores.to_csv(args.output_scores_folder + os.sep + DMS_id + ".csv", index=False)
+    if rank == 0:
+        all_scores.to_csv(args.output_scores_folder + os.sep + DMS_id + ".csv", index=False)
     scorer.close()
+    _finish_distributed(world)
 
 
 if __name__ == '__main__':

@@ -279,11 +279,37 @@ class TranceptionScorer:
         out = pd.DataFrame(recs, columns=["mutated_sequence", "sliced_mutated_sequence", "window_start", "window_end"])
         return out.drop_duplicates().reset_index(drop=True)
 
+    shard = None  # (rank, world) with an initialised torch.distributed group: split the sequence rows of each direction over the ranks
+
+    def _sharded_logprobs(self, strings, windows, reverse, prior_kw):
+        """``sequence_logprobs`` over all ``strings``; with ``self.shard`` set, every rank scores a strided subset (rows are sorted
+        by length inside sequence_logprobs, so a stride balances the padded work) and one all-gather completes the vector
+        (the mutant row is the unit for Tranception). A sequence's value does not depend on what it is batched with,
+        so the result is the same for any world size."""
+        if self.shard is None or self.shard[1] <= 1:
+            return self.sequence_logprobs(strings, windows=windows, flip=reverse, **prior_kw)
+        import torch.distributed as dist
+        rank, world = self.shard
+        n = len(strings)
+        mine = list(range(rank, n, world))
+        local = self.sequence_logprobs([strings[i] for i in mine], windows=[windows[i] for i in mine], flip=reverse, **prior_kw)
+        width = (n + world - 1) // world
+        dev = self.device if dist.get_backend() == "nccl" else torch.device("cpu")
+        buf = torch.zeros(width, dtype=torch.float32, device=dev)
+        buf[:len(mine)] = torch.from_numpy(np.asarray(local, dtype=np.float32)).to(dev)
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf)
+        out = np.zeros(n, dtype=np.float32)
+        for r in range(world):
+            idx = np.arange(r, n, world)
+            out[idx] = parts[r][:len(idx)].cpu().numpy()
+        return out
+
     def _direction(self, sl, target_seq, name, scoring_window, reverse, prior_kw):
         strings = [s[::-1] for s in sl["sliced_mutated_sequence"]] if reverse else list(sl["sliced_mutated_sequence"])
         windows = list(zip(sl["window_start"], sl["window_end"]))
         sc = sl.copy()
-        sc["score"] = self.sequence_logprobs(strings, windows=windows, flip=reverse, **prior_kw).astype(np.float32)
+        sc["score"] = self._sharded_logprobs(strings, windows, reverse, prior_kw).astype(np.float32)
         if scoring_window == "sliding":
             sc = sc[["mutated_sequence", "score"]].groupby("mutated_sequence").sum().reset_index()
         sc["score"] = sc["score"] / sc["mutated_sequence"].map(len)

@@ -100,3 +100,53 @@ def test_position_partition_chunks_and_row_gather_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res)
+
+
+def _worker_tranception_rows(rank, world, port, q):
+    """TranceptEVE scoring with the sequence rows of each direction split over 2 ranks (CPU stand-in for the device half)."""
+    import json
+    import sys
+    import tempfile
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(4)
+    from conftest import GOLDEN
+    from cpu_trancepteve import CpuTranceptEVE
+    from trancepteve_cases import CASES, make_inputs
+    name = "trancepteve_long"
+    case = CASES[name]
+    gd = os.path.join(GOLDEN, name)
+    meta = json.load(open(os.path.join(gd, "meta.json")))
+    a = case["arch"]
+    arch = synth.TranceptionArch(a[0], a[1], a[2], a[3], n_ctx=a[4])
+    inp = make_inputs(case, tempfile.mkdtemp())
+    sc = CpuTranceptEVE(arch, synth.make_tranception_state(arch, meta["tranception_seed"]), meta["target_seq"], case["kind"],
+                        np.load(os.path.join(gd, "msa_log_prior_init.npy")), np.load(os.path.join(gd, "eve_log_prior_init.npy")),
+                        case["msa"][0], case["msa"][1], (meta["MSA_processed_depth"], meta["EVE_processed_depth"]), meta["focus_cols"],
+                        case["col_thr"], case["msa_recal"], case["eve_recal"])
+    sc.device = torch.device("cpu")
+    sc.shard = (rank, world)
+    out = sc.score_mutants(inp["dms"], meta["target_seq"])
+    import pandas as pd
+    ref = pd.read_csv(os.path.join(gd, "reference_scores.csv"))
+    err = float(np.abs(out["avg_score"].values - ref["avg_score"].values).max())
+    q.put((rank, err, list(out["mutated_sequence"]) == list(ref["mutated_sequence"]), out["avg_score"].values.tolist()))
+    dist.destroy_process_group()
+
+
+def test_tranception_rows_split_over_two_ranks_match_reference():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_tranception_rows, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] < 2e-5 and res[1][1] < 2e-5 and res[0][2] and res[1][2]
+    assert res[0][3] == res[1][3]   # every rank ends up with the same, complete score vector
