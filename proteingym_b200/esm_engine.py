@@ -119,10 +119,10 @@ class EsmScorer:
                                                 out.data_ptr(), stream), self.handle)
         return out
 
-    def _forward_window(self, tokens: torch.Tensor, start: int, T: int) -> torch.Tensor:
+    def _forward_window(self, tokens: torch.Tensor, start: int, T: int, mask_pos: int = -1) -> torch.Tensor:
         out = torch.empty((T, self.config.vocab), dtype=torch.float32, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(self.lib.pg_forward_logprobs(self.handle, tokens.data_ptr(), int(tokens.numel()), start, T, -1,
+        _lib.check(self.lib.pg_forward_logprobs(self.handle, tokens.data_ptr(), int(tokens.numel()), start, T, mask_pos,
                                                 out.data_ptr(), stream), self.handle)
         return out
 

@@ -204,3 +204,24 @@ def test_tranception_checkpoint_round_trip(tmp_path):
     assert (cfg["n_embd"], cfg["n_head"], cfg["n_layer"], cfg["n_inner"]) == (256, 4, 2, 512)
     assert "lm_head.weight" not in state and torch.equal(state["wte.weight"], st["transformer.wte.weight"])
     assert torch.equal(state["h.1.mlp.c_fc.weight"], st["transformer.h.1.mlp.c_fc.weight"])
+
+
+def test_model_object_seam_host_side():
+    """proteingym_b200.pretrained: batch converter = the reference's for one or several sequences (data.py:262-297); mask detection;
+    no CPU forward behind the model object."""
+    from proteingym_b200 import pretrained
+    from proteingym_b200.alphabet import ALPHABET
+    labels, strs, tok = ALPHABET.get_batch_converter()([("protein1", "MKV"), ("p2", "ACDEF")])
+    assert labels == ["protein1", "p2"] and strs == ["MKV", "ACDEF"] and tok.dtype == torch.int64 and tuple(tok.shape) == (2, 7)
+    assert tok[0].tolist() == [0, 20, 15, 7, 2, 1, 1] and tok[1].tolist() == [0, 5, 23, 13, 9, 18, 2]
+    row = tok[1].clone()
+    assert pretrained.mask_position(row, ALPHABET.mask_idx) == -1
+    row[3] = ALPHABET.mask_idx
+    assert pretrained.mask_position(row, ALPHABET.mask_idx) == 3
+    row[4] = ALPHABET.mask_idx
+    with pytest.raises(NotImplementedError):
+        pretrained.mask_position(row, ALPHABET.mask_idx)
+    m = pretrained.B200EsmModel(None, {}, "x")
+    assert m.eval() is m
+    with pytest.raises(RuntimeError, match="no CPU forward"):
+        m(tok[:1])
