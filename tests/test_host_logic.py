@@ -225,3 +225,17 @@ def test_model_object_seam_host_side():
     assert m.eval() is m
     with pytest.raises(RuntimeError, match="no CPU forward"):
         m(tok[:1])
+
+
+def test_tranception_tokenize_batch_equals_per_sequence_tokenize():
+    from proteingym_b200.tranception_engine import PAD, tokenize, tokenize_batch
+    rng = np.random.RandomState(0)
+    seqs = ["", "M", "ACDEFGHIKLMNPQRSTVWY", "MKU*-xZ", "B" * 5] + ["".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWYXBJZ"), size=n)) for n in (3, 17, 64, 200)]
+    T = max(len(s) for s in seqs) + 2
+    ids, lens = tokenize_batch(seqs, T)
+    assert ids.dtype == np.int32 and ids.shape == (len(seqs), T) and lens.dtype == np.int32
+    for r, s in enumerate(seqs):
+        t = tokenize(s)
+        assert lens[r] == len(t) and ids[r, :len(t)].tolist() == t and (ids[r, len(t):] == PAD).all()
+    e, l0 = tokenize_batch([], 4)
+    assert e.shape == (0, 4) and l0.shape == (0,)
