@@ -373,6 +373,36 @@ class TranceptionScorer:
         return out
 
 
+def prefix_reuse_plan(slices: pd.DataFrame, target_seq: str, tile: int = 128) -> pd.DataFrame:
+    """Planning aid for exact wild-type-prefix reuse (not used by the scorer yet). In a causal decoder every hidden
+    state of a mutant before its first changed token equals the wild type's, so with the WT scored in the same window
+
+        score(mutant) - score(WT) = [ lp_WT[fd-1, tok_m[fd]] - lp_WT[fd-1, tok_WT[fd]] ]            (row fd-1: same state, other label)
+                                   + sum_{t >= fd} lp_m[t, label_m[t]] - sum_{t >= fd} lp_WT[t, label_WT[t]]
+
+    where fd is the first token index at which the two ``[CLS] slice [SEP]`` strings differ and lp[t] the log-probability row that
+    predicts token t+1. Only rows >= fd need the transformer (keys / values of earlier rows come from the WT run). For every
+    (mutant slice, direction) this returns fd, the tile-aligned start the kernels would use, and the rows to compute, so the
+    saving can be read off an assay before any kernel exists. ``slices``: output of ``TranceptionScorer.slices`` (optimal windows)."""
+    wt_by_window = {(a, b): s for ms, s, a, b in zip(slices["mutated_sequence"], slices["sliced_mutated_sequence"], slices["window_start"],
+                                                    slices["window_end"]) if ms == target_seq}
+    recs = []
+    for ms, s, a, b in zip(slices["mutated_sequence"], slices["sliced_mutated_sequence"], slices["window_start"], slices["window_end"]):
+        if ms == target_seq:
+            continue
+        wt = wt_by_window.get((a, b))
+        if wt is None or len(wt) != len(s):
+            continue  # indels: no position-wise correspondence with a WT slice
+        T = len(s) + 2
+        for direction, x, y in (("L_to_R", s, wt), ("R_to_L", s[::-1], wt[::-1])):
+            diff = next((i for i, (c, d) in enumerate(zip(x, y)) if c != d), len(x))
+            fd = 1 + diff                                    # token index ([CLS] is token 0)
+            start = (fd // tile) * tile
+            recs.append((ms, a, b, direction, T, fd, start, T - fd, T - start))
+    return pd.DataFrame(recs, columns=["mutated_sequence", "window_start", "window_end", "direction", "tokens", "first_diff_token",
+                                       "aligned_start", "rows_exact", "rows_tile_aligned"])
+
+
 def apply_substitutions(focus_seq: str, mutant: str, start_idx: int = 1) -> str:
     """scoring_utils.get_mutated_sequence (:16-31), same assertion messages."""
     s = list(focus_seq)

@@ -211,3 +211,39 @@ def test_cli_flag_surface_matches_reference(tag):
     assert set(mine) - set(ref) <= {"precision", "device", "MSA_log_prior_npy", "EVE_sampler"} and not set(ref) - set(mine)
     for k, v in ref.items():
         assert mine[k] == v, k
+
+
+def test_prefix_reuse_identity_and_expected_saving():
+    """The identity behind exact wild-type-prefix reuse, checked with the oracle's CPU forward, and the row counts the
+    planner predicts for a config-4-like assay (L = 512 single substitutions)."""
+    from oracle import tranception_oracle as O
+    from proteingym_b200.tranception_engine import TranceptionScorer, prefix_reuse_plan, tokenize
+    arch = synth.TranceptionArch(2, 128, 4, 256)
+    st = synth.make_tranception_state(arch, 3)
+    wt = synth.random_protein(40, 8)
+    rows_wt, tot_wt = O.fused_logprob_rows(st, wt, arch.layers, arch.heads)
+    for mut in ("A7C" if wt[6] == "A" else f"{wt[6]}7C", f"{wt[0]}1W:{wt[30]}31Y", f"{wt[39]}40D"):
+        ms = synth.apply_mutant(wt, mut)
+        for rev in (False, True):
+            x, y = (ms[::-1], wt[::-1]) if rev else (ms, wt)
+            rows_y, tot_y = O.fused_logprob_rows(st, y, arch.layers, arch.heads) if rev else (rows_wt, tot_wt)
+            rows_x, tot_x = O.fused_logprob_rows(st, x, arch.layers, arch.heads)
+            tx, ty = tokenize(x), tokenize(y)
+            fd = next(i for i in range(len(tx)) if tx[i] != ty[i])
+            assert np.abs(rows_x[:fd] - rows_y[:fd]).max() < 1e-6           # identical states before the first changed token
+            tail = lambda r, t: sum(float(r[k, t[k + 1]]) for k in range(fd, len(t) - 1))  # noqa: E731
+            delta = (float(rows_y[fd - 1, tx[fd]]) - float(rows_y[fd - 1, ty[fd]])) + tail(rows_x, tx) - tail(rows_y, ty)
+            assert abs(delta - (tot_x - tot_y)) < 1e-4
+    # planner on a 512-residue protein with 400 random single substitutions
+    seq = synth.random_protein(512, 1)
+    muts = synth.sample_mutants(seq, 400, 2)
+    df = pd.DataFrame({"mutant": muts, "mutated_sequence": [synth.apply_mutant(seq, m) for m in muts]})
+    sc = TranceptionScorer.__new__(TranceptionScorer)
+    sc.n_ctx = 1024
+    plan = prefix_reuse_plan(sc.slices(df, seq), seq)
+    assert len(plan) == 2 * len(muts) and (plan["tokens"] == 514).all()
+    exact, aligned = plan["rows_exact"].sum() / plan["tokens"].sum(), plan["rows_tile_aligned"].sum() / plan["tokens"].sum()
+    assert 0.45 < exact < 0.55 and 0.55 < aligned < 0.70   # half the rows exactly; ~5/8 with 128-row tile alignment
+    lr = plan[plan.direction == "L_to_R"].set_index("mutated_sequence")
+    m0 = muts[0]
+    assert lr.loc[synth.apply_mutant(seq, m0), "first_diff_token"] == int(m0[1:-1])  # residue i (1-based) is token i
