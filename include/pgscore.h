@@ -29,11 +29,15 @@ enum pg_arch {
                              (tranception/model_pytorch.py:90-632); max_positions = n_ctx, vocab = 25 */
 };
 
-/* Tensor-core operand precision. The reference is strict fp32.
- *  PG_PREC_F16X3: every GEMM/attention operand is split into fp16 hi+lo and three tcgen05 passes (hi*hi + lo*hi + hi*lo)
- *                 accumulate in fp32 — ~22-bit operands; meets the 1e-3 abs per-mutant parity target.
- *  PG_PREC_F16  : single fp16 pass, fp32 accumulate; ~3x faster, |error| ~1e-2 on scores of std ~6 (Spearman > 0.999). */
-enum pg_precision { PG_PREC_F16 = 0, PG_PREC_F16X3 = 1 };
+/* Tensor-core operand precision. The reference is strict fp32. Every operand is an fp16 pair hi + lo.
+ *  PG_PREC_F16X3: three tcgen05 kind::f16 passes (hi*hi + lo*hi + hi*lo), fp32 accumulate — ~22-bit operands, 3 tensor-pipe
+ *                 units per product; the most accurate mode.
+ *  PG_PREC_F16F8: linear layers = one kind::f16 pass hi*hi + one kind::f8f6f4 pass holding BOTH cross terms as e4m3
+ *                 ([lo8 | hi8] x [hi8 | lo8] along K, 2x the fp16 rate) = 2 units; attention keeps the x3 scheme. ~16-bit
+ *                 operands; meets the 1e-3 abs per-mutant parity target. Default of the host code.
+ *  PG_PREC_F16  : single fp16 pass; fastest, |error| ~1e-2 on scores of std ~6 (Spearman > 0.999) — not a parity mode.
+ * In all modes the hi*hi accumulation is cut into K chunks that the epilogue adds in round-to-nearest fp32 (gemm_tc.cu). */
+enum pg_precision { PG_PREC_F16 = 0, PG_PREC_F16X3 = 1, PG_PREC_F16F8 = 2 };
 
 typedef struct {
   int32_t arch;            /* pg_arch */
@@ -58,7 +62,10 @@ typedef struct {
 
 /* Replaces pretrained.load_model_and_alphabet + model.cuda() (compute_fitness.py:349-353; esm/pretrained.py:24-218):
  * create a model instance, then hand it the (already key-normalised) fp32 state dict; the library repacks into its own
- * fp16 hi/lo buffers (q scaling folded in, multihead_attention.py:261), so the caller may free its tensors. */
+ * operand buffers (q scaling folded in, multihead_attention.py:261). pg_load_weights is SYNCHRONOUS: it runs on the default
+ * stream and returns after the repack has finished, so the caller may free its tensors immediately.
+ * Limits of one handle: head_dim 64; a pass holds at most max_rows token rows and 8192 sequences (longer inputs are processed
+ * in several passes inside the call; results do not depend on the split). */
 int pg_create(const pg_model_desc* desc, pg_handle* out);
 int pg_load_weights(pg_handle h, const pg_tensor* tensors, int32_t n);
 int pg_destroy(pg_handle h);
@@ -132,9 +139,13 @@ int pg_score_mutants(const float* table, int32_t n_rows, int32_t vocab, const in
 
 /* ---- kernel-level entry points (used by the parity tests and bench roofline legs; same kernels as above) ---- */
 
-/* C = epilogue(A[M,K] * W[N,K]^T + bias). fp16 operands in [hi | lo] column blocks when nseg == 3.
- *   a: [M, lda] fp16 (lda >= K, or >= 2K with lo at column offset K when nseg == 3); w: [N, ldw] likewise.
- *   epi 0: out_h[M, ldo] = fp16(acc + bias) (lo part at column offset out_lo_off if > 0)
+/* C = epilogue(A[M,K] * W[N,K]^T + bias). Operand rows (pitches lda/ldw/ldo in fp16 elements):
+ *   nseg 1: [hi fp16 (K)]        nseg 3: [hi fp16 (K) | lo fp16 (K)]
+ *   nseg 2: a = [hi fp16 (K) | lo8 (K bytes) | hi8 (K bytes)] with lo8 = e4m3(lo * 2^11 * a_scale), hi8 = e4m3(hi * a_scale);
+ *           w = [hi fp16 (K) | hi8 (K bytes) | lo8 (K bytes)] with the per-row scale t_n, w_inv[n] = 1/t_n (pg_pack_weight fmt 2)
+ *   out_fmt (epi != 2): 0 = auto (1 if out_lo_off > 0), 1 = fp16 lo plane at column out_lo_off, 2 = e4m3 planes
+ *           [lo8 (N bytes) | hi8 (N bytes)] at column out_lo_off scaled by out_scale (i.e. an `a` operand for an nseg-2 GEMM)
+ *   epi 0: out_h[M, ldo] = fp16(acc + bias) (+ second plane(s) per out_fmt)
  *   epi 1: same with exact-erf GELU (esm/modules.py:17-24)
  *   epi 2: resid[M, ldr] (fp32) += acc + bias
  *   epi 3: as 0, with rotary applied to the first 2*rot_dim columns ([q | k], heads of 64; esm/rotary_embedding.py:11-20),
@@ -148,12 +159,19 @@ typedef struct {
   void* out_h; int64_t ldo; int64_t out_lo_off;
   float* resid; int64_t ldr;
   const float* rot_cos; const float* rot_sin; int32_t rot_T; int32_t rot_dim;
+  float a_scale; const float* w_inv; /* nseg 2 */
+  int32_t out_fmt; float out_scale;
 } pg_gemm_args;
 int pg_gemm(const pg_gemm_args* args, pg_stream stream);
 
-/* LayerNorm (eps 1e-5, esm/modules.py:68-81) of fp32 rows -> fp16 hi (and lo at column offset lo_off if > 0). */
+/* fp32 weights [N, K] (nn.Linear layout) -> the operand format of pg_gemm's `w`: fmt 0 = nseg 1, fmt 1 = nseg 3,
+ * fmt 2 = nseg 2 (writes w_inv[N]). out has N rows of K (fmt 0) or 2K (fmt 1, 2) fp16 elements. */
+int pg_pack_weight(const float* w, int32_t N, int32_t K, int32_t fmt, void* out, float* w_inv, pg_stream stream);
+
+/* LayerNorm (eps 1e-5, esm/modules.py:68-81) of fp32 rows -> fp16 hi, and at column offset lo_off (if > 0) the second
+ * plane(s): fmt 0 = auto (fp16 lo), 1 = fp16 lo, 2 = e4m3 [lo8 | hi8] scaled by `scale` (an nseg-2 `a` operand). */
 int pg_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int32_t rows, int32_t d,
-                     void* out, int64_t ldo, int64_t lo_off, pg_stream stream);
+                     void* out, int64_t ldo, int64_t lo_off, int32_t fmt, float scale, pg_stream stream);
 
 /* Multi-head self-attention over equal-length sequences (multihead_attention.py:357-394), head_dim 64, q pre-scaled.
  *   qkv [B*T, ld] fp16 with q at column 0, k at column d, v at 2d (d = heads*64); lo parts at +lo_off when nseg == 3.
@@ -163,7 +181,8 @@ typedef struct {
   void* out; int64_t ldo; int64_t out_lo_off;
   int32_t B, T, heads, nseg;
   int32_t causal; const float* alibi_slopes; /* NULL = none */
-  int32_t impl; /* 0 = auto (what the model uses: 4 unless PG_ATTN_INPLACE=0), 1 = mma.sync kernel, 2 = tcgen05 kernel with P in its own TMEM columns, 3 = tcgen05 tile-pair kernel (experimental), 4 = tcgen05 kernel with P in place over S */
+  int32_t impl; /* 0 = the model's kernel (tcgen05/TMEM, P in place over S), 1 = mma.sync cross-check kernel */
+  int32_t out_fmt; float out_scale; /* as pg_gemm_args (0 = auto); 2 only with impl 0 */
 } pg_attn_args;
 int pg_attention(const pg_attn_args* args, pg_stream stream);
 

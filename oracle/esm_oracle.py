@@ -81,7 +81,7 @@ def load_state(st: dict, kind: str, dtype=torch.float32) -> dict:
 
 
 def esm_forward(st: dict, tokens: torch.Tensor, kind: str, layers: int, heads: int, token_dropout=True,
-                dtype=torch.float32, rnd=None) -> torch.Tensor:
+                dtype=torch.float32, rnd=None, mm=None) -> torch.Tensor:
     """logits [B,T,V]. Restates ProteinBertModel.forward (esm/model/esm1.py:116-193, ESM-1b branch) and
     ESM2.forward (esm/model/esm2.py:76-143); TransformerLayer (esm/modules.py:120-142); MultiheadAttention manual
     path (esm/multihead_attention.py:242-395; the F.multi_head_attention_forward fast path :196-230 is the same
@@ -89,9 +89,14 @@ def esm_forward(st: dict, tokens: torch.Tensor, kind: str, layers: int, heads: i
     sequence or equal-length windows), so padding-mask branches reduce to identity.
 
     ``rnd`` (default None = exact) is a numerics-study hook, not reference behaviour: a function applied to every
-    tensor-core GEMM operand (e.g. round-trip through fp16) to emulate the CUDA path's operand rounding on CPU."""
+    tensor-core GEMM operand (e.g. round-trip through fp16) to emulate the CUDA path's operand rounding on CPU.
+    ``mm`` (default None = exact ``a @ w.T``) is the same kind of hook for the four linear layers as a whole: ``mm(a, w, site)``
+    with site in {"qkv", "out", "fc1", "fc2"} returns the emulated product (used to study split-operand schemes whose result is
+    not a product of two rounded operands, e.g. fp16 hi*hi + fp8 cross terms)."""
     if rnd is None:
         rnd = lambda t: t
+    if mm is None:
+        mm = lambda a, w, site: rnd(a) @ rnd(w).T
     E = st["lm_head.weight"].to(dtype)  # shared embedding / output matrix, see load_state
     B, T = tokens.shape
     d = E.shape[1]
@@ -113,10 +118,10 @@ def esm_forward(st: dict, tokens: torch.Tensor, kind: str, layers: int, heads: i
     for i in range(layers):
         p = f"layers.{i}."
         W = lambda n: st[p + n].to(dtype)
-        h = rnd(layer_norm(x, W("self_attn_layer_norm.weight"), W("self_attn_layer_norm.bias")))
-        q = h @ rnd(W("self_attn.q_proj.weight")).T + W("self_attn.q_proj.bias")
-        k = h @ rnd(W("self_attn.k_proj.weight")).T + W("self_attn.k_proj.bias")
-        v = h @ rnd(W("self_attn.v_proj.weight")).T + W("self_attn.v_proj.bias")
+        h = layer_norm(x, W("self_attn_layer_norm.weight"), W("self_attn_layer_norm.bias"))
+        q = mm(h, W("self_attn.q_proj.weight"), "qkv") + W("self_attn.q_proj.bias")
+        k = mm(h, W("self_attn.k_proj.weight"), "qkv") + W("self_attn.k_proj.bias")
+        v = mm(h, W("self_attn.v_proj.weight"), "qkv") + W("self_attn.v_proj.bias")
         q = q * hd ** -0.5  # multihead_attention.py:261
         q = q.view(B, T, heads, hd).transpose(1, 2)
         k = k.view(B, T, heads, hd).transpose(1, 2)
@@ -126,11 +131,11 @@ def esm_forward(st: dict, tokens: torch.Tensor, kind: str, layers: int, heads: i
             k = k * cos + rotate_half(k) * sin
         q, k, v = rnd(q), rnd(k), rnd(v)
         a = torch.softmax(q @ k.transpose(-1, -2), dim=-1)  # :357, :379
-        o = rnd((rnd(a) @ v).transpose(1, 2).reshape(B, T, d))  # :387-394
-        x = x + o @ rnd(W("self_attn.out_proj.weight")).T + W("self_attn.out_proj.bias")
-        h = rnd(layer_norm(x, W("final_layer_norm.weight"), W("final_layer_norm.bias")))
-        h = rnd(gelu(h @ rnd(W("fc1.weight")).T + W("fc1.bias")))
-        x = x + h @ rnd(W("fc2.weight")).T + W("fc2.bias")
+        o = (rnd(a) @ v).transpose(1, 2).reshape(B, T, d)  # :387-394
+        x = x + mm(o, W("self_attn.out_proj.weight"), "out") + W("self_attn.out_proj.bias")
+        h = layer_norm(x, W("final_layer_norm.weight"), W("final_layer_norm.bias"))
+        h = gelu(mm(h, W("fc1.weight"), "fc1") + W("fc1.bias"))
+        x = x + mm(h, W("fc2.weight"), "fc2") + W("fc2.bias")
     x = layer_norm(x, st["emb_layer_norm_after.weight"].to(dtype), st["emb_layer_norm_after.bias"].to(dtype))
     h = gelu(x @ st["lm_head.dense.weight"].to(dtype).T + st["lm_head.dense.bias"].to(dtype))
     h = layer_norm(h, st["lm_head.layer_norm.weight"].to(dtype), st["lm_head.layer_norm.bias"].to(dtype))

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpgscore.so")
 
 PG_ARCH_ESM1B, PG_ARCH_ESM2, PG_ARCH_TRANCEPTION = 0, 1, 2
-PG_PREC_F16, PG_PREC_F16X3 = 0, 1
+PG_PREC_F16, PG_PREC_F16X3, PG_PREC_F16F8 = 0, 1, 2
 
 
 class PgModelDesc(C.Structure):
@@ -26,14 +26,16 @@ class PgGemmArgs(C.Structure):
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("nseg", C.c_int32), ("epi", C.c_int32),
                 ("out_h", C.c_void_p), ("ldo", C.c_int64), ("out_lo_off", C.c_int64),
                 ("resid", C.c_void_p), ("ldr", C.c_int64),
-                ("rot_cos", C.c_void_p), ("rot_sin", C.c_void_p), ("rot_T", C.c_int32), ("rot_dim", C.c_int32)]
+                ("rot_cos", C.c_void_p), ("rot_sin", C.c_void_p), ("rot_T", C.c_int32), ("rot_dim", C.c_int32),
+                ("a_scale", C.c_float), ("w_inv", C.c_void_p), ("out_fmt", C.c_int32), ("out_scale", C.c_float)]
 
 
 class PgAttnArgs(C.Structure):
     _fields_ = [("qkv", C.c_void_p), ("ld", C.c_int64), ("lo_off", C.c_int64),
                 ("out", C.c_void_p), ("ldo", C.c_int64), ("out_lo_off", C.c_int64),
                 ("B", C.c_int32), ("T", C.c_int32), ("heads", C.c_int32), ("nseg", C.c_int32),
-                ("causal", C.c_int32), ("alibi_slopes", C.c_void_p), ("impl", C.c_int32)]
+                ("causal", C.c_int32), ("alibi_slopes", C.c_void_p), ("impl", C.c_int32),
+                ("out_fmt", C.c_int32), ("out_scale", C.c_float)]
 
 
 class PgArFusion(C.Structure):
@@ -61,7 +63,8 @@ SIGNATURES = {
                                      C.c_void_p]),
     "pg_gemm": (C.c_int, [C.POINTER(PgGemmArgs), C.c_void_p]),
     "pg_layernorm_f16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
-                                   C.c_int64, C.c_int64, C.c_void_p]),
+                                   C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),
+    "pg_pack_weight": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pg_attention": (C.c_int, [C.POINTER(PgAttnArgs), C.c_void_p]),
     "pg_msa_cluster_neighbors": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pg_msa_prior": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),

@@ -18,15 +18,17 @@ int set_error(int code, const std::string& msg) {
   tls_error() = msg;
   return code;
 }
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+int num_sms() {  // of the current device (cached per ordinal: one process may hold handles on several GPUs)
+  static int n[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!n[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
 }
 
 // ---- launch accounting / profiling -------------------------------------------------------------------------------
@@ -95,6 +97,39 @@ __global__ void pack_weight_t_kernel(const float* __restrict__ w, int N, int K, 
   out[static_cast<long long>(n) * K * np + k] = hi;
   if (np == 2) out[static_cast<long long>(n) * K * np + K + k] = lo;
 }
+// Weight row n in the fp16 + e4m3 format of gemm_tc.cu (nseg 2): [hi fp16 (K) | hi8 (K bytes) | lo8 (K bytes)], row pitch 4K bytes,
+// hi8 = e4m3(hi * t), lo8 = e4m3(lo * 2^11 * t) with t = the power of two that puts the row's largest |hi| in (112, 224];
+// w_inv[n] = 1 / t. One warp per row; element (n, k) of the source is w[n * sn + k * sk] (sk = 1: nn.Linear; sn = 1: Conv1D).
+__global__ void pack_weight_f8_kernel(const float* __restrict__ w, int N, int K, long long sn, long long sk, float scale,
+                                      __half* __restrict__ out, float* __restrict__ w_inv) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* wr = w + static_cast<long long>(n) * sn;
+  float amax = 0.f;
+  for (int k = lane; k < K; k += 32) amax = fmaxf(amax, fabsf(__half2float(f2h_sat(wr[k * sk] * scale))));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  float t = 1.f;
+  if (amax > 0.f) {
+    int e;
+    frexpf(amax, &e);                 // amax = m * 2^e, m in [0.5, 1)
+    t = ldexpf(1.f, 8 - e);           // amax * t in [128, 256)
+    if (amax * t > 224.f) t *= 0.5f;  // -> (112, 224]: one binade of headroom below the e4m3 maximum of 448
+  }
+  __half* orow = out + static_cast<long long>(n) * K * 2;
+  uint8_t* f8 = reinterpret_cast<uint8_t*>(orow + K);
+  for (int k = lane; k < K; k += 32) {
+    const float v = wr[k * sk] * scale;
+    __half hi, lo;
+    split_hi_lo(v, hi, lo);
+    const float hf = __half2float(hi);
+    orow[k] = hi;
+    f8[k] = static_cast<uint8_t>(cvt_e4m3x2(hf * t, 0.f) & 0xff);
+    f8[K + k] = static_cast<uint8_t>(cvt_e4m3x2((v - hf) * t * 2048.f, 0.f) & 0xff);
+  }
+  if (lane == 0) w_inv[n] = 1.f / t;
+}
 __global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, float scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i] * scale;
@@ -104,15 +139,26 @@ struct Layer {
   __half *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
   float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
   float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+  float *iqkv = nullptr, *io = nullptr, *i1 = nullptr, *i2 = nullptr;  // PG_PREC_F16F8: 1 / t_n per weight row
   float* conv_taps = nullptr;  // Tranception: [3][4][64][8]
 };
+
+// Power-of-two scales the producers of A operands apply to their e4m3 planes (PG_PREC_F16F8; gemm_tc.cu header). e4m3 keeps
+// ~2^-4 relative precision from 2^-6 to 448 (scaled), so the scale only places the window: values above 448/s saturate (their
+// cross-term contribution degrades towards single-fp16 accuracy, nothing worse), values below 2^-9/s vanish from the cross term.
+// Measured insensitive between 1 and 16 (scripts/precision_f8.py).
+constexpr float S_LN = 4.f;     // LayerNorm output            -> QKV / fc1 GEMM     (|x| up to 112)
+constexpr float S_ATT = 4.f;    // attention output            -> out_proj GEMM
+constexpr float S_GELU = 2.f;   // GELU(fc1) (ESM)             -> fc2 GEMM           (up to 224)
+constexpr float S_RELU2 = 1.f;  // relu(fc1)^2 (Tranception)   -> fc2 GEMM           (up to 448)
 
 }  // namespace
 }  // namespace pg
 
 struct pg_handle_s {
   pg_model_desc desc{};
-  int np = 1;  // operand planes: 1 (fp16) or 2 (hi|lo)
+  int np = 1;    // operand row pitch in units of the fp16 hi plane: 1 (fp16) or 2 (hi | lo, or hi | e4m3 planes)
+  int nseg = 1;  // GEMM operand mode: 1 fp16, 3 fp16 hi/lo x3, 2 fp16 + e4m3 cross terms
   bool loaded = false;
   std::string err;
   std::vector<void*> allocs;
@@ -163,12 +209,40 @@ __global__ void row_select_kernel(const int32_t* positions, const int32_t* win_s
   sel[i] = tok - (win_start ? win_start[gp] : 0);
 }
 
+// One linear layer of the model: A in the handle's operand format (common.h: fmt 0 / 1 / 2 by precision mode).
+struct Lin {
+  const __half* a; int64_t lda; float a_scale;  // a_scale: scale of A's e4m3 planes (PG_PREC_F16F8)
+  const __half* w; const float* w_inv; const float* bias;
+  int M, N, K, epi;
+  __half* out = nullptr; int out_fmt = 0; float out_scale = 0.f;  // epi != 2
+  float* resid = nullptr;                                          // epi == 2
+};
+int run_lin(pg_handle h, int cat, const Lin& L, cudaStream_t s, int rot_T = 0) {
+  const int np = h->np;
+  GemmLaunch g{};
+  g.a = L.a; g.lda = L.lda; g.w = L.w; g.ldw = static_cast<int64_t>(L.K) * np; g.bias = L.bias;
+  g.M = L.M; g.N = L.N; g.K = L.K; g.nseg = h->nseg; g.epi = L.epi;
+  g.a_scale = L.a_scale; g.w_inv = L.w_inv;
+  if (L.epi == 2) {
+    g.resid = L.resid; g.ldr = L.N;
+  } else {
+    g.out = L.out; g.ldo = static_cast<int64_t>(L.N) * np; g.out_fmt = L.out_fmt; g.out_lo_off = L.out_fmt ? L.N : 0;
+    g.out_scale = L.out_scale;
+  }
+  if (L.epi == 3) { g.rot_cos = h->rot_cos; g.rot_sin = h->rot_sin; g.rot_T = rot_T; g.rot_dim = h->desc.embed_dim; }
+  ProfScope ps(cat, s);
+  return launch_gemm(g, s);
+}
+
 // `emit_rows` (device, [Bc]) = the one row per sequence the caller will read, or null when every row is needed. When given,
 // the last layer runs its attention-output / out_proj / LayerNorm / MLP for those rows only and leaves them in h->xc [Bc, d].
 int forward_rows(pg_handle h, const int32_t* tokens, int n_tokens, const int32_t* positions, const int32_t* win_start,
                  int p_offset, int Bc, int T, cudaStream_t s, const int32_t* emit_rows = nullptr) {
   const pg_model_desc& D = h->desc;
-  const int d = D.embed_dim, f = D.ffn_dim, np = h->np, nseg = (np == 2) ? 3 : 1;
+  const int d = D.embed_dim, f = D.ffn_dim, np = h->np;
+  const int afmt = h->nseg == 2 ? 2 : (np == 2 ? 1 : 0);  // operand format of GEMM inputs
+  const int qfmt = np == 2 ? 1 : 0;                        // q/k/v for the attention kernel: fp16 hi [| lo]
+  const int64_t ldd = static_cast<int64_t>(d) * np, ldf = static_cast<int64_t>(f) * np, ldq = static_cast<int64_t>(3 * d) * np;
   const int rows = Bc * T;
   EmbedLaunch e{};
   e.tokens = tokens; e.n_tokens = n_tokens; e.positions = positions; e.win_start = win_start;
@@ -179,66 +253,58 @@ int forward_rows(pg_handle h, const int32_t* tokens, int n_tokens, const int32_t
   { ProfScope ps(CAT_EMBED, s); rc = launch_embed(e, s); }
   if (rc) return rc;
   const bool rotary = (D.arch == PG_ARCH_ESM2);
+  auto ln = [&](const float* x, const float* g, const float* b, int nrows, __half* out) {
+    ProfScope ps(CAT_LN, s);
+    return launch_layernorm_f16(x, d, g, b, nrows, d, out, ldd, np == 2 ? d : 0, s, afmt, S_LN);
+  };
   for (int l = 0; l < D.layers; ++l) {
     const Layer& L = h->layers[l];
-    { ProfScope ps(CAT_LN, s); rc = launch_layernorm_f16(h->x, d, L.ln1g, L.ln1b, rows, d, h->abuf, static_cast<int64_t>(d) * np, np == 2 ? d : 0, s); }
+    rc = ln(h->x, L.ln1g, L.ln1b, rows, h->abuf);
     if (rc) return rc;
-    GemmLaunch g{};
-    g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.wqkv; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.bqkv;
-    g.M = rows; g.N = 3 * d; g.K = d; g.nseg = nseg; g.epi = rotary ? 3 : 0;
-    g.out = h->qkv; g.ldo = static_cast<int64_t>(3 * d) * np; g.out_lo_off = np == 2 ? 3 * d : 0;
-    g.rot_cos = h->rot_cos; g.rot_sin = h->rot_sin; g.rot_T = T; g.rot_dim = d;
-    { ProfScope ps(CAT_GEMM_QKV, s); rc = launch_gemm(g, s); }
+    Lin q{h->abuf, ldd, S_LN, L.wqkv, L.iqkv, L.bqkv, rows, 3 * d, d, rotary ? 3 : 0};
+    q.out = h->qkv; q.out_fmt = qfmt;
+    rc = run_lin(h, CAT_GEMM_QKV, q, s, T);
     if (rc) return rc;
     if (emit_rows && l == D.layers - 1) {
       // exact pruning of the final layer: one query row per sequence from here on
-      const int64_t lda_c = static_cast<int64_t>(d) * np, ldf_c = static_cast<int64_t>(f) * np;
       { ProfScope ps(CAT_ATTN, s, 2);
-        rc = launch_attn_single_query(h->qkv, static_cast<int64_t>(3 * d) * np, np == 2 ? 3 * d : 0, emit_rows, Bc, T, D.heads, h->cabuf,
-                                      lda_c, np == 2 ? d : 0, s);
+        rc = launch_attn_single_query(h->qkv, ldq, np == 2 ? 3 * d : 0, emit_rows, Bc, T, D.heads, h->cabuf, ldd, np == 2 ? d : 0, s,
+                                      afmt, S_ATT);
         if (!rc) rc = launch_gather_rows(h->x, emit_rows, Bc, T, d, h->xc, s); }
       if (rc) return rc;
-      g = GemmLaunch{};
-      g.a = h->cabuf; g.lda = lda_c; g.w = L.wo; g.ldw = lda_c; g.bias = L.bo;
-      g.M = Bc; g.N = d; g.K = d; g.nseg = nseg; g.epi = 2; g.resid = h->xc; g.ldr = d;
-      { ProfScope ps(CAT_GEMM_OUT, s); rc = launch_gemm(g, s); }
+      Lin o{h->cabuf, ldd, S_ATT, L.wo, L.io, L.bo, Bc, d, d, 2};
+      o.resid = h->xc;
+      rc = run_lin(h, CAT_GEMM_OUT, o, s);
       if (rc) return rc;
-      { ProfScope ps(CAT_LN, s); rc = launch_layernorm_f16(h->xc, d, L.ln2g, L.ln2b, Bc, d, h->cabuf, lda_c, np == 2 ? d : 0, s); }
+      rc = ln(h->xc, L.ln2g, L.ln2b, Bc, h->cabuf);
       if (rc) return rc;
-      g = GemmLaunch{};
-      g.a = h->cabuf; g.lda = lda_c; g.w = L.w1; g.ldw = lda_c; g.bias = L.b1;
-      g.M = Bc; g.N = f; g.K = d; g.nseg = nseg; g.epi = 1; g.out = h->cfbuf; g.ldo = ldf_c; g.out_lo_off = np == 2 ? f : 0;
-      { ProfScope ps(CAT_GEMM_FC1, s); rc = launch_gemm(g, s); }
+      Lin f1{h->cabuf, ldd, S_LN, L.w1, L.i1, L.b1, Bc, f, d, 1};
+      f1.out = h->cfbuf; f1.out_fmt = afmt; f1.out_scale = S_GELU;
+      rc = run_lin(h, CAT_GEMM_FC1, f1, s);
       if (rc) return rc;
-      g = GemmLaunch{};
-      g.a = h->cfbuf; g.lda = ldf_c; g.w = L.w2; g.ldw = ldf_c; g.bias = L.b2;
-      g.M = Bc; g.N = d; g.K = f; g.nseg = nseg; g.epi = 2; g.resid = h->xc; g.ldr = d;
-      { ProfScope ps(CAT_GEMM_FC2, s); rc = launch_gemm(g, s); }
-      return rc;
+      Lin f2{h->cfbuf, ldf, S_GELU, L.w2, L.i2, L.b2, Bc, d, f, 2};
+      f2.resid = h->xc;
+      return run_lin(h, CAT_GEMM_FC2, f2, s);
     }
     AttnLaunch a{};
-    a.qkv = h->qkv; a.ld = static_cast<int64_t>(3 * d) * np; a.lo_off = np == 2 ? 3 * d : 0;
-    a.out = h->abuf; a.ldo = static_cast<int64_t>(d) * np; a.out_lo_off = np == 2 ? d : 0;
-    a.B = Bc; a.T = T; a.heads = D.heads; a.nseg = nseg; a.causal = 0; a.alibi_slopes = nullptr;
+    a.qkv = h->qkv; a.ld = ldq; a.lo_off = np == 2 ? 3 * d : 0;
+    a.out = h->abuf; a.ldo = ldd; a.out_lo_off = np == 2 ? d : 0; a.out_fmt = afmt; a.out_scale = S_ATT;
+    a.B = Bc; a.T = T; a.heads = D.heads; a.nseg = np == 2 ? 3 : 1; a.causal = 0; a.alibi_slopes = nullptr;
     { ProfScope ps(CAT_ATTN, s); rc = launch_attention_tc(a, s); }
     if (rc) return rc;
-    g = GemmLaunch{};
-    g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.wo; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.bo;
-    g.M = rows; g.N = d; g.K = d; g.nseg = nseg; g.epi = 2; g.resid = h->x; g.ldr = d;
-    { ProfScope ps(CAT_GEMM_OUT, s); rc = launch_gemm(g, s); }
+    Lin o{h->abuf, ldd, S_ATT, L.wo, L.io, L.bo, rows, d, d, 2};
+    o.resid = h->x;
+    rc = run_lin(h, CAT_GEMM_OUT, o, s);
     if (rc) return rc;
-    { ProfScope ps(CAT_LN, s); rc = launch_layernorm_f16(h->x, d, L.ln2g, L.ln2b, rows, d, h->abuf, static_cast<int64_t>(d) * np, np == 2 ? d : 0, s); }
+    rc = ln(h->x, L.ln2g, L.ln2b, rows, h->abuf);
     if (rc) return rc;
-    g = GemmLaunch{};
-    g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.w1; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.b1;
-    g.M = rows; g.N = f; g.K = d; g.nseg = nseg; g.epi = 1;
-    g.out = h->fbuf; g.ldo = static_cast<int64_t>(f) * np; g.out_lo_off = np == 2 ? f : 0;
-    { ProfScope ps(CAT_GEMM_FC1, s); rc = launch_gemm(g, s); }
+    Lin f1{h->abuf, ldd, S_LN, L.w1, L.i1, L.b1, rows, f, d, 1};
+    f1.out = h->fbuf; f1.out_fmt = afmt; f1.out_scale = S_GELU;
+    rc = run_lin(h, CAT_GEMM_FC1, f1, s);
     if (rc) return rc;
-    g = GemmLaunch{};
-    g.a = h->fbuf; g.lda = static_cast<int64_t>(f) * np; g.w = L.w2; g.ldw = static_cast<int64_t>(f) * np; g.bias = L.b2;
-    g.M = rows; g.N = d; g.K = f; g.nseg = nseg; g.epi = 2; g.resid = h->x; g.ldr = d;
-    { ProfScope ps(CAT_GEMM_FC2, s); rc = launch_gemm(g, s); }
+    Lin f2{h->fbuf, ldf, S_GELU, L.w2, L.i2, L.b2, rows, d, f, 2};
+    f2.resid = h->x;
+    rc = run_lin(h, CAT_GEMM_FC2, f2, s);
     if (rc) return rc;
   }
   return PG_OK;
@@ -248,49 +314,47 @@ int forward_rows(pg_handle h, const int32_t* tokens, int n_tokens, const int32_t
 // because pads sit to the right of every real token and attention is causal.
 int forward_tranception(pg_handle h, const int32_t* ids, int B, int T, cudaStream_t s) {
   const pg_model_desc& D = h->desc;
-  const int d = D.embed_dim, f = D.ffn_dim, np = h->np, nseg = (np == 2) ? 3 : 1;
+  const int d = D.embed_dim, f = D.ffn_dim, np = h->np;
+  const int afmt = h->nseg == 2 ? 2 : (np == 2 ? 1 : 0);
+  const int qfmt = np == 2 ? 1 : 0;
+  const int64_t ldd = static_cast<int64_t>(d) * np, ldf = static_cast<int64_t>(f) * np, ldq = static_cast<int64_t>(3 * d) * np;
   const int rows = B * T;
   int rc;
   { ProfScope ps(CAT_EMBED, s); rc = launch_gather_embed(ids, h->embed, rows, d, D.vocab, h->x, s); }
   if (rc) return rc;
+  auto ln = [&](const float* g, const float* b) {
+    ProfScope ps(CAT_LN, s);
+    return launch_layernorm_f16(h->x, d, g, b, rows, d, h->abuf, ldd, np == 2 ? d : 0, s, afmt, S_LN);
+  };
   for (int l = 0; l < D.layers; ++l) {
     const Layer& L = h->layers[l];
-    { ProfScope ps(CAT_LN, s); rc = launch_layernorm_f16(h->x, d, L.ln1g, L.ln1b, rows, d, h->abuf, static_cast<int64_t>(d) * np, np == 2 ? d : 0, s); }
+    rc = ln(L.ln1g, L.ln1b);
     if (rc) return rc;
-    GemmLaunch g{};
-    g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.wqkv; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.bqkv;
-    g.M = rows; g.N = 3 * d; g.K = d; g.nseg = nseg; g.epi = 0;
-    g.out = h->qkv; g.ldo = static_cast<int64_t>(3 * d) * np; g.out_lo_off = np == 2 ? 3 * d : 0;
-    { ProfScope ps(CAT_GEMM_QKV, s); rc = launch_gemm(g, s); }
+    Lin q{h->abuf, ldd, S_LN, L.wqkv, L.iqkv, L.bqkv, rows, 3 * d, d, 0};
+    q.out = h->qkv; q.out_fmt = qfmt;
+    rc = run_lin(h, CAT_GEMM_QKV, q, s);
     if (rc) return rc;
-    { ProfScope ps(CAT_OTHER, s); rc = launch_qkv_conv(h->qkv, h->qkv2, static_cast<int64_t>(3 * d) * np, np == 2 ? 3 * d : 0, B, T, D.heads, L.conv_taps, 0.125f, s); }
+    { ProfScope ps(CAT_OTHER, s); rc = launch_qkv_conv(h->qkv, h->qkv2, ldq, np == 2 ? 3 * d : 0, B, T, D.heads, L.conv_taps, 0.125f, s); }
     if (rc) return rc;
     AttnLaunch a{};
-    a.qkv = h->qkv2; a.ld = static_cast<int64_t>(3 * d) * np; a.lo_off = np == 2 ? 3 * d : 0;
-    a.out = h->abuf; a.ldo = static_cast<int64_t>(d) * np; a.out_lo_off = np == 2 ? d : 0;
-    a.B = B; a.T = T; a.heads = D.heads; a.nseg = nseg; a.causal = 1; a.alibi_slopes = h->slopes;
-    // causal + ALiBi: the mma.sync kernel is currently the faster of the two here (622 vs 837 ms on the L=512 bench, f16x3);
-    // the tcgen05 kernel's causal path is correct (tests) but its masked/biased softmax loop is instruction-bound.
-    { static const bool use_mma = getenv("PG_TRANCEPTION_ATTN_MMA") != nullptr;
-      ProfScope ps(CAT_ATTN, s); rc = use_mma ? launch_attention(a, s) : launch_attention_tc(a, s); }
+    a.qkv = h->qkv2; a.ld = ldq; a.lo_off = np == 2 ? 3 * d : 0;
+    a.out = h->abuf; a.ldo = ldd; a.out_lo_off = np == 2 ? d : 0; a.out_fmt = afmt; a.out_scale = S_ATT;
+    a.B = B; a.T = T; a.heads = D.heads; a.nseg = np == 2 ? 3 : 1; a.causal = 1; a.alibi_slopes = h->slopes;
+    { ProfScope ps(CAT_ATTN, s); rc = launch_attention_tc(a, s); }
     if (rc) return rc;
-    g = GemmLaunch{};
-    g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.wo; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.bo;
-    g.M = rows; g.N = d; g.K = d; g.nseg = nseg; g.epi = 2; g.resid = h->x; g.ldr = d;
-    { ProfScope ps(CAT_GEMM_OUT, s); rc = launch_gemm(g, s); }
+    Lin o{h->abuf, ldd, S_ATT, L.wo, L.io, L.bo, rows, d, d, 2};
+    o.resid = h->x;
+    rc = run_lin(h, CAT_GEMM_OUT, o, s);
     if (rc) return rc;
-    { ProfScope ps(CAT_LN, s); rc = launch_layernorm_f16(h->x, d, L.ln2g, L.ln2b, rows, d, h->abuf, static_cast<int64_t>(d) * np, np == 2 ? d : 0, s); }
+    rc = ln(L.ln2g, L.ln2b);
     if (rc) return rc;
-    g = GemmLaunch{};
-    g.a = h->abuf; g.lda = static_cast<int64_t>(d) * np; g.w = L.w1; g.ldw = static_cast<int64_t>(d) * np; g.bias = L.b1;
-    g.M = rows; g.N = f; g.K = d; g.nseg = nseg; g.epi = 4;
-    g.out = h->fbuf; g.ldo = static_cast<int64_t>(f) * np; g.out_lo_off = np == 2 ? f : 0;
-    { ProfScope ps(CAT_GEMM_FC1, s); rc = launch_gemm(g, s); }
+    Lin f1{h->abuf, ldd, S_LN, L.w1, L.i1, L.b1, rows, f, d, 4};
+    f1.out = h->fbuf; f1.out_fmt = afmt; f1.out_scale = S_RELU2;
+    rc = run_lin(h, CAT_GEMM_FC1, f1, s);
     if (rc) return rc;
-    g = GemmLaunch{};
-    g.a = h->fbuf; g.lda = static_cast<int64_t>(f) * np; g.w = L.w2; g.ldw = static_cast<int64_t>(f) * np; g.bias = L.b2;
-    g.M = rows; g.N = d; g.K = f; g.nseg = nseg; g.epi = 2; g.resid = h->x; g.ldr = d;
-    { ProfScope ps(CAT_GEMM_FC2, s); rc = launch_gemm(g, s); }
+    Lin f2{h->fbuf, ldf, S_RELU2, L.w2, L.i2, L.b2, rows, d, f, 2};
+    f2.resid = h->x;
+    rc = run_lin(h, CAT_GEMM_FC2, f2, s);
     if (rc) return rc;
   }
   return PG_OK;
@@ -312,7 +376,7 @@ using namespace pg;
 
 extern "C" {
 
-int pg_abi_version(void) { return 2; }
+int pg_abi_version(void) { return 3; }
 
 long long pg_launch_count(void) {
   std::lock_guard<std::mutex> lk(prof_mu());
@@ -359,7 +423,8 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
   if (D.embed_dim % 64 || D.ffn_dim % 64) return set_error(PG_ERR_UNSUPPORTED, "pg_create: embed_dim and ffn_dim must be multiples of 64");
   if (D.arch != PG_ARCH_ESM1B && D.arch != PG_ARCH_ESM2 && D.arch != PG_ARCH_TRANCEPTION) return set_error(PG_ERR_UNSUPPORTED, "pg_create: unknown arch");
   if (D.arch == PG_ARCH_TRANCEPTION && D.heads % 4) return set_error(PG_ERR_UNSUPPORTED, "pg_create: Tranception needs heads % 4 == 0 (model_pytorch.py:129-131)");
-  if (D.precision != PG_PREC_F16 && D.precision != PG_PREC_F16X3) return set_error(PG_ERR_ARG, "pg_create: unknown precision");
+  if (D.precision != PG_PREC_F16 && D.precision != PG_PREC_F16X3 && D.precision != PG_PREC_F16F8)
+    return set_error(PG_ERR_ARG, "pg_create: unknown precision");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return set_error(PG_ERR_CUDA, "pg_create: no CUDA device (the B200 path has no CPU fallback)");
   if (D.device < 0 || D.device >= ndev) return set_error(PG_ERR_ARG, "pg_create: bad device ordinal");
@@ -369,7 +434,8 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
   if (prop.major != 10) return set_error(PG_ERR_UNSUPPORTED, "pg_create: device is not sm_100 (tcgen05/TMEM required)");
   pg_handle h = new pg_handle_s();
   h->desc = D;
-  h->np = (D.precision == PG_PREC_F16X3) ? 2 : 1;
+  h->np = (D.precision == PG_PREC_F16) ? 1 : 2;
+  h->nseg = (D.precision == PG_PREC_F16) ? 1 : (D.precision == PG_PREC_F16X3 ? 3 : 2);
   h->max_rows = D.max_rows > 0 ? D.max_rows : 131072;
   h->head_cap = 8192;
   const int d = D.embed_dim, f = D.ffn_dim, np = h->np;
@@ -381,6 +447,7 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
     A(&L.w1, static_cast<size_t>(f) * d * np); A(&L.w2, static_cast<size_t>(d) * f * np);
     A(&L.bqkv, 3 * d); A(&L.bo, d); A(&L.b1, f); A(&L.b2, d);
     A(&L.ln1g, d); A(&L.ln1b, d); A(&L.ln2g, d); A(&L.ln2b, d);
+    if (h->nseg == 2) { A(&L.iqkv, 3 * d); A(&L.io, d); A(&L.i1, f); A(&L.i2, d); }
     if (D.arch == PG_ARCH_TRANCEPTION) A(&L.conv_taps, 3 * 4 * 64 * 8);
   }
   if (D.arch == PG_ARCH_TRANCEPTION) {
@@ -437,28 +504,32 @@ int pg_load_weights(pg_handle h, const pg_tensor* tensors, int32_t n) {
     if (!src) return;
     scale_copy_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256>>>(src, dst, static_cast<int>(cnt), scale);
   };
-  auto pack = [&](__half* dst, const float* src, int N, int K, float scale = 1.f) {
+  const bool f8 = h->nseg == 2;
+  // inv: where the per-row 1/t_n of this matrix go (PG_PREC_F16F8 only)
+  auto pack = [&](__half* dst, float* inv, const float* src, int N, int K, float scale = 1.f) {
     if (!src) return;
     const long long tot = static_cast<long long>(N) * K;
-    pack_weight_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256>>>(src, N, K, scale, dst, np);
+    if (f8) pack_weight_f8_kernel<<<(N + 7) / 8, 256>>>(src, N, K, K, 1, scale, dst, inv);
+    else pack_weight_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256>>>(src, N, K, scale, dst, np);
   };
-  auto pack_t = [&](__half* dst, const float* src, int N, int K) {
+  auto pack_t = [&](__half* dst, float* inv, const float* src, int N, int K) {
     if (!src) return;
     const long long tot = static_cast<long long>(N) * K;
-    pack_weight_t_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256>>>(src, N, K, dst, np);
+    if (f8) pack_weight_f8_kernel<<<(N + 7) / 8, 256>>>(src, N, K, 1, N, 1.f, dst, inv);
+    else pack_weight_t_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256>>>(src, N, K, dst, np);
   };
   if (D.arch == PG_ARCH_TRANCEPTION) {
     // HF GPT2-style names with the "transformer." prefix stripped by the host; Conv1D weights are [in, out].
     for (int l = 0; l < D.layers; ++l) {
       Layer& L = h->layers[l];
       const std::string p = "h." + std::to_string(l) + ".";
-      pack_t(L.wqkv, get(p + "attn.c_attn.weight", d, 3 * d), 3 * d, d);
+      pack_t(L.wqkv, L.iqkv, get(p + "attn.c_attn.weight", d, 3 * d), 3 * d, d);
       copy(L.bqkv, get(p + "attn.c_attn.bias", 3 * d, 1), 3 * d);
-      pack_t(L.wo, get(p + "attn.c_proj.weight", d, d), d, d);
+      pack_t(L.wo, L.io, get(p + "attn.c_proj.weight", d, d), d, d);
       copy(L.bo, get(p + "attn.c_proj.bias", d, 1), d);
-      pack_t(L.w1, get(p + "mlp.c_fc.weight", d, f), f, d);
+      pack_t(L.w1, L.i1, get(p + "mlp.c_fc.weight", d, f), f, d);
       copy(L.b1, get(p + "mlp.c_fc.bias", f, 1), f);
-      pack_t(L.w2, get(p + "mlp.c_proj.weight", f, d), d, f);
+      pack_t(L.w2, L.i2, get(p + "mlp.c_proj.weight", f, d), d, f);
       copy(L.b2, get(p + "mlp.c_proj.bias", d, 1), d);
       copy(L.ln1g, get(p + "ln_1.weight", d, 1), d);
       copy(L.ln1b, get(p + "ln_1.bias", d, 1), d);
@@ -481,17 +552,17 @@ int pg_load_weights(pg_handle h, const pg_tensor* tensors, int32_t n) {
     Layer& L = h->layers[l];
     const std::string p = "layers." + std::to_string(l) + ".";
     const size_t dd = static_cast<size_t>(d) * d * np;
-    pack(L.wqkv, get(p + "self_attn.q_proj.weight", d, d), d, d, qscale);
-    pack(L.wqkv + dd, get(p + "self_attn.k_proj.weight", d, d), d, d);
-    pack(L.wqkv + 2 * dd, get(p + "self_attn.v_proj.weight", d, d), d, d);
+    pack(L.wqkv, L.iqkv, get(p + "self_attn.q_proj.weight", d, d), d, d, qscale);
+    pack(L.wqkv + dd, f8 ? L.iqkv + d : nullptr, get(p + "self_attn.k_proj.weight", d, d), d, d);
+    pack(L.wqkv + 2 * dd, f8 ? L.iqkv + 2 * d : nullptr, get(p + "self_attn.v_proj.weight", d, d), d, d);
     copy(L.bqkv, get(p + "self_attn.q_proj.bias", d, 1), d, qscale);
     copy(L.bqkv + d, get(p + "self_attn.k_proj.bias", d, 1), d);
     copy(L.bqkv + 2 * d, get(p + "self_attn.v_proj.bias", d, 1), d);
-    pack(L.wo, get(p + "self_attn.out_proj.weight", d, d), d, d);
+    pack(L.wo, L.io, get(p + "self_attn.out_proj.weight", d, d), d, d);
     copy(L.bo, get(p + "self_attn.out_proj.bias", d, 1), d);
-    pack(L.w1, get(p + "fc1.weight", f, d), f, d);
+    pack(L.w1, L.i1, get(p + "fc1.weight", f, d), f, d);
     copy(L.b1, get(p + "fc1.bias", f, 1), f);
-    pack(L.w2, get(p + "fc2.weight", d, f), d, f);
+    pack(L.w2, L.i2, get(p + "fc2.weight", d, f), d, f);
     copy(L.b2, get(p + "fc2.bias", d, 1), d);
     copy(L.ln1g, get(p + "self_attn_layer_norm.weight", d, 1), d);
     copy(L.ln1b, get(p + "self_attn_layer_norm.bias", d, 1), d);
@@ -655,14 +726,33 @@ int pg_gemm(const pg_gemm_args* a, pg_stream stream) {
   g.out = static_cast<__half*>(a->out_h); g.ldo = a->ldo; g.out_lo_off = a->out_lo_off;
   g.resid = a->resid; g.ldr = a->ldr;
   g.rot_cos = a->rot_cos; g.rot_sin = a->rot_sin; g.rot_T = a->rot_T; g.rot_dim = a->rot_dim;
+  g.a_scale = a->a_scale; g.w_inv = a->w_inv; g.out_scale = a->out_scale;
+  g.out_fmt = a->out_fmt ? a->out_fmt : (a->out_lo_off > 0 ? 1 : 0);
   ProfScope ps(CAT_OTHER, static_cast<cudaStream_t>(stream));
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 
 int pg_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int32_t rows, int32_t d, void* out,
-                     int64_t ldo, int64_t lo_off, pg_stream stream) {
+                     int64_t ldo, int64_t lo_off, int32_t fmt, float scale, pg_stream stream) {
   if (!x || !gamma || !beta || !out) return set_error(PG_ERR_ARG, "pg_layernorm_f16: null buffer");
-  return launch_layernorm_f16(x, ldx, gamma, beta, rows, d, static_cast<__half*>(out), ldo, lo_off, static_cast<cudaStream_t>(stream));
+  return launch_layernorm_f16(x, ldx, gamma, beta, rows, d, static_cast<__half*>(out), ldo, lo_off, static_cast<cudaStream_t>(stream),
+                              fmt ? fmt : -1, scale);
+}
+
+int pg_pack_weight(const float* w, int32_t N, int32_t K, int32_t fmt, void* out, float* w_inv, pg_stream stream) {
+  if (!w || !out || N <= 0 || K <= 0) return set_error(PG_ERR_ARG, "pg_pack_weight: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long tot = static_cast<long long>(N) * K;
+  if (fmt == 2) {
+    if (!w_inv) return set_error(PG_ERR_ARG, "pg_pack_weight: fmt 2 needs w_inv[N]");
+    pack_weight_f8_kernel<<<(N + 7) / 8, 256, 0, s>>>(w, N, K, K, 1, 1.f, static_cast<__half*>(out), w_inv);
+  } else if (fmt == 0 || fmt == 1) {
+    pack_weight_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(w, N, K, 1.f, static_cast<__half*>(out), fmt + 1);
+  } else {
+    return set_error(PG_ERR_ARG, "pg_pack_weight: fmt must be 0, 1 or 2");
+  }
+  PG_CUDA_OK(cudaGetLastError());
+  return PG_OK;
 }
 
 int pg_attention(const pg_attn_args* a, pg_stream stream) {
@@ -671,11 +761,11 @@ int pg_attention(const pg_attn_args* a, pg_stream stream) {
   l.qkv = static_cast<const __half*>(a->qkv); l.ld = a->ld; l.lo_off = a->lo_off;
   l.out = static_cast<__half*>(a->out); l.ldo = a->ldo; l.out_lo_off = a->out_lo_off;
   l.B = a->B; l.T = a->T; l.heads = a->heads; l.nseg = a->nseg; l.causal = a->causal; l.alibi_slopes = a->alibi_slopes;
+  l.out_fmt = a->out_fmt ? a->out_fmt : -1; l.out_scale = a->out_scale;
   ProfScope ps(CAT_OTHER, static_cast<cudaStream_t>(stream));
-  if (a->impl == 3) return launch_attention_tc2(l, static_cast<cudaStream_t>(stream));
-  if (a->impl == 4) return launch_attention_tc3(l, static_cast<cudaStream_t>(stream));
-  if (a->impl == 0) return launch_attention_tc(l, static_cast<cudaStream_t>(stream));   // the model's default dispatch
-  if (a->impl == 2) return launch_attention_tc_own(l, static_cast<cudaStream_t>(stream));
+  if (a->impl == 0) return launch_attention_tc(l, static_cast<cudaStream_t>(stream));   // the model's kernel (tcgen05)
+  if (a->impl != 1) return set_error(PG_ERR_ARG, "pg_attention: impl must be 0 (tcgen05, the model's kernel) or 1 (mma.sync cross-check)");
+  if (l.out_fmt == 2) return set_error(PG_ERR_UNSUPPORTED, "pg_attention: the mma.sync cross-check kernel writes fp16 planes only");
   return launch_attention(l, static_cast<cudaStream_t>(stream));
 }
 

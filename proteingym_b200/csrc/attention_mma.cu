@@ -219,10 +219,12 @@ int launch_attention(const AttnLaunch& a, cudaStream_t s) {
     attn_mma_kernel<1><<<grid, 128, smem, s>>>(a);
   } else {
     const int smem = 10 * TILE_BYTES;
-    static bool set = false;
-    if (!set) {
+    int dev = 0;
+    PG_CUDA_OK(cudaGetDevice(&dev));
+    static bool set[64] = {};  // the attribute is per device
+    if (dev < 64 && !set[dev]) {
       PG_CUDA_OK(cudaFuncSetAttribute(attn_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      set = true;
+      set[dev] = true;
     }
     attn_mma_kernel<3><<<grid, 128, smem, s>>>(a);
   }

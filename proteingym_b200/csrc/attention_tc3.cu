@@ -1,6 +1,6 @@
-// K4 (v4) — tcgen05/TMEM attention, head_dim 64, with P written IN PLACE over the S tile it was computed from.
-// Same arithmetic as attention_tc.cu (single-pass online softmax with lazy rescaling, optional causal + ALiBi, NP = 2 runs the
-// hi/lo three-product scheme); what changes is the TMEM plan and therefore the synchronisation per key block:
+// K4 — tcgen05/TMEM attention, head_dim 64, with P written IN PLACE over the S tile it was computed from.
+// Single-pass online softmax with lazy rescaling, optional causal + ALiBi; NP = 2 runs the hi/lo three-product scheme.
+// TMEM plan and synchronisation per key block:
 //
 //   TMEM columns   [0,128) [128,256) [256,384)  a ring of three 128x128 fp32 S tiles;   [384,448) the 128x64 fp32 O accumulator.
 //   P(j) = exp2(S(j) - m) is stored as packed fp16 pairs into the SAME 128 columns S(j) occupied (hi pairs in the first 64 columns,
@@ -13,7 +13,7 @@
 //     softmax writes P(n)  <- each thread first loaded its own 64 S columns; the columns it overwrites that belong to the row's
 //                             other thread are touched only after the pair barrier both threads pass after their loads
 //     PV(n)  reads P(n)    <- after p_full[b]
-//   Compared with attention_tc.cu there is no wait for "previous PV finished, P buffer free" (the largest per-block stall in its
+//   Compared with round 1's first tcgen05 kernel (P in its own TMEM columns) there is no wait for "previous PV finished, P buffer free" (the largest per-block stall in its
 //   ncu profile, profiles/ncu_r01_attention_ptmem_summary.txt) and no s_empty hand-back; the softmax warps wait for a finished PV
 //   only on the rare blocks that rescale O (pv_done), and in the epilogue (o_full).
 //   MMA issue order per work item:  QK0 QK1 QK2 | PV0 QK3 | PV1 QK4 | ...   TMA load order: K0 K1 K2 | V0 K3 | V1 K4 | ...
@@ -48,6 +48,7 @@ struct Attn3Params {
   __half* out; long long ldo; long long out_lo_off;
   int causal;
   const float* alibi_slopes;
+  int out_fmt; float out_scale;  // common.h operand formats: 1 = fp16 lo plane, 2 = e4m3 [lo8 | hi8] planes for the out_proj GEMM
 };
 
 __device__ __forceinline__ float ex2a3(float x) {
@@ -366,20 +367,41 @@ __global__ void __launch_bounds__(384, 1) attn_tc3_kernel(const __grid_constant_
         const float rl = 1.f / l;
         __half* orow = p.out + (static_cast<long long>(b) * p.T + qidx) * p.ldo + h * 64 + g * 32;
         uint32_t hi[16], lo[16];
+        float lf[32];
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const float x0 = __uint_as_float(o[2 * u]) * rl, x1 = __uint_as_float(o[2 * u + 1]) * rl;
           hi[u] = cvt2h(x0, x1);
           const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
-          lo[u] = cvt2h(x0 - hf.x, x1 - hf.y);
+          lf[2 * u] = x0 - hf.x;
+          lf[2 * u + 1] = x1 - hf.y;
+          lo[u] = cvt2h(lf[2 * u], lf[2 * u + 1]);
         }
         uint4* d4 = reinterpret_cast<uint4*>(orow);
 #pragma unroll
         for (int u = 0; u < 4; ++u) d4[u] = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
-        if (p.out_lo_off > 0) {
+        if (p.out_fmt == 1) {
           uint4* l4 = reinterpret_cast<uint4*>(orow + p.out_lo_off);
 #pragma unroll
           for (int u = 0; u < 4; ++u) l4[u] = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+        } else if (p.out_fmt == 2) {
+          uint8_t* f8 = reinterpret_cast<uint8_t*>(p.out + (static_cast<long long>(b) * p.T + qidx) * p.ldo + p.out_lo_off) + h * 64 + g * 32;
+          const float sh = p.out_scale, sl = p.out_scale * 2048.f;
+          uint32_t w8l[8], w8h[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&hi[2 * u]));
+            const float2 h23 = __half22float2(*reinterpret_cast<const __half2*>(&hi[2 * u + 1]));
+            w8h[u] = pack4_e4m3(h01.x * sh, h01.y * sh, h23.x * sh, h23.y * sh);
+            w8l[u] = pack4_e4m3(lf[4 * u] * sl, lf[4 * u + 1] * sl, lf[4 * u + 2] * sl, lf[4 * u + 3] * sl);
+          }
+          uint4* l4 = reinterpret_cast<uint4*>(f8);
+          uint4* h4 = reinterpret_cast<uint4*>(f8 + p.d);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            l4[u] = make_uint4(w8l[4 * u], w8l[4 * u + 1], w8l[4 * u + 2], w8l[4 * u + 3]);
+            h4[u] = make_uint4(w8h[4 * u], w8h[4 * u + 1], w8h[4 * u + 2], w8h[4 * u + 3]);
+          }
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // red[] / redh[] are rewritten by the next item
@@ -404,6 +426,10 @@ int launch_attention_tc3(const AttnLaunch& a, cudaStream_t s) {
   p.nqt = (a.T + QT - 1) / QT; p.nkb = (a.T + KT - 1) / KT;
   p.lo_off = a.lo_off; p.out = a.out; p.ldo = a.ldo; p.out_lo_off = a.out_lo_off;
   p.causal = a.causal; p.alibi_slopes = a.alibi_slopes;
+  p.out_fmt = a.out_fmt < 0 ? (a.out_lo_off > 0 ? 1 : 0) : a.out_fmt;
+  p.out_scale = a.out_scale;
+  if (p.out_fmt > 2 || (p.out_fmt >= 1 && a.out_lo_off <= 0) || (p.out_fmt == 2 && !(a.out_scale > 0.f)))
+    return set_error(PG_ERR_ARG, "attention_tc3: bad output format");
   const int np = a.nseg == 3 ? 2 : 1;
   const uint64_t width = static_cast<uint64_t>(3) * p.d * np;
   if (np == 2 && a.lo_off != 3ll * p.d) return set_error(PG_ERR_ARG, "attention_tc3: lo planes must follow the hi planes (lo_off == 3*d)");
@@ -412,11 +438,13 @@ int launch_attention_tc3(const AttnLaunch& a, cudaStream_t s) {
   if (rc) return rc;
   const long long nitems = static_cast<long long>(a.B) * a.heads * p.nqt;
   const int grid = nitems < num_sms() ? static_cast<int>(nitems) : num_sms();
-  static bool attr_set = false;
-  if (!attr_set) {
+  int dev = 0;
+  PG_CUDA_OK(cudaGetDevice(&dev));
+  static bool attr_set[64] = {};
+  if (dev < 64 && !attr_set[dev]) {
     PG_CUDA_OK(cudaFuncSetAttribute(attn_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem3<1>::TOTAL));
     PG_CUDA_OK(cudaFuncSetAttribute(attn_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem3<2>::TOTAL));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   if (np == 1) attn_tc3_kernel<1><<<grid, 384, Smem3<1>::TOTAL, s>>>(tm, p);
   else attn_tc3_kernel<2><<<grid, 384, Smem3<2>::TOTAL, s>>>(tm, p);

@@ -33,19 +33,30 @@ struct ProfScope {  // records an event pair around the launches issued in its l
 };
 
 // ---- kernel launchers (each returns a pg_status) ----
+// Operand row formats (pitches in fp16 elements; a "plane" is a column block of the row):
+//   fmt 0  [hi fp16 (n)]
+//   fmt 1  [hi fp16 (n) | lo fp16 (n)]                     lo at element offset lo_off
+//   fmt 2  [hi fp16 (n) | lo8 (n bytes) | hi8 (n bytes)]   e4m3 planes start at element offset lo_off (= byte 2*lo_off);
+//          lo8 = e4m3(lo * 2^11 * s), hi8 = e4m3(hi * s) with the power-of-two scale s of the consuming GEMM (gemm_tc.cu).
+//          Weights use [hi fp16 | hi8 | lo8] with a per-row scale instead (api.cu pack_weight_f8_kernel).
 struct GemmLaunch {
   const void* a; int64_t lda;
   const void* w; int64_t ldw;
   const float* bias;
-  int M, N, K, nseg, epi;
+  int M, N, K, nseg, epi;   // nseg: 1 fp16, 3 fp16 hi/lo x3, 2 fp16 hi*hi + e4m3 cross terms (a in fmt 2, w in weight fmt 2)
   __half* out; int64_t ldo; int64_t out_lo_off;
   float* resid; int64_t ldr;
   const float* rot_cos; const float* rot_sin; int rot_T; int rot_dim;
+  float a_scale = 0.f;            // nseg 2: s used by the producer of a's e4m3 planes
+  const float* w_inv = nullptr;   // nseg 2: [N] 1 / t_n of the weight rows
+  int out_fmt = 0;                // epi != 2: 0, 1 or 2 (see above); planes at out_lo_off
+  float out_scale = 0.f;          // out_fmt 2: s of the GEMM that will consume `out`
 };
 int launch_gemm(const GemmLaunch& g, cudaStream_t s);
 
+// fmt / scale as above (fmt 0 when lo_off == 0).
 int launch_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int rows, int d, __half* out,
-                         int64_t ldo, int64_t lo_off, cudaStream_t s);
+                         int64_t ldo, int64_t lo_off, cudaStream_t s, int fmt = -1, float scale = 0.f);
 
 struct AttnLaunch {
   const __half* qkv; int64_t ld; int64_t lo_off;
@@ -53,6 +64,8 @@ struct AttnLaunch {
   int B, T, heads, nseg, causal;
   const float* alibi_slopes;
   int q_begin = 0;  // first query row handled by this launch (mma.sync kernel only): rows [q_begin, T)
+  int out_fmt = -1;        // -1: 1 if out_lo_off > 0 else 0; 2: e4m3 planes with out_scale (tcgen05 kernel only)
+  float out_scale = 0.f;
 };
 int launch_attention(const AttnLaunch& a, cudaStream_t s);
 
@@ -95,15 +108,16 @@ namespace pg {
 // 2D fp16 row-major tensor map [rows, cols] (pitch ld elements), box [box_rows, box_cols], SWIZZLE_128B, OOB -> 0.
 int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                      uint32_t box_cols);
-int launch_attention_tc(const AttnLaunch& a, cudaStream_t s);      // tcgen05/TMEM attention: the model's dispatch (default attention_tc3.cu)
-int launch_attention_tc_own(const AttnLaunch& a, cudaStream_t s);  // attention_tc.cu's kernel (P in its own TMEM columns)
-int launch_attention_tc2(const AttnLaunch& a, cudaStream_t s);  // two query tiles in flight per CTA (attention_tc2.cu)
-int launch_attention_tc3(const AttnLaunch& a, cudaStream_t s);  // P stored in place over S, three-slot TMEM ring (attention_tc3.cu)
+// General form: elem_bytes 2 (fp16) / 4 (fp32) / 1 (bytes), swizzle 128 or 64 bytes. Encoded maps are cached per host thread.
+int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
+                 int elem_bytes, int swizzle);
+int launch_attention_tc3(const AttnLaunch& a, cudaStream_t s);  // tcgen05/TMEM attention (attention_tc3.cu): the model's kernel
+inline int launch_attention_tc(const AttnLaunch& a, cudaStream_t s) { return launch_attention_tc3(a, s); }
 }  // namespace pg
 
 namespace pg {
 int launch_attn_single_query(const __half* qkv, int64_t ld, int64_t lo_off, const int32_t* row_sel, int B, int T, int heads,
-                             __half* out, int64_t ldo, int64_t out_lo_off, cudaStream_t s);
+                             __half* out, int64_t ldo, int64_t out_lo_off, cudaStream_t s, int out_fmt = -1, float out_scale = 0.f);
 int launch_gather_rows(const float* x, const int32_t* row_sel, int B, int T, int d, float* xc, cudaStream_t s);
 int launch_gather_embed(const int32_t* ids, const float* wte, long long rows, int d, int vocab, float* x, cudaStream_t s);
 int launch_qkv_conv(const __half* in, __half* out, int64_t ld, int64_t lo_off, int B, int T, int heads, const float* taps,

@@ -40,7 +40,7 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 template <int MAXV>  // float4 vectors per lane; d <= MAXV*128
 __global__ void layernorm_f16_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, int rows, int d, __half* __restrict__ out,
-                                     long long ldo, long long lo_off) {
+                                     long long ldo, long long lo_off, int fmt, float scale) {
   const int warps_per_block = blockDim.x >> 5;
   const long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -81,7 +81,17 @@ __global__ void layernorm_f16_kernel(const float* __restrict__ x, long long ldx,
 #pragma unroll
       for (int j = 0; j < 4; ++j) split_hi_lo(y[j], h[j], l[j]);
       *reinterpret_cast<uint2*>(orow + idx * 4) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
-      if (lo_off > 0) *reinterpret_cast<uint2*>(orow + lo_off + idx * 4) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+      if (fmt == 1) {
+        *reinterpret_cast<uint2*>(orow + lo_off + idx * 4) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+      } else if (fmt == 2) {  // e4m3 planes [lo8 (d bytes) | hi8 (d bytes)] for the fp8 cross terms of the next GEMM
+        uint8_t* f8 = reinterpret_cast<uint8_t*>(orow + lo_off);
+        const float sl = scale * 2048.f;
+        *reinterpret_cast<uint32_t*>(f8 + idx * 4) =
+            pack4_e4m3((y[0] - __half2float(h[0])) * sl, (y[1] - __half2float(h[1])) * sl, (y[2] - __half2float(h[2])) * sl,
+                       (y[3] - __half2float(h[3])) * sl);
+        *reinterpret_cast<uint32_t*>(f8 + d + idx * 4) =
+            pack4_e4m3(__half2float(h[0]) * scale, __half2float(h[1]) * scale, __half2float(h[2]) * scale, __half2float(h[3]) * scale);
+      }
     }
   }
 }
@@ -252,7 +262,8 @@ __global__ void score_kernel(const float* __restrict__ table, int n_rows, int vo
 // from all rows. One warp per (sequence, head); fp32 SIMT arithmetic on the fp16 hi(+lo) q/k/v.
 __global__ void __launch_bounds__(128) attn_single_query_kernel(const __half* __restrict__ qkv, long long ld, long long lo_off,
                                                                 const int32_t* __restrict__ row_sel, int B, int T, int heads,
-                                                                __half* __restrict__ out, long long ldo, long long out_lo_off) {
+                                                                __half* __restrict__ out, long long ldo, long long out_lo_off,
+                                                                int out_fmt, float out_scale) {
   const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (wid >= B * heads) return;
   const int b = wid / heads, h = wid % heads, lane = threadIdx.x & 31;
@@ -310,7 +321,14 @@ __global__ void __launch_bounds__(128) attn_single_query_kernel(const __half* __
       __half hi, lo;
       split_hi_lo(v, hi, lo);
       orow[i] = hi;
-      if (out_lo_off > 0) orow[out_lo_off + i] = lo;
+      if (out_fmt == 1) {
+        orow[out_lo_off + i] = lo;
+      } else if (out_fmt == 2) {  // e4m3 planes [lo8 (d) | hi8 (d)] of the row, head h at byte h*64 of each plane
+        uint8_t* f8 = reinterpret_cast<uint8_t*>(out + static_cast<long long>(b) * ldo + out_lo_off);
+        const float hf = __half2float(hi);
+        f8[h * 64 + i] = static_cast<uint8_t>(cvt_e4m3x2((v - hf) * out_scale * 2048.f, 0.f) & 0xff);
+        f8[d + h * 64 + i] = static_cast<uint8_t>(cvt_e4m3x2(hf * out_scale, 0.f) & 0xff);
+      }
     }
   }
 }
@@ -326,9 +344,11 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, const int32_t* _
 }  // namespace
 
 int launch_attn_single_query(const __half* qkv, int64_t ld, int64_t lo_off, const int32_t* row_sel, int B, int T, int heads,
-                             __half* out, int64_t ldo, int64_t out_lo_off, cudaStream_t s) {
+                             __half* out, int64_t ldo, int64_t out_lo_off, cudaStream_t s, int out_fmt, float out_scale) {
   if (B <= 0) return PG_OK;
-  attn_single_query_kernel<<<(B * heads + 3) / 4, 128, 0, s>>>(qkv, ld, lo_off, row_sel, B, T, heads, out, ldo, out_lo_off);
+  if (out_fmt < 0) out_fmt = out_lo_off > 0 ? 1 : 0;
+  attn_single_query_kernel<<<(B * heads + 3) / 4, 128, 0, s>>>(qkv, ld, lo_off, row_sel, B, T, heads, out, ldo, out_lo_off, out_fmt,
+                                                              out_scale);
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;
 }
@@ -341,15 +361,17 @@ int launch_gather_rows(const float* x, const int32_t* row_sel, int B, int T, int
 }
 
 int launch_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int rows, int d, __half* out,
-                         int64_t ldo, int64_t lo_off, cudaStream_t s) {
+                         int64_t ldo, int64_t lo_off, cudaStream_t s, int fmt, float scale) {
   if (rows <= 0) return PG_OK;
   if (d % 4 || ldx % 4 || ldo % 4 || lo_off % 4) return set_error(PG_ERR_ARG, "layernorm: d and pitches must be multiples of 4");
+  if (fmt < 0) fmt = lo_off > 0 ? 1 : 0;
+  if (fmt > 2 || (fmt >= 1 && lo_off <= 0) || (fmt == 2 && !(scale > 0.f))) return set_error(PG_ERR_ARG, "layernorm: bad output format");
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
-  if (d <= 128 * 4) layernorm_f16_kernel<4><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off);
-  else if (d <= 128 * 10) layernorm_f16_kernel<10><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off);
-  else if (d <= 128 * 20) layernorm_f16_kernel<20><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off);
-  else if (d <= 128 * 40) layernorm_f16_kernel<40><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off);
+  if (d <= 128 * 4) layernorm_f16_kernel<4><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale);
+  else if (d <= 128 * 10) layernorm_f16_kernel<10><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale);
+  else if (d <= 128 * 20) layernorm_f16_kernel<20><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale);
+  else if (d <= 128 * 40) layernorm_f16_kernel<40><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale);
   else return set_error(PG_ERR_UNSUPPORTED, "layernorm: d > 5120");
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;

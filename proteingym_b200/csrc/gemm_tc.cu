@@ -1,20 +1,38 @@
 // K3 — tcgen05/TMA GEMM with fused epilogues for the linear layers of the ESM / Tranception forward
 // (reference ops: esm/multihead_attention.py:243-261,395; esm/modules.py:138-140).
 //
-//   C[M,N] = epilogue( A[M,K] * W[N,K]^T + bias )        A, W fp16 K-major (row-major), fp32 accumulate in TMEM.
+//   C[M,N] = epilogue( A[M,K] * W[N,K]^T + bias )        A, W K-major (row-major), fp32 accumulate in TMEM.
 //
-// Precision: the reference is fp32. With nseg == 3 each operand is an fp16 (hi | lo) pair stored as two column blocks
-// and the K loop runs three segments  hi*hi + lo*hi + hi*lo  into the same TMEM accumulator (~22-bit operands).
+// Precision (the reference is fp32). Every operand x is an fp16 pair hi = rn(x), lo = rn(x - hi). Three operand modes:
+//   nseg 1  single pass            hi*hi                                                     (fast mode, ~1e-2 on scores)
+//   nseg 3  fp16 x3                hi*hi + lo*hi + hi*lo, all kind::f16                      (3 tensor-pipe units)
+//   nseg 2  fp16 + fp8 cross terms hi*hi (kind::f16) + [lo8 | hi8] * [hi8 | lo8]^T (kind::f8f6f4, e4m3, K-concatenated, 2x rate)
+//           with lo8 = e4m3(lo * 2^11 * s), hi8 = e4m3(hi * s): s = a fixed power of two on the A side (applied by the producing
+//           kernel), a per-row power of two t_n on the W side (chosen at load time); the epilogue rescales by 1/(2^11 s t_n).
+//           2 tensor-pipe units; emulated on CPU at true ESM-1v size: 3.0e-4 max score error (scripts/precision_f8.py).
+//
+// Accumulation: tcgen05.mma adds into its fp32 TMEM accumulator with truncation, a bias that grows with the number of
+// accumulation steps (DESIGN.md "hardware finding"). The K loop is therefore cut into CHUNKS: each chunk accumulates into one of
+// the two TMEM buffers from zero, and the epilogue warps add the chunks in registers in round-to-nearest fp32 (fixed order, so
+// results stay deterministic). The small-magnitude cross terms form chunk 0 (their own truncation is irrelevant), the hi*hi
+// product is split into pieces of <= kchunk (default 1024) along K. The same double-buffered TMEM that used to overlap the
+// epilogue of tile i with the MMAs of tile i+1 now also overlaps the read-out of chunk c with the MMAs of chunk c+1.
 //
 // Structure (one persistent CTA per SM, 384 threads, no clusters):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (128x64 of A, 256x64 of W, 128B swizzle) into a 4-stage ring
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16) x4 per stage; tcgen05.commit frees the
-//               stage and, after the last k-block, publishes the accumulator
-//   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, so the epilogue of tile i overlaps the
-//               MMAs of tile i+1)
-//   warps 4-11  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> bias / erf-GELU / residual / rotary ->
-//               global (fp16 hi[/lo] or fp32 residual stream)
-// Roofline: tensor bound. Algorithmic FLOPs = 2*M*N*K*nseg.
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D tiles (128 rows x 128 B of A, 256 rows x 128 B of W, 128B swizzle; a row
+//               of 128 B is 64 fp16 or 128 e4m3 along K) into a 4-stage ring
+//   warp 1      MMA issuer: one thread issues tcgen05.mma M=128 N=256 (K=16 fp16 / K=32 e4m3: 32 B of each row either way)
+//               x4 per stage; tcgen05.commit frees the stage and, after the last k-block of a chunk, publishes the accumulator
+//   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators)
+//   warps 4-11  epilogue (224 registers each via setmaxnreg; the control warps drop to 56): tcgen05.ld chunk -> register
+//               accumulators; after the last chunk bias / erf-GELU / relu^2 / rotary, then fp16 hi [+ fp16 lo | + e4m3 planes
+//               for the next GEMM] staged in shared memory and written with TMA bulk tensor stores, or TMA reduce-add into the
+//               fp32 residual stream
+// Roofline: tensor bound. Algorithmic FLOPs = 2*M*N*K; issued tensor-pipe work = x1 / x2 / x3 by mode.
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -34,22 +52,32 @@ constexpr uint32_t STG_BYTES = 4096;
 constexpr uint32_t OFF_BAR = OFF_STG + NUM_EPI_WARPS * STG_BYTES;
 constexpr uint32_t GEMM_SMEM = OFF_BAR + 256 + 1024;  // + barriers + 1 KiB alignment slack
 constexpr uint32_t TMEM_COLS = 512;
+constexpr int MAX_SEGS = 24;
+
+// One run of k-blocks with fixed operand planes. kind: 0 = fp16 (columns in elements), 1 = e4m3 (columns in bytes).
+// commit: 1 = the chunk ends after this segment (publish the accumulator, switch TMEM buffer).
+struct GemmSeg {
+  int a_col, b_col, nkb;
+  short kind, commit;
+};
 
 struct GemmKParams {
-  int M, N, K, nseg;
-  int a_off[3], b_off[3];
+  int M, N, K;
+  int nsegs, nchunks;
+  int scale_first;        // chunk 0 = e4m3 cross terms: acc = v * a_inv * w_inv[col]
+  float a_inv;            // 1 / (2^11 * s_A)
+  const float* w_inv;     // [N] 1 / t_n
+  GemmSeg seg[MAX_SEGS];
   const float* bias;
-  int epi;
-  __half* out; long long ldo; long long lo_off;
-  float* resid; long long ldr;
+  int out_fmt;            // 0 fp16 hi; 1 fp16 hi + fp16 lo; 2 fp16 hi + e4m3 [lo8 | hi8] byte planes
+  float out_scale;        // out_fmt 2: s of the consuming GEMM (hi8 = e4m3(hi*s), lo8 = e4m3(lo*2^11*s))
   const float* rot_cos; const float* rot_sin; int rot_T; int rot_dim;
   int tiles_m, tiles_n;
 };
 
 // Exact-erf GELU (esm/modules.py:17-24): 0.5*x*(1+erf(x/sqrt2)) = 0.5*x + 0.5*|x|*erf(|x|/sqrt2).
 // erf via Abramowitz & Stegun 7.1.26 (abs error <= 1.5e-7; measured |gelu error| <= 4.7e-7, below torch's own fp32 gelu),
-// branch-free: MUFU.RCP + MUFU.EX2 + ~11 FMA-pipe ops instead of erff()'s two divergent code paths, so the fc1 epilogue
-// fits under the MMAs of the next tile even in single-pass mode.
+// branch-free: MUFU.RCP + MUFU.EX2 + ~11 FMA-pipe ops instead of erff()'s two divergent code paths.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x);
   float t;
@@ -65,10 +93,12 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(0.5f * ax, erf_abs, 0.5f * x);
 }
 
-// Epilogue staging: each warp owns a 32-row x 128-byte tile in shared memory laid out for a SWIZZLE_128B TMA store
-// (16-byte chunk c of row r lives at chunk c ^ (r & 7)), so the per-thread row writes are bank-conflict free and the
-// global write is one coalesced bulk tensor store (or reduce-add) per 32x64 fp16 / 32x32 fp32 block, clipped at M and N.
-__device__ __forceinline__ void stage_row_f16(uint8_t* stg, int lane, const float (&v0)[32], const float (&v1)[32], bool lo_plane) {
+// Epilogue staging: each warp owns a 4 KiB tile in shared memory laid out for a swizzled TMA store, so the per-thread row writes
+// are bank-conflict free and the global write is one coalesced bulk tensor store (or reduce-add) per block, clipped at M and N.
+//   fp16 / fp32: 32 rows x 128 B, SWIZZLE_128B (16-byte chunk c of row r lives at chunk c ^ (r & 7))
+//   e4m3       : two tiles of 32 rows x 64 B (lo8 at +0, hi8 at +2048), SWIZZLE_64B (chunk c of row r at c ^ ((r >> 1) & 3))
+template <int OFF>
+__device__ __forceinline__ void stage_row_f16(uint8_t* stg, int lane, const float (&acc)[128], bool lo_plane) {
   uint8_t* row = stg + lane * 128;
   const int sw = lane & 7;
 #pragma unroll
@@ -76,8 +106,7 @@ __device__ __forceinline__ void stage_row_f16(uint8_t* stg, int lane, const floa
     uint32_t w[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float x0 = (c < 4) ? v0[c * 8 + 2 * u] : v1[(c - 4) * 8 + 2 * u];
-      const float x1 = (c < 4) ? v0[c * 8 + 2 * u + 1] : v1[(c - 4) * 8 + 2 * u + 1];
+      const float x0 = acc[OFF + c * 8 + 2 * u], x1 = acc[OFF + c * 8 + 2 * u + 1];
       const uint32_t hi = cvt_f16x2_rn(x0, x1);
       if (lo_plane) {
         const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
@@ -89,19 +118,143 @@ __device__ __forceinline__ void stage_row_f16(uint8_t* stg, int lane, const floa
     *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
-__device__ __forceinline__ void stage_row_f32(uint8_t* stg, int lane, const float (&v)[32]) {
+template <int OFF>
+__device__ __forceinline__ void stage_row_f8(uint8_t* stg, int lane, const float (&acc)[128], float s_hi, float s_lo) {
+  uint8_t* rlo = stg + lane * 64;
+  uint8_t* rhi = stg + 2048 + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t wl[4], wh[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float x0 = acc[OFF + c * 16 + 4 * u], x1 = acc[OFF + c * 16 + 4 * u + 1];
+      const float x2 = acc[OFF + c * 16 + 4 * u + 2], x3 = acc[OFF + c * 16 + 4 * u + 3];
+      const uint32_t h01 = cvt_f16x2_rn(x0, x1), h23 = cvt_f16x2_rn(x2, x3);
+      const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+      const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+      wh[u] = pack4_e4m3(f01.x * s_hi, f01.y * s_hi, f23.x * s_hi, f23.y * s_hi);
+      wl[u] = pack4_e4m3((x0 - f01.x) * s_lo, (x1 - f01.y) * s_lo, (x2 - f23.x) * s_lo, (x3 - f23.y) * s_lo);
+    }
+    *reinterpret_cast<uint4*>(rlo + ((c ^ sw) << 4)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    *reinterpret_cast<uint4*>(rhi + ((c ^ sw) << 4)) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+  }
+}
+template <int OFF>
+__device__ __forceinline__ void stage_row_f32(uint8_t* stg, int lane, const float (&acc)[128]) {
   uint8_t* row = stg + lane * 128;
   const int sw = lane & 7;
 #pragma unroll
   for (int c = 0; c < 8; ++c)
-    *reinterpret_cast<float4*>(row + ((c ^ sw) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    *reinterpret_cast<float4*>(row + ((c ^ sw) << 4)) =
+        make_float4(acc[OFF + 4 * c], acc[OFF + 4 * c + 1], acc[OFF + 4 * c + 2], acc[OFF + 4 * c + 3]);
+}
+
+struct EpiCtx {
+  const CUtensorMap* tmHi; const CUtensorMap* tmLo; const CUtensorMap* tmRes;
+  uint8_t* stg;
+  int lane, gcol, grow0;
+  long long row; bool row_ok;
+};
+
+// Bias, activation and store of one 64-column group (G = 0, 1) of this thread's 128 accumulated columns.
+template <int EPI, int G>
+__device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKParams& p, const EpiCtx& c) {
+  constexpr int O = G * 64;
+  const int gcol = c.gcol + O;
+  if (gcol >= p.N) return;  // warp-uniform
+  if (p.bias != nullptr) {
+    if (gcol + 64 <= p.N) {  // fast path: 16 vector loads of the (warp-uniform) bias slice
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 x = __ldg(b4 + j);
+        acc[O + 4 * j] += x.x; acc[O + 4 * j + 1] += x.y; acc[O + 4 * j + 2] += x.z; acc[O + 4 * j + 3] += x.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) acc[O + j] += (gcol + j < p.N) ? __ldg(p.bias + gcol + j) : 0.f;
+    }
+  }
+  if (EPI == 1) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[O + j] = gelu_erf(acc[O + j]);
+  } else if (EPI == 4) {  // squared ReLU (Tranception MLP, tranception/activations.py:79-84)
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+      const float a = fmaxf(acc[O + j], 0.f);
+      acc[O + j] = a * a;
+    }
+  } else if (EPI == 3 && gcol < 2 * p.rot_dim) {
+    // rotary: x*cos + rotate_half(x)*sin over one 64-wide head; cos/sin[t, j] for j in [0,32) (both halves equal)
+    const int t = static_cast<int>(c.row % p.rot_T);
+    const float* cs = p.rot_cos + static_cast<long long>(t) * 32;
+    const float* sn = p.rot_sin + static_cast<long long>(t) * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float co = c.row_ok ? __ldg(cs + j) : 1.f, s = c.row_ok ? __ldg(sn + j) : 0.f;
+      const float a = acc[O + j], b = acc[O + 32 + j];
+      acc[O + j] = a * co - b * s;
+      acc[O + 32 + j] = b * co + a * s;
+    }
+  }
+  uint8_t* stg = c.stg;
+  const int lane = c.lane;
+  if (EPI == 2) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      if (gcol + hh * 32 >= p.N) break;
+      if (lane == 0) bulk_wait_read0();  // the previous bulk store has finished reading this warp's staging tile
+      __syncwarp();
+      if (hh == 0) stage_row_f32<O>(stg, lane, acc); else stage_row_f32<O + 32>(stg, lane, acc);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(c.tmRes, stg, gcol + hh * 32, c.grow0);
+        bulk_commit();
+      }
+    }
+  } else {
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+    stage_row_f16<O>(stg, lane, acc, false);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(c.tmHi, stg, gcol, c.grow0);
+      bulk_commit();
+    }
+    if (p.out_fmt == 1) {
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      stage_row_f16<O>(stg, lane, acc, true);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(c.tmLo, stg, gcol, c.grow0);
+        bulk_commit();
+      }
+    } else if (p.out_fmt == 2) {
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      stage_row_f8<O>(stg, lane, acc, p.out_scale, p.out_scale * 2048.f);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(c.tmLo, stg, gcol, c.grow0);                 // lo8 plane: bytes [0, N) of the e4m3 region
+        tma_store_2d(c.tmLo, stg + 2048, p.N + gcol, c.grow0);    // hi8 plane: bytes [N, 2N)
+        bulk_commit();
+      }
+    }
+  }
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8,
                const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo,
-               const __grid_constant__ CUtensorMap tmRes, const GemmKParams p) {
+               const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
@@ -116,7 +269,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int kblocks = p.K / BK;
   const int ntiles = p.tiles_m * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
@@ -143,163 +295,141 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
-        for (int seg = 0; seg < p.nseg; ++seg) {
-          for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
-            tma_load_2d(smA + stage * A_BYTES, &tmA, &full[stage], p.a_off[seg] + kb * BK, m_blk * BM);
-            tma_load_2d(smB + stage * B_BYTES, &tmB, &full[stage], p.b_off[seg] + kb * BK, n_blk * BN);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t tphase = (it >> 1) & 1;
-        mbar_wait(&tempty[buf], tphase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * BN;
-        uint32_t accumulate = 0;
-        for (int seg = 0; seg < p.nseg; ++seg) {
-          for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(&full[stage], phase);
-            tc_fence_after();
-            const uint64_t adesc = make_desc_sw128(smem_u32(smA + stage * A_BYTES), 1024);
-            const uint64_t bdesc = make_desc_sw128(smem_u32(smB + stage * B_BYTES), 1024);
-#pragma unroll
-            for (int k = 0; k < BK / UK; ++k) {
-              // advance 16 fp16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-              umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
-              accumulate = 1;
+  if (warp < FIRST_EPI_WARP) {
+    setmaxnreg_dec<56>();
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+          const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+          for (int s = 0; s < p.nsegs; ++s) {
+            const GemmSeg sg = p.seg[s];
+            const CUtensorMap* ma = sg.kind ? &tmA8 : &tmA;
+            const CUtensorMap* mb = sg.kind ? &tmB8 : &tmB;
+            const int step = sg.kind ? 2 * BK : BK;  // 128 B of a row: 64 fp16 or 128 e4m3
+            for (int kb = 0; kb < sg.nkb; ++kb) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
+              tma_load_2d(smA + stage * A_BYTES, ma, &full[stage], sg.a_col + kb * step, m_blk * BM);
+              tma_load_2d(smB + stage * B_BYTES, mb, &full[stage], sg.b_col + kb * step, n_blk * BN);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&empty[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(&tfull[buf]);
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);  // same bit pattern for kind::f8f6f4 with e4m3 operands
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t g = 0;  // running chunk number: TMEM buffer g & 1, barrier phase (g >> 1) & 1
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+          bool fresh = true;
+          uint32_t accumulate = 0;
+          for (int s = 0; s < p.nsegs; ++s) {
+            const GemmSeg sg = p.seg[s];
+            const uint32_t buf = g & 1;
+            if (fresh) {
+              mbar_wait(&tempty[buf], ((g >> 1) & 1) ^ 1);
+              tc_fence_after();
+              accumulate = 0;
+              fresh = false;
+            }
+            const uint32_t tmem_d = tmem_base + buf * BN;
+            for (int kb = 0; kb < sg.nkb; ++kb) {
+              mbar_wait(&full[stage], phase);
+              tc_fence_after();
+              const uint64_t adesc = make_desc_sw128(smem_u32(smA + stage * A_BYTES), 1024);
+              const uint64_t bdesc = make_desc_sw128(smem_u32(smB + stage * B_BYTES), 1024);
+              if (sg.kind) {
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k) {  // 32 e4m3 = 32 bytes along K per instruction
+                  umma_f8(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                  accumulate = 1;
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k) {
+                  // advance 16 fp16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+                  umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+              umma_commit(&empty[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (sg.commit) {
+              umma_commit(&tfull[buf]);
+              ++g;
+              fresh = true;
+            }
+          }
+        }
       }
     }
-  } else if (warp >= FIRST_EPI_WARP) {
+  } else {
+    setmaxnreg_inc<224>();
     const int q = warp & 3;                           // TMEM lane quadrant this warp may read
     const int half_id = (warp - FIRST_EPI_WARP) >> 2;  // which 128-column half of the tile
-    int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    uint32_t g = 0;
+    EpiCtx c;
+    c.tmHi = &tmHi; c.tmLo = &tmLo; c.tmRes = &tmRes;
+    c.stg = smStg + (warp - FIRST_EPI_WARP) * STG_BYTES;
+    c.lane = lane;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
-      const int buf = it & 1;
-      const uint32_t tphase = (it >> 1) & 1;
-      mbar_wait(&tfull[buf], tphase);
-      tc_fence_after();
-      const long long row = static_cast<long long>(m_blk) * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
-#pragma unroll 1
-      for (int cp = 0; cp < 2; ++cp) {  // pairs of 32-column chunks = one 64-wide head
-        const int col0 = half_id * 128 + cp * 64;
-        const int gcol = n_blk * BN + col0;
-        if (gcol >= p.N) break;  // warp-uniform
-        uint32_t r0[32], r1[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + col0;
-        tmem_ld_32x32b_x32(taddr, r0);
-        tmem_ld_32x32b_x32(taddr + 32, r1);
-        tmem_ld_wait();
-        float v0[32], v1[32];
-        if (p.bias != nullptr && gcol + 64 <= p.N) {  // fast path: 16 vector loads of the (warp-uniform) bias slice
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol);
+      c.gcol = n_blk * BN + half_id * 128;
+      c.grow0 = m_blk * BM + q * 32;
+      c.row = static_cast<long long>(c.grow0) + lane;
+      c.row_ok = c.row < p.M;
+      float acc[128];
+      for (int ch = 0; ch < p.nchunks; ++ch, ++g) {
+        const uint32_t buf = g & 1;
+        mbar_wait(&tfull[buf], (g >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + half_id * 128;
+        const bool first = (ch == 0);
+        const bool scaled = first && p.scale_first;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 x = __ldg(b4 + j), y = __ldg(b4 + 8 + j);
-            v0[4 * j] = __uint_as_float(r0[4 * j]) + x.x; v0[4 * j + 1] = __uint_as_float(r0[4 * j + 1]) + x.y;
-            v0[4 * j + 2] = __uint_as_float(r0[4 * j + 2]) + x.z; v0[4 * j + 3] = __uint_as_float(r0[4 * j + 3]) + x.w;
-            v1[4 * j] = __uint_as_float(r1[4 * j]) + y.x; v1[4 * j + 1] = __uint_as_float(r1[4 * j + 1]) + y.y;
-            v1[4 * j + 2] = __uint_as_float(r1[4 * j + 2]) + y.z; v1[4 * j + 3] = __uint_as_float(r1[4 * j + 3]) + y.w;
-          }
-        } else {
+        for (int hp = 0; hp < 2; ++hp) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(taddr + hp * 64, r0);
+          tmem_ld_32x32b_x32(taddr + hp * 64 + 32, r1);
+          tmem_ld_wait();
+          if (scaled) {
+            const int col = c.gcol + hp * 64;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float b0 = (p.bias && gcol + j < p.N) ? __ldg(p.bias + gcol + j) : 0.f;
-            const float b1 = (p.bias && gcol + 32 + j < p.N) ? __ldg(p.bias + gcol + 32 + j) : 0.f;
-            v0[j] = __uint_as_float(r0[j]) + b0;
-            v1[j] = __uint_as_float(r1[j]) + b1;
-          }
-        }
-        if (EPI == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v0[j] = gelu_erf(v0[j]);
-            v1[j] = gelu_erf(v1[j]);
-          }
-        } else if (EPI == 4) {  // squared ReLU (Tranception MLP, tranception/activations.py:79-84)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float a = fmaxf(v0[j], 0.f), b = fmaxf(v1[j], 0.f);
-            v0[j] = a * a;
-            v1[j] = b * b;
-          }
-        } else if (EPI == 3 && gcol < 2 * p.rot_dim) {
-          // rotary: x*cos + rotate_half(x)*sin over one 64-wide head; cos/sin[t, j] for j in [0,32) (both halves equal)
-          const int t = static_cast<int>(row % p.rot_T);
-          const float* cs = p.rot_cos + static_cast<long long>(t) * 32;
-          const float* sn = p.rot_sin + static_cast<long long>(t) * 32;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float c = row_ok ? __ldg(cs + j) : 1.f, s = row_ok ? __ldg(sn + j) : 0.f;
-            const float a = v0[j], b = v1[j];
-            v0[j] = a * c - b * s;
-            v1[j] = b * c + a * s;
-          }
-        }
-        uint8_t* stg = smStg + (warp - FIRST_EPI_WARP) * STG_BYTES;
-        const int grow0 = m_blk * BM + q * 32;
-        if (EPI == 2) {
-#pragma unroll 1
-          for (int hh = 0; hh < 2; ++hh) {
-            if (gcol + hh * 32 >= p.N) break;
-            if (lane == 0) bulk_wait_read0();  // the previous bulk store has finished reading this warp's staging tile
-            __syncwarp();
-            if (hh == 0) stage_row_f32(stg, lane, v0); else stage_row_f32(stg, lane, v1);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_reduce_add_2d(&tmRes, stg, gcol + hh * 32, grow0);
-              bulk_commit();
+            for (int j = 0; j < 32; ++j) {
+              const float f0 = (col + j < p.N) ? p.a_inv * __ldg(p.w_inv + col + j) : 0.f;
+              const float f1 = (col + 32 + j < p.N) ? p.a_inv * __ldg(p.w_inv + col + 32 + j) : 0.f;
+              acc[hp * 64 + j] = __uint_as_float(r0[j]) * f0;
+              acc[hp * 64 + 32 + j] = __uint_as_float(r1[j]) * f1;
             }
-          }
-        } else {
-#pragma unroll 1
-          for (int pl = 0; pl < 2; ++pl) {
-            if (pl == 1 && p.lo_off <= 0) break;
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
-            stage_row_f16(stg, lane, v0, v1, pl == 1);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              if (pl) tma_store_2d(&tmLo, stg, gcol, grow0);
-              else tma_store_2d(&tmHi, stg, gcol, grow0);
-              bulk_commit();
+          } else if (first) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              acc[hp * 64 + j] = __uint_as_float(r0[j]);
+              acc[hp * 64 + 32 + j] = __uint_as_float(r1[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              acc[hp * 64 + j] += __uint_as_float(r0[j]);
+              acc[hp * 64 + 32 + j] += __uint_as_float(r1[j]);
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      finalize_group<EPI, 0>(acc, p, c);
+      finalize_group<EPI, 1>(acc, p, c);
     }
+    if (lane == 0) bulk_wait0();  // all bulk stores of this warp have landed
   }
 
-  if (warp >= FIRST_EPI_WARP && lane == 0) bulk_wait0();  // all bulk stores of this warp have landed
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
@@ -321,12 +451,38 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Host-side cache of encoded tensor maps: the model issues the same few (buffer, shape) combinations thousands of times per
+// assay. thread_local: one map per calling thread, so handles driven from different threads never share state.
+struct TmapKey {
+  const void* ptr; uint64_t rows, cols, ld; uint32_t box_rows, box_cols; int elem_bytes, swizzle;
+  bool operator==(const TmapKey& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return static_cast<size_t>(h);
+  }
+};
+static_assert(sizeof(TmapKey) % 8 == 0, "TmapKey is hashed as 64-bit words");
+
 }  // namespace
 
-// 2D fp16 row-major tensor [rows, cols] with row pitch ld (elements); box = [box_rows, 64 cols], 128B swizzle,
-// out-of-bounds elements read as zero.
-static int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
-                        uint32_t box_cols, int elem_bytes) {
+// 2D row-major tensor [rows, cols] with row pitch ld (elements); box = [box_rows, box_cols], out-of-bounds reads give zero,
+// out-of-bounds parts of a store are clipped. elem_bytes 2 = fp16, 4 = fp32, 1 = bytes (e4m3 planes). swizzle in bytes: 128 or 64.
+int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
+                 int elem_bytes, int swizzle) {
+  TmapKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.rows = rows; key.cols = cols; key.ld = ld; key.box_rows = box_rows; key.box_cols = box_cols;
+  key.elem_bytes = elem_bytes; key.swizzle = swizzle;
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *m = it->second;
+    return PG_OK;
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(PG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * elem_bytes) % 16)
@@ -335,71 +491,126 @@ static int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t
   cuuint64_t strides[1] = {ld * elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                 : elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  CUresult r = fn(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(PG_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(static_cast<int>(r)));
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *m);
   return PG_OK;
 }
 int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                      uint32_t box_cols) {
-  return make_tmap_2d(m, ptr, rows, cols, ld, box_rows, box_cols, 2);
+  return make_tmap_2d(m, ptr, rows, cols, ld, box_rows, box_cols, 2, 128);
+}
+
+int gemm_kchunk() {
+  static int kc = 0;
+  if (!kc) {
+    const char* e = getenv("PG_GEMM_KCHUNK");
+    kc = e ? atoi(e) : 1024;
+    if (kc < BK) kc = 1 << 30;  // PG_GEMM_KCHUNK=0: no chunking (the round-1 behaviour, for the accumulation probe)
+  }
+  return kc;
 }
 
 int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(PG_ERR_ARG, "gemm: empty problem");
   if (g.K % BK) return set_error(PG_ERR_ARG, "gemm: K must be a multiple of 64");
-  if (g.nseg != 1 && g.nseg != 3) return set_error(PG_ERR_ARG, "gemm: nseg must be 1 or 3");
+  if (g.nseg < 1 || g.nseg > 3) return set_error(PG_ERR_ARG, "gemm: nseg must be 1, 2 (fp16 + e4m3 cross terms) or 3");
   if (g.epi < 0 || g.epi > 4) return set_error(PG_ERR_ARG, "gemm: bad epilogue");
   if (g.epi == 2 ? !g.resid : !g.out) return set_error(PG_ERR_ARG, "gemm: missing output");
   if (g.epi == 3 && (!g.rot_cos || !g.rot_sin || g.rot_T <= 0 || g.rot_dim % 64)) return set_error(PG_ERR_ARG, "gemm: bad rotary args");
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (g.nseg == 2 && (!g.w_inv || !(g.a_scale > 0.f))) return set_error(PG_ERR_ARG, "gemm: nseg 2 needs w_inv[N] and a_scale > 0");
+  if (g.out_fmt < 0 || g.out_fmt > 2) return set_error(PG_ERR_ARG, "gemm: bad out_fmt");
+  if (g.epi != 2 && g.out_fmt == 2 && (g.N % 64 || !(g.out_scale > 0.f)))
+    return set_error(PG_ERR_ARG, "gemm: out_fmt 2 needs N % 64 == 0 and out_scale > 0");
+  if (g.epi != 2 && g.out_fmt >= 1 && g.out_lo_off <= 0) return set_error(PG_ERR_ARG, "gemm: out_fmt 1/2 need out_lo_off > 0");
+  int dev = 0;
+  PG_CUDA_OK(cudaGetDevice(&dev));
+  static bool attr_set[64] = {};
+  if (dev < 64 && !attr_set[dev]) {
     PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    attr_set = true;
+    attr_set[dev] = true;
   }
-  const uint64_t width = static_cast<uint64_t>(g.K) * (g.nseg == 3 ? 2 : 1);
-  CUtensorMap tmA, tmB;
-  int rc = make_tmap_f16_2d(&tmA, g.a, g.M, width, g.lda, BM, BK);
+  const uint64_t K = static_cast<uint64_t>(g.K);
+  const uint64_t width = K * (g.nseg == 3 ? 2 : 1);
+  CUtensorMap tmA, tmB, tmA8{}, tmB8{};
+  int rc = make_tmap_2d(&tmA, g.a, g.M, width, g.lda, BM, BK, 2, 128);
   if (rc) return rc;
-  rc = make_tmap_f16_2d(&tmB, g.w, g.N, width, g.ldw, BN, BK);
+  rc = make_tmap_2d(&tmB, g.w, g.N, width, g.ldw, BN, BK, 2, 128);
   if (rc) return rc;
+  if (g.nseg == 2) {  // e4m3 planes follow the fp16 hi plane of each row: bytes [2K, 4K) = K-concatenated [lo8 | hi8] / [hi8 | lo8]
+    rc = make_tmap_2d(&tmA8, static_cast<const uint8_t*>(g.a) + 2 * K, g.M, 2 * K, static_cast<uint64_t>(g.lda) * 2, BM, 2 * BK, 1, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmB8, static_cast<const uint8_t*>(g.w) + 2 * K, g.N, 2 * K, static_cast<uint64_t>(g.ldw) * 2, BN, 2 * BK, 1, 128);
+    if (rc) return rc;
+  }
   CUtensorMap tmHi{}, tmLo{}, tmRes{};
   if (g.epi == 2) {
-    rc = make_tmap_2d(&tmRes, g.resid, g.M, g.N, g.ldr, 32, 32, 4);
+    rc = make_tmap_2d(&tmRes, g.resid, g.M, g.N, g.ldr, 32, 32, 4, 128);
     if (rc) return rc;
   } else {
-    rc = make_tmap_2d(&tmHi, g.out, g.M, g.N, g.ldo, 32, 64, 2);
+    rc = make_tmap_2d(&tmHi, g.out, g.M, g.N, g.ldo, 32, 64, 2, 128);
     if (rc) return rc;
-    if (g.out_lo_off > 0) {
-      rc = make_tmap_2d(&tmLo, g.out + g.out_lo_off, g.M, g.N, g.ldo, 32, 64, 2);
+    if (g.out_fmt == 1) {
+      rc = make_tmap_2d(&tmLo, g.out + g.out_lo_off, g.M, g.N, g.ldo, 32, 64, 2, 128);
+      if (rc) return rc;
+    } else if (g.out_fmt == 2) {
+      rc = make_tmap_2d(&tmLo, g.out + g.out_lo_off, g.M, 2 * static_cast<uint64_t>(g.N), static_cast<uint64_t>(g.ldo) * 2, 32, 64, 1, 64);
       if (rc) return rc;
     }
   }
   GemmKParams p{};
-  p.M = g.M; p.N = g.N; p.K = g.K; p.nseg = g.nseg;
-  // segments: hi*hi, lo*hi, hi*lo
-  p.a_off[0] = 0; p.b_off[0] = 0;
-  p.a_off[1] = g.K; p.b_off[1] = 0;
-  p.a_off[2] = 0; p.b_off[2] = g.K;
-  p.bias = g.bias; p.epi = g.epi;
-  p.out = g.out; p.ldo = g.ldo; p.lo_off = g.out_lo_off;
-  p.resid = g.resid; p.ldr = g.ldr;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  const int kblocks = g.K / BK;
+  int ns = 0, nchunks = 0;
+  auto push = [&](int a_col, int b_col, int nkb, int kind, int commit) {
+    p.seg[ns].a_col = a_col; p.seg[ns].b_col = b_col; p.seg[ns].nkb = nkb;
+    p.seg[ns].kind = static_cast<short>(kind); p.seg[ns].commit = static_cast<short>(commit);
+    ++ns;
+    nchunks += commit;
+  };
+  // hi*hi pieces: as equal as possible, each <= kchunk along K, at most what the segment table holds
+  int pieces = (g.K + gemm_kchunk() - 1) / gemm_kchunk();
+  if (pieces < 1) pieces = 1;
+  if (pieces > MAX_SEGS - 2) pieces = MAX_SEGS - 2;
+  if (pieces > kblocks) pieces = kblocks;
+  if (g.nseg == 2) {
+    push(0, 0, kblocks, 1, 1);  // [lo8 | hi8] x [hi8 | lo8]: 2K bytes = kblocks blocks of 128 B
+    p.scale_first = 1;
+    p.a_inv = 1.0f / (2048.f * g.a_scale);
+    p.w_inv = g.w_inv;
+  } else if (g.nseg == 3) {
+    push(g.K, 0, kblocks, 0, 0);  // lo*hi
+    push(0, g.K, kblocks, 0, 1);  // hi*lo
+  }
+  for (int i = 0, kb0 = 0; i < pieces; ++i) {
+    const int nkb = kblocks / pieces + (i < kblocks % pieces ? 1 : 0);
+    push(kb0 * BK, kb0 * BK, nkb, 0, 1);
+    kb0 += nkb;
+  }
+  p.nsegs = ns; p.nchunks = nchunks;
+  p.bias = g.bias;
+  p.out_fmt = (g.epi == 2) ? 0 : g.out_fmt;
+  p.out_scale = g.out_scale;
   p.rot_cos = g.rot_cos; p.rot_sin = g.rot_sin; p.rot_T = g.rot_T; p.rot_dim = g.rot_dim;
   p.tiles_m = (g.M + BM - 1) / BM;
   p.tiles_n = (g.N + BN - 1) / BN;
   const int ntiles = p.tiles_m * p.tiles_n;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
   switch (g.epi) {
-    case 0: gemm_tc_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmHi, tmLo, tmRes, p); break;
-    case 1: gemm_tc_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmHi, tmLo, tmRes, p); break;
-    case 2: gemm_tc_kernel<2><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmHi, tmLo, tmRes, p); break;
-    case 3: gemm_tc_kernel<3><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmHi, tmLo, tmRes, p); break;
-    default: gemm_tc_kernel<4><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmHi, tmLo, tmRes, p); break;
+    case 0: gemm_tc_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    case 1: gemm_tc_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    case 2: gemm_tc_kernel<2><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    case 3: gemm_tc_kernel<3><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    default: gemm_tc_kernel<4><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
   }
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;

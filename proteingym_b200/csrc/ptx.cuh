@@ -74,6 +74,19 @@ __device__ __forceinline__ uint32_t cvt_f16x2_rn(float lo_elem, float hi_elem) {
   return d;
 }
 
+// two fp32 -> packed e4m3 pair (round to nearest even, saturating at +-448): byte 0 = e0, byte 1 = e1
+__device__ __forceinline__ uint32_t cvt_e4m3x2(float e0, float e1) {
+  uint16_t d;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(d) : "f"(e1), "f"(e0));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack4_e4m3(float e0, float e1, float e2, float e3) {
+  return cvt_e4m3x2(e0, e1) | (cvt_e4m3x2(e2, e3) << 16);
+}
+// Register re-budgeting between warpgroups (all four warps of a warpgroup execute the same instruction).
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
@@ -95,6 +108,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same with kind::f8f6f4 (e4m3 operands as packed bytes in shared memory, K = 32 per instruction, fp32 accumulate; SASS UTCQMMA).
+// The instruction descriptor has the layout of make_idesc_f16 with a_format = b_format = 0 meaning E4M3.
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");

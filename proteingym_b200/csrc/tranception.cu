@@ -348,10 +348,12 @@ int launch_qkv_conv(const __half* in, __half* out, int64_t ld, int64_t lo_off, i
     const dim3 grid(3 * heads * 64 / CV_C, (T + CV_T - 1) / CV_T, B);
     const int np = lo_off > 0 ? 2 : 1;
     const int smem = np * (CV_T + 6) * CV_C * 2;
-    static bool attr = false;
-    if (!attr) {
+    int dev = 0;
+    PG_CUDA_OK(cudaGetDevice(&dev));
+    static bool attr[64] = {};  // the attribute is per device
+    if (dev < 64 && !attr[dev]) {
       PG_CUDA_OK(cudaFuncSetAttribute(qkv_conv2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (CV_T + 6) * CV_C * 2));
-      attr = true;
+      attr[dev] = true;
     }
     if (np == 2) qkv_conv2_kernel<2><<<grid, 128, smem, s>>>(in, out, ld, lo_off, T, heads, taps, qscale);
     else qkv_conv2_kernel<1><<<grid, 128, smem, s>>>(in, out, ld, lo_off, T, heads, taps, qscale);

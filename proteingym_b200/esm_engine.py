@@ -19,11 +19,11 @@ from .checkpoint import EsmConfig, rotary_tables
 from .mutants import parse_mutants
 from .windows import optimal_window_starts
 
-PRECISIONS = {"f16": _lib.PG_PREC_F16, "f16x3": _lib.PG_PREC_F16X3}
+PRECISIONS = {"f16": _lib.PG_PREC_F16, "f16x3": _lib.PG_PREC_F16X3, "f16f8": _lib.PG_PREC_F16F8}
 
 
 class EsmScorer:
-    def __init__(self, config: EsmConfig, state: dict, precision: str = "f16x3", device: int = 0, max_rows: int = 0):
+    def __init__(self, config: EsmConfig, state: dict, precision: str = "f16f8", device: int = 0, max_rows: int = 0):
         if not torch.cuda.is_available():
             raise _lib.PgError("no CUDA device: the B200 scorer has no CPU fallback")
         self.lib = _lib.load()

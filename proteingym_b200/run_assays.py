@@ -38,7 +38,7 @@ def main(argv=None):
     ap.add_argument("--dms-input", required=True)
     ap.add_argument("--dms-output", required=True)
     ap.add_argument("--mutation-col", default="mutant")
-    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "f16"])
+    ap.add_argument("--precision", default="f16f8", choices=["f16f8", "f16x3", "f16"])
     ap.add_argument("--indices", type=int, nargs="*", default=None, help="subset of dms_index values (default: all rows)")
     ap.add_argument("--partition", default="auto", choices=["auto", "assays", "positions"],
                     help="what is split across GPUs: whole assays (LPT) or the masked positions of each assay")

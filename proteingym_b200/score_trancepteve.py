@@ -57,7 +57,7 @@ def create_parser():
     parser = argparse.ArgumentParser(description="TranceptEVE scoring on B200 (score_trancepteve.py drop-in)")
     for flag, kw in _FLAGS:
         parser.add_argument(flag, **kw)
-    parser.add_argument("--precision", default="f16x3", choices=["f16x3", "f16"])
+    parser.add_argument("--precision", default="f16f8", choices=["f16f8", "f16x3", "f16"])
     parser.add_argument("--device", default=0, type=int)
     parser.add_argument("--EVE_sampler", default="auto", choices=["auto", "stream", "local"])
     return parser

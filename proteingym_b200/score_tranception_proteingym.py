@@ -49,7 +49,7 @@ def create_parser():
     for flag, kw in _FLAGS:
         parser.add_argument(flag, **kw)
     # additive
-    parser.add_argument("--precision", default="f16x3", choices=["f16x3", "f16"])
+    parser.add_argument("--precision", default="f16f8", choices=["f16f8", "f16x3", "f16"])
     parser.add_argument("--device", default=0, type=int)
     parser.add_argument("--MSA_log_prior_npy", default=None, type=str, help="precomputed [L_full, 25] log prior for --inference_time_retrieval")
     return parser

@@ -63,7 +63,7 @@ class TranceptEVEScorer(TranceptionScorer):
                  MSA_threshold_sequence_frac_gaps=None, MSA_threshold_focus_cols_frac_gaps=None, EVE_model_paths=None,
                  EVE_num_samples_log_proba=10, EVE_model_parameters_location=None, MSA_recalibrate_probas=False,
                  EVE_recalibrate_probas=True, retrieval_weights_manual=False, retrieval_inference_MSA_weight=0.5,
-                 retrieval_inference_EVE_weight=0.5, scoring_window="optimal", precision="f16x3", device=0, max_rows=0,
+                 retrieval_inference_EVE_weight=0.5, scoring_window="optimal", precision="f16f8", device=0, max_rows=0,
                  EVE_sampler="auto"):
         super().__init__(config, state, precision=precision, device=device, max_rows=max_rows)
         self.full_target_seq = full_target_seq

@@ -151,7 +151,7 @@ def prior_rows(prow, prow2, ws, we, msa_start, msa_end, flip, nonfocus=None):
 
 
 class TranceptionScorer:
-    def __init__(self, config: dict, state: dict, precision: str = "f16x3", device: int = 0, max_rows: int = 0):
+    def __init__(self, config: dict, state: dict, precision: str = "f16f8", device: int = 0, max_rows: int = 0):
         if not torch.cuda.is_available():
             raise _lib.PgError("no CUDA device: the B200 scorer has no CPU fallback")
         self.lib = _lib.load()
@@ -167,7 +167,7 @@ class TranceptionScorer:
         self.config = config
         desc = _lib.PgModelDesc(arch=_lib.PG_ARCH_TRANCEPTION, layers=layers, embed_dim=d, heads=heads, ffn_dim=ffn, vocab=self.vocab,
                                 max_positions=self.n_ctx, token_dropout=0, emb_ln_before=0,
-                                precision={"f16": _lib.PG_PREC_F16, "f16x3": _lib.PG_PREC_F16X3}[precision], device=device,
+                                precision={"f16": _lib.PG_PREC_F16, "f16x3": _lib.PG_PREC_F16X3, "f16f8": _lib.PG_PREC_F16F8}[precision], device=device,
                                 max_rows=max_rows)
         self.handle = C.c_void_p()
         _lib.check(self.lib.pg_create(C.byref(desc), C.byref(self.handle)))

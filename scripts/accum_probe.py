@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from proteingym_b200 import _lib
 lib = _lib.load()
-for K in (256, 1024, 4096, 16384):
+for K in (256, 1280, 5120, 10240, 16384):
     M, N = 256, 256
     g = torch.Generator(device="cuda").manual_seed(K)
     A = (torch.rand(M, K, device="cuda", generator=g) + 0.5).half(); W = (torch.rand(N, K, device="cuda", generator=g) + 0.5).half()

@@ -16,9 +16,10 @@ from proteingym_b200 import _lib, checkpoint, synth
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
+PARITY_MODES = ["f16f8", "f16x3"]  # both must meet the 1e-3 bar; f16f8 (2 tensor-pipe units) is the product default
 
 
-def scorer(arch, state, precision="f16x3", max_rows=32768):
+def scorer(arch, state, precision="f16f8", max_rows=32768):
     from proteingym_b200.esm_engine import EsmScorer
     return EsmScorer(checkpoint.config_from_synth(arch), checkpoint.normalise_synth_state(arch, state), precision=precision,
                      max_rows=max_rows)
@@ -31,6 +32,28 @@ def kind(arch):
 def hilo(t):
     hi = t.to(torch.float16)
     return torch.cat([hi, (t - hi.float()).to(torch.float16)], dim=1).contiguous()
+
+
+def q8(t):
+    """round-to-nearest e4m3 with saturation (what cvt.rn.satfinite.e4m3x2.f32 does), as raw bytes."""
+    return t.float().clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+
+
+def dq8(b):
+    return b.view(torch.float8_e4m3fn).double()
+
+
+def pack_a_f8(t, s):
+    """fp32 [M, K] -> the nseg-2 `a` operand rows [hi fp16 (2K bytes) | lo8 (K) | hi8 (K)] as uint8 [M, 4K] (common.h fmt 2)."""
+    hi = t.to(torch.float16)
+    lo = t - hi.float()
+    return torch.cat([hi.view(torch.uint8), q8(lo * (2048.0 * s)), q8(hi.float() * s)], dim=1).contiguous()
+
+
+def unpack_f8(buf, n, s):
+    """uint8 [M, 4n] fmt-2 rows -> (hi, lo8 / (2048 s), hi8 / s) as float64 [M, n]."""
+    hi = buf[:, :2 * n].contiguous().view(torch.float16).double()
+    return hi, dq8(buf[:, 2 * n:3 * n].contiguous()) / (2048.0 * s), dq8(buf[:, 3 * n:].contiguous()) / s
 
 
 def spearman(a, b):
@@ -89,6 +112,88 @@ def test_gemm_matches_fp64(M, N, K, nseg, epi):
     assert err < bound, (err, bound)
 
 
+@pytest.mark.parametrize("M,N,K,epi,out_fmt", [(128, 256, 64, 0, 1), (300, 320, 128, 1, 2), (257, 576, 192, 2, 0), (1000, 1280, 1280, 2, 0),
+                                               (500, 384, 128, 3, 1), (640, 5120, 1280, 1, 2), (300, 1280, 5120, 2, 0),
+                                               (130, 192, 10240, 0, 2)])
+def test_gemm_f16f8_matches_fp64(M, N, K, epi, out_fmt):
+    """nseg 2: fp16 hi*hi + e4m3 cross terms. The kernel's products are exact in fp32, so against an fp64 evaluation of the SAME
+    quantised planes only accumulation error remains; pg_pack_weight's row scales are checked on the way."""
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    W[::7] *= 37.0  # rows of very different magnitude: the per-row weight scale has to follow
+    bias = torch.randn(N, device="cuda", generator=g)
+    sA, sO = 4.0, 2.0
+    a_op = pack_a_f8(A, sA)
+    w_op = torch.zeros(N, 4 * K, device="cuda", dtype=torch.uint8)
+    w_inv = torch.zeros(N, device="cuda")
+    _lib.check(lib.pg_pack_weight(W.data_ptr(), N, K, 2, w_op.data_ptr(), w_inv.data_ptr(), None))
+    torch.cuda.synchronize()
+    t = 1.0 / w_inv.double()
+    whi = w_op[:, :2 * K].contiguous().view(torch.float16)
+    assert torch.equal(whi, W.to(torch.float16))
+    amax = whi.float().abs().amax(dim=1).double()
+    assert torch.all(torch.log2(t) == torch.floor(torch.log2(t))) and torch.all(amax * t <= 224.0) and torch.all(amax * t > 112.0)
+    assert torch.equal(w_op[:, 2 * K:3 * K], q8(whi.float() * t[:, None].float()))
+    assert torch.equal(w_op[:, 3 * K:], q8((W - whi.float()) * (2048.0 * t[:, None].float())))
+    ahi, alo8, ahi8 = unpack_f8(a_op, K, sA)
+    whi8 = dq8(w_op[:, 2 * K:3 * K].contiguous()) / t[:, None]
+    wlo8 = dq8(w_op[:, 3 * K:].contiguous()) / (2048.0 * t[:, None])
+    ref = ahi @ whi.double().T + alo8 @ whi8.T + ahi8 @ wlo8.T + bias.double()
+    full = A.double() @ W.double().T + bias.double()
+    args = _lib.PgGemmArgs()
+    args.a, args.lda, args.w, args.ldw, args.bias = a_op.data_ptr(), 2 * K, w_op.data_ptr(), 2 * K, bias.data_ptr()
+    args.M, args.N, args.K, args.nseg, args.epi = M, N, K, 2, epi
+    args.a_scale, args.w_inv = sA, w_inv.data_ptr()
+    if epi == 2:
+        resid = torch.randn(M, N, device="cuda", generator=g)
+        ref = ref + resid.double()
+        full = full + resid.double()
+        args.resid, args.ldr = resid.data_ptr(), N
+    else:
+        out = torch.zeros(M, 4 * N, device="cuda", dtype=torch.uint8)
+        args.out_h, args.ldo, args.out_lo_off, args.out_fmt, args.out_scale = out.data_ptr(), 2 * N, N, out_fmt, sO
+        if epi == 1:
+            ref = ref * 0.5 * (1 + torch.erf(ref / 2 ** 0.5))
+            full = full * 0.5 * (1 + torch.erf(full / 2 ** 0.5))
+    if epi == 3:
+        T = 37
+        cos, sin = torch.rand(T, 32, device="cuda", generator=g), torch.rand(T, 32, device="cuda", generator=g)
+        d = (N // 3 // 64) * 64
+        args.rot_cos, args.rot_sin, args.rot_T, args.rot_dim = cos.data_ptr(), sin.data_ptr(), T, d
+        tt = torch.arange(M, device="cuda") % T
+        c, sn = cos[tt].double(), sin[tt].double()
+
+        def rot(x):
+            r = x.clone()
+            for h0 in range(0, 2 * d, 64):
+                x1, x2 = x[:, h0:h0 + 32], x[:, h0 + 32:h0 + 64]
+                r[:, h0:h0 + 32], r[:, h0 + 32:h0 + 64] = x1 * c - x2 * sn, x2 * c + x1 * sn
+            return r
+        ref, full = rot(ref), rot(full)
+    _lib.check(lib.pg_gemm(C.byref(args), None))
+    torch.cuda.synchronize()
+    amax = ref.abs().max().item()
+    bound = 4e-7 * (3 * K) ** 0.5 * max(4.0, amax)
+    if epi == 2:
+        got = resid.double()
+    elif out_fmt == 1:
+        o16 = out.view(torch.float16)
+        got = o16[:, :N].double() + o16[:, N:].double()
+    else:
+        hi, lo8, hi8 = unpack_f8(out, N, sO)
+        got = hi + lo8
+        # the e4m3 planes are what the next GEMM's cross terms read: hi8 ~ hi within e4m3 rounding, lo8 ~ (x - hi) likewise
+        assert ((hi8 - hi).abs() <= 2 ** -4 * hi.abs() + 2 ** -10 / sO).all()
+        assert torch.equal(out[:, 3 * N:], q8(hi.float() * sO))
+        bound = bound + 2 ** -16 * max(1.0, amax)  # lo carried at 4 bits instead of 11
+    err = (got - ref).abs().max().item()
+    print(f"\nf16f8 gemm {M}x{N}x{K} epi {epi}: |got - planes_fp64| = {err:.2e} (bound {bound:.2e}); |got - exact fp32-operand product| = "
+          f"{(got - full).abs().max().item():.2e}")
+    assert err < bound, (err, bound)
+
+
 def test_gemm_rejects_bad_arguments():
     lib = _lib.load()
     a = torch.zeros(8, 60, device="cuda", dtype=torch.float16)
@@ -97,8 +202,10 @@ def test_gemm_rejects_bad_arguments():
     args.out_h, args.ldo = a.data_ptr(), 60
     assert lib.pg_gemm(C.byref(args), None) == 1 and b"multiple of 64" in lib.pg_last_error(None)
     args.K = 64
-    args.nseg = 2
+    args.nseg = 4
     assert lib.pg_gemm(C.byref(args), None) == 1
+    args.nseg = 2  # fp16 + e4m3 mode without the weight scales
+    assert lib.pg_gemm(C.byref(args), None) == 1 and b"w_inv" in lib.pg_last_error(None)
 
 
 @pytest.mark.parametrize("rows,d", [(1, 64), (100, 64), (1000, 1280), (77, 2560)])
@@ -107,16 +214,24 @@ def test_layernorm_matches_fp64(rows, d):
     x = torch.randn(rows, d, device="cuda") * 3 + 1
     g, b = torch.randn(d, device="cuda"), torch.randn(d, device="cuda")
     out = torch.zeros(rows, 2 * d, device="cuda", dtype=torch.float16)
-    _lib.check(lib.pg_layernorm_f16(x.data_ptr(), d, g.data_ptr(), b.data_ptr(), rows, d, out.data_ptr(), 2 * d, d, None))
+    _lib.check(lib.pg_layernorm_f16(x.data_ptr(), d, g.data_ptr(), b.data_ptr(), rows, d, out.data_ptr(), 2 * d, d, 1, 0.0, None))
     torch.cuda.synchronize()
     ref = torch.nn.functional.layer_norm(x.double(), (d,), g.double(), b.double(), 1e-5)
     assert (out[:, :d].double() + out[:, d:].double() - ref).abs().max().item() < 1e-5
+    # fmt 2: same hi plane, e4m3 planes consistent with it
+    out8 = torch.zeros(rows, 4 * d, device="cuda", dtype=torch.uint8)
+    _lib.check(lib.pg_layernorm_f16(x.data_ptr(), d, g.data_ptr(), b.data_ptr(), rows, d, out8.data_ptr(), 2 * d, d, 2, 4.0, None))
+    torch.cuda.synchronize()
+    hi, lo8, hi8 = unpack_f8(out8, d, 4.0)
+    assert torch.equal(out8[:, :2 * d].contiguous().view(torch.float16), out[:, :d])
+    assert torch.equal(out8[:, 3 * d:], q8(out[:, :d].float() * 4.0))
+    assert (hi + lo8 - ref).abs().max().item() < 2 ** -15 * max(1.0, ref.abs().max().item())
 
 
 @pytest.mark.parametrize("B,T,H,nseg,causal", [(2, 64, 2, 1, 0), (3, 100, 2, 1, 0), (2, 514, 4, 1, 0), (1, 1024, 2, 1, 0),
                                                (1, 1, 1, 1, 0), (2, 3, 1, 3, 0), (3, 100, 2, 3, 0), (2, 514, 4, 3, 0),
                                                (2, 130, 2, 1, 1), (2, 130, 2, 3, 1), (2, 514, 4, 1, 1), (1, 1024, 2, 3, 1)])
-@pytest.mark.parametrize("impl", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("impl", [0, 1])
 def test_attention_matches_fp64(B, T, H, nseg, causal, impl):
     slopes = None
     lib = _lib.load()
@@ -144,6 +259,15 @@ def test_attention_matches_fp64(B, T, H, nseg, causal, impl):
     torch.cuda.synchronize()
     got = out[:, :d].double() + (out[:, d:].double() if nseg == 3 else 0)
     assert (got - ref).abs().max().item() < ((1e-4 if causal else 3e-5) if nseg == 3 else 3e-3)
+    if impl == 0 and nseg == 3:  # same launch writing the out_proj operand with e4m3 planes (common.h fmt 2)
+        out8 = torch.zeros(B * T, 4 * d, device="cuda", dtype=torch.uint8)
+        a.out, a.out_fmt, a.out_scale = out8.data_ptr(), 2, 4.0
+        _lib.check(lib.pg_attention(C.byref(a), None))
+        torch.cuda.synchronize()
+        hi, lo8, hi8 = unpack_f8(out8, d, 4.0)
+        assert torch.equal(out8[:, :2 * d].contiguous().view(torch.float16), out[:, :d])
+        assert torch.equal(out8[:, 3 * d:], q8(out[:, :d].float() * 4.0))
+        assert (hi + lo8 - got).abs().max().item() < 2 ** -15 * max(1.0, got.abs().max().item())
 
 
 def test_score_mutants_bit_exact_vs_label_row():
@@ -172,11 +296,12 @@ def test_score_mutants_bit_exact_vs_label_row():
 @pytest.mark.parametrize("knd,L,layers,d,heads,ffn,lnb", [("esm1v", 70, 2, 128, 2, 256, False), ("esm1v", 130, 2, 128, 2, 256, True),
                                                           ("esm2", 100, 3, 128, 2, 512, False), ("esm1v", 37, 1, 64, 1, 64, False),
                                                           ("esm1v", 257, 4, 256, 4, 1024, False)])
-def test_model_matches_oracle_parity_mode(knd, L, layers, d, heads, ffn, lnb):
+@pytest.mark.parametrize("mode", PARITY_MODES)
+def test_model_matches_oracle_parity_mode(knd, L, layers, d, heads, ffn, lnb, mode):
     arch = synth.EsmArch(knd, layers, d, heads, ffn, emb_layer_norm_before=lnb)
     st = synth.make_esm_state(arch, seed=3)
     seq = synth.random_protein(L, 11)
-    sc = scorer(arch, st)
+    sc = scorer(arch, st, precision=mode)
     table = sc.masked_marginal_table(seq).cpu().double()
     ref = O.masked_marginal_table(O.load_state(st, knd, torch.float64), seq, knd, layers, heads, dtype=torch.float64,
                                   positions=range(1, L + 1))
@@ -271,15 +396,17 @@ def test_golden_true_size_blat_config1():
     col = g["meta"]["ckpt_names"][0].split(".")[0]
     want = df[col].to_numpy()
     st = g["state"]()
-    sc = scorer(arch, st, max_rows=131072)
-    got = sc.score_assay(seq, list(df["mutant"]))
-    err = np.abs(got - want)
-    print(f"\nBLAT 650M f16x3: max|d|={err.max():.2e} mean={err.mean():.2e} spearman={spearman(got, want):.6f}")
-    assert err.max() < TOL and spearman(got, want) >= 0.999
-    tab = sc.masked_marginal_table(seq, positions=range(24, 287)).cpu().numpy()
-    assert np.abs(tab[24:287] - g["table"][24:287]).max() < 5e-4
+    for mode in PARITY_MODES:
+        sc = scorer(arch, st, precision=mode, max_rows=131072)
+        got = sc.score_assay(seq, list(df["mutant"]))
+        err = np.abs(got - want)
+        tab = sc.masked_marginal_table(seq, positions=range(24, 287)).cpu().numpy()
+        terr = np.abs(tab[24:287] - g["table"][24:287]).max()
+        print(f"\nBLAT 650M {mode}: max|d|={err.max():.2e} mean={err.mean():.2e} spearman={spearman(got, want):.6f} max|dlogp|={terr:.2e}")
+        assert err.max() < TOL and spearman(got, want) >= 0.999
+        assert terr < 5e-4
+        sc.close()
     assert np.allclose(df["Ensemble_ESM1v"].to_numpy(), want, atol=1e-6)  # single checkpoint: ensemble == column
-    sc.close()
     sc = scorer(arch, st, precision="f16", max_rows=131072)
     got = sc.score_assay(seq, list(df["mutant"]))
     err = np.abs(got - want)

@@ -41,7 +41,7 @@ def _setup(name, tmp_path, with_weights=True, with_cache=True):
     return case, meta, gd, inp, ck, paths
 
 
-def _scorer(case, meta, inp, ck, paths, precision="f16x3"):
+def _scorer(case, meta, inp, ck, paths, precision="f16f8"):
     from proteingym_b200.tranception_engine import load_tranception_checkpoint
     from proteingym_b200.trancepteve_engine import TranceptEVEScorer
     config, state = load_tranception_checkpoint(ck)

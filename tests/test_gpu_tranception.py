@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
-def make_scorer(arch, raw_state, precision="f16x3", max_rows=32768):
+def make_scorer(arch, raw_state, precision="f16f8", max_rows=32768):
     from proteingym_b200.tranception_engine import TranceptionScorer
     cfg = {"n_embd": arch.embed_dim, "n_head": arch.heads, "n_layer": arch.layers, "n_ctx": arch.n_ctx, "n_inner": arch.ffn_dim,
            "vocab_size": arch.vocab, "layer_norm_epsilon": arch.ln_eps, "activation_function": "squared_relu"}
@@ -31,7 +31,7 @@ def load(name):
         pd.read_csv(os.path.join(GOLDEN, f"{name}_reference_scores.csv"))
 
 
-@pytest.mark.parametrize("precision,tol", [("f16x3", 2e-4), ("f16", 5e-2)])
+@pytest.mark.parametrize("precision,tol", [("f16f8", 2e-4), ("f16x3", 2e-4), ("f16", 5e-2)])
 def test_sequence_logprobs_match_oracle(precision, tol):
     arch = synth.TranceptionArch(2, 256, 4, 512)
     st = synth.make_tranception_state(arch, 9)
