@@ -207,6 +207,11 @@ long long pg_launch_count(void);
 int pg_profile_begin(void);
 int pg_profile_end(float* ms, int32_t* counts, int32_t ncat);
 
+/* Process-wide tuning knobs (benchmarks / numerics probes; defaults are the measured-best values):
+ *   "gemm_kchunk"  longest run of K (elements) a hi*hi accumulation chunk covers before the epilogue adds it in RN fp32
+ *                  (default 1024; 0 = no chunking). Also settable through the environment variable PG_GEMM_KCHUNK. */
+int pg_set_tuning(const char* key, int32_t value);
+
 /* Build/version probe (also what the CPU-only test suite calls to check the library loads). */
 int pg_abi_version(void);
 

@@ -4,7 +4,7 @@ Runs the UNMODIFIED reference (vendored fair-esm modules + compute_fitness.main 
 synthetic checkpoints and writes small golden fixtures under tests/golden/. The checkpoints themselves are NOT stored:
 ``proteingym_b200.synth.make_esm_state(arch, seed)`` regenerates them bit-identically (torch CPU generator).
 
-  python oracle/gen_golden.py [tiny] [window] [blat650m]
+  python oracle/gen_golden.py [tiny] [window] [blat650m] [esm2_3b]
 """
 from __future__ import annotations
 
@@ -35,14 +35,16 @@ def blat_sequence():
     return row["target_seq"].upper()
 
 
-def reference_table(mod, ckpt_path, seq):
-    """token_probs [L+2, 33] by the reference's own loop body (compute_fitness.py:486-504), run on the reference model."""
+def reference_table(mod, ckpt_path, seq, positions=None):
+    """token_probs [L+2, 33] by the reference's own loop body (compute_fitness.py:486-504), run on the reference model.
+    ``positions`` (token indices) restricts the loop to those rows (true-size cases: one forward per row is minutes of CPU);
+    the result then holds only those rows, in that order."""
     model, alphabet = mod.pretrained.load_model_and_alphabet(ckpt_path)
     model.eval()
     _, _, toks = alphabet.get_batch_converter()([("protein1", seq)])
     rows = []
     with torch.no_grad():
-        for i in range(toks.size(1)):
+        for i in (range(toks.size(1)) if positions is None else positions):
             t = toks.clone()
             t[0, i] = alphabet.mask_idx
             if toks.size(1) > 1024:
@@ -54,7 +56,7 @@ def reference_table(mod, ckpt_path, seq):
     return torch.cat(rows, 0).numpy()
 
 
-def run_case(name, arch, seed, seq, mutants, ckpt_name, model_type, with_table=True, extra_ckpt=None):
+def run_case(name, arch, seed, seq, mutants, ckpt_name, model_type, with_table=True, extra_ckpt=None, table_positions=None):
     mod = ref_shims.install()
     tmp = tempfile.mkdtemp(prefix="pg_gold_")
     try:
@@ -77,8 +79,10 @@ def run_case(name, arch, seed, seq, mutants, ckpt_name, model_type, with_table=T
                 "sequence": seq, "ckpt_names": [os.path.basename(c) for c in ckpts], "extra_seed": extra_ckpt[1] if extra_ckpt else None,
                 "model_type": model_type, "reference_cli_seconds": dt, "torch": torch.__version__,
                 "threads": torch.get_num_threads()}
+        if table_positions is not None:
+            meta["table_positions"] = [int(i) for i in table_positions]
         if with_table:
-            tab = reference_table(mod, ckpts[0], seq)
+            tab = reference_table(mod, ckpts[0], seq, table_positions)
             np.save(os.path.join(GOLD, f"{name}_reference_table.npy"), tab.astype(np.float32))
         with open(os.path.join(GOLD, f"{name}_meta.json"), "w") as fh:
             json.dump(meta, fh, indent=1)
@@ -109,6 +113,13 @@ def main():
         seq = blat_sequence()
         muts = synth.all_single_mutants(seq, first=24, last=286)
         run_case("blat_esm1v_650m", synth.ESM1V_650M, 0, seq, muts, "esm1v_t33_650M_UR90S_1.pt", "ESM1v", with_table=True)
+    if "esm2_3b" in which:
+        # BASELINE.json config 3 architecture at true size (36 x 2560, 40 heads, ffn 10240, rotary): 256-residue protein, 300 mutants
+        # of which ~70 % are 2-5-site multi-mutants (errors of independently masked sites add up), table rows at 40 positions
+        seq = synth.random_protein(256, seed=31)
+        muts = synth.sample_mutants(seq, 300, seed=6, multi_frac=0.7)
+        run_case("esm2_3b_multi", synth.ESM2_3B, 2, seq, muts, "esm2_t36_3B_UR50D.pt", "ESM2", with_table=True,
+                 table_positions=list(range(3, 257, 6))[:40] + [1, 256])
 
 
 if __name__ == "__main__":

@@ -8,6 +8,7 @@ plus the architecture description the C-ABI needs. Nothing here builds an nn.Mod
 from __future__ import annotations
 
 import argparse
+import os
 import re
 from dataclasses import dataclass
 from pathlib import Path
@@ -39,8 +40,14 @@ def _strip_v1(name: str) -> str:
     return name
 
 
+def checkpoint_column_name(model_location: str) -> str:
+    """Name of the score column a checkpoint produces: the reference's ``model_location.split("/")[-1].split(".")[0]``
+    (compute_fitness.py:350), i.e. everything before the FIRST dot of the file name (``esm1v.v2.pt`` -> ``esm1v``)."""
+    return os.path.basename(str(model_location)).split(".")[0]
+
+
 def load_esm_checkpoint(model_location: str):
-    """-> (EsmConfig, state: dict[str, fp32 CPU tensor], model_name)."""
+    """-> (EsmConfig, state: dict[str, fp32 CPU tensor], score column name)."""
     path = Path(model_location)
     if not str(model_location).endswith(".pt"):
         raise ValueError("only local .pt checkpoints are supported (no network): " + str(model_location))
@@ -70,7 +77,7 @@ def load_esm_checkpoint(model_location: str):
     state = {k: v.detach().to(torch.float32).contiguous() for k, v in raw.items()
              if not k.startswith("contact_head") and k != "lm_head.weight"}
     state["embed_tokens.weight"] = tied.detach().to(torch.float32).contiguous()
-    return conf, state, name
+    return conf, state, checkpoint_column_name(model_location)
 
 
 def config_from_synth(arch) -> EsmConfig:

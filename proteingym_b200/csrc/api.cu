@@ -718,6 +718,12 @@ int pg_score_mutants(const float* table, int32_t n_rows, int32_t vocab, const in
   return launch_score(table, n_rows, vocab, site_row, site_wt, site_mt, row_offsets, M, out_scores, static_cast<cudaStream_t>(stream));
 }
 
+int pg_set_tuning(const char* key, int32_t value) {
+  if (!key) return set_error(PG_ERR_ARG, "pg_set_tuning: null key");
+  if (std::string(key) == "gemm_kchunk") { set_gemm_kchunk(value); return PG_OK; }
+  return set_error(PG_ERR_ARG, std::string("pg_set_tuning: unknown key ") + key);
+}
+
 int pg_gemm(const pg_gemm_args* a, pg_stream stream) {
   if (!a) return set_error(PG_ERR_ARG, "pg_gemm: null args");
   GemmLaunch g{};

@@ -53,6 +53,7 @@ struct GemmLaunch {
   float out_scale = 0.f;          // out_fmt 2: s of the GEMM that will consume `out`
 };
 int launch_gemm(const GemmLaunch& g, cudaStream_t s);
+void set_gemm_kchunk(int v);  // tuning: see gemm_tc.cu
 
 // fmt / scale as above (fmt 0 when lo_off == 0).
 int launch_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int rows, int d, __half* out,

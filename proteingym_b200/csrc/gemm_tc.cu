@@ -118,26 +118,28 @@ __device__ __forceinline__ void stage_row_f16(uint8_t* stg, int lane, const floa
     *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
+// e4m3 planes of 64 accumulated columns as packed words (16 x lo8, 16 x hi8): pure register math, so it can run while the TMA
+// store of the fp16 hi tile is still reading the staging buffer.
 template <int OFF>
-__device__ __forceinline__ void stage_row_f8(uint8_t* stg, int lane, const float (&acc)[128], float s_hi, float s_lo) {
+__device__ __forceinline__ void pack_row_f8(const float (&acc)[128], float s_hi, float s_lo, uint32_t (&wl)[16], uint32_t (&wh)[16]) {
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const float x0 = acc[OFF + 4 * u], x1 = acc[OFF + 4 * u + 1], x2 = acc[OFF + 4 * u + 2], x3 = acc[OFF + 4 * u + 3];
+    const uint32_t h01 = cvt_f16x2_rn(x0, x1), h23 = cvt_f16x2_rn(x2, x3);
+    const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+    const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+    wh[u] = pack4_e4m3(f01.x * s_hi, f01.y * s_hi, f23.x * s_hi, f23.y * s_hi);
+    wl[u] = pack4_e4m3((x0 - f01.x) * s_lo, (x1 - f01.y) * s_lo, (x2 - f23.x) * s_lo, (x3 - f23.y) * s_lo);
+  }
+}
+__device__ __forceinline__ void stage_row_f8(uint8_t* stg, int lane, const uint32_t (&wl)[16], const uint32_t (&wh)[16]) {
   uint8_t* rlo = stg + lane * 64;
   uint8_t* rhi = stg + 2048 + lane * 64;
   const int sw = (lane >> 1) & 3;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    uint32_t wl[4], wh[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float x0 = acc[OFF + c * 16 + 4 * u], x1 = acc[OFF + c * 16 + 4 * u + 1];
-      const float x2 = acc[OFF + c * 16 + 4 * u + 2], x3 = acc[OFF + c * 16 + 4 * u + 3];
-      const uint32_t h01 = cvt_f16x2_rn(x0, x1), h23 = cvt_f16x2_rn(x2, x3);
-      const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
-      const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
-      wh[u] = pack4_e4m3(f01.x * s_hi, f01.y * s_hi, f23.x * s_hi, f23.y * s_hi);
-      wl[u] = pack4_e4m3((x0 - f01.x) * s_lo, (x1 - f01.y) * s_lo, (x2 - f23.x) * s_lo, (x3 - f23.y) * s_lo);
-    }
-    *reinterpret_cast<uint4*>(rlo + ((c ^ sw) << 4)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-    *reinterpret_cast<uint4*>(rhi + ((c ^ sw) << 4)) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+    *reinterpret_cast<uint4*>(rlo + ((c ^ sw) << 4)) = make_uint4(wl[4 * c], wl[4 * c + 1], wl[4 * c + 2], wl[4 * c + 3]);
+    *reinterpret_cast<uint4*>(rhi + ((c ^ sw) << 4)) = make_uint4(wh[4 * c], wh[4 * c + 1], wh[4 * c + 2], wh[4 * c + 3]);
   }
 }
 template <int OFF>
@@ -235,9 +237,11 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
         bulk_commit();
       }
     } else if (p.out_fmt == 2) {
+      uint32_t wl[16], wh[16];
+      pack_row_f8<O>(acc, p.out_scale, p.out_scale * 2048.f, wl, wh);  // overlaps the hi store's read of the staging tile
       if (lane == 0) bulk_wait_read0();
       __syncwarp();
-      stage_row_f8<O>(stg, lane, acc, p.out_scale, p.out_scale * 2048.f);
+      stage_row_f8(stg, lane, wl, wh);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -506,15 +510,17 @@ int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
   return make_tmap_2d(m, ptr, rows, cols, ld, box_rows, box_cols, 2, 128);
 }
 
+// Longest run of K one hi*hi chunk accumulates before the epilogue takes it over (see the header). Default 1024; the environment
+// variable PG_GEMM_KCHUNK or pg_set_tuning("gemm_kchunk", v) override it; 0 = no chunking (round-1 behaviour, for the probe).
+static int g_kchunk = -1;
 int gemm_kchunk() {
-  static int kc = 0;
-  if (!kc) {
+  if (g_kchunk < 0) {
     const char* e = getenv("PG_GEMM_KCHUNK");
-    kc = e ? atoi(e) : 1024;
-    if (kc < BK) kc = 1 << 30;  // PG_GEMM_KCHUNK=0: no chunking (the round-1 behaviour, for the accumulation probe)
+    g_kchunk = e ? atoi(e) : 1024;
   }
-  return kc;
+  return g_kchunk < BK ? (1 << 30) : g_kchunk;
 }
+void set_gemm_kchunk(int v) { g_kchunk = v < 0 ? 0 : v; }
 
 int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(PG_ERR_ARG, "gemm: empty problem");

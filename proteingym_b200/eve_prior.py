@@ -173,22 +173,31 @@ def eve_log_prior(EVE_model_paths, EVE_model_parameters_location: str, msa, full
                   EVE_num_samples_log_proba: int = 10, device="cuda", sampler: str = "auto") -> torch.Tensor:
     """get_EVE_models_and_log_prior (model_pytorch.py:940-967): ensemble mean of the per-model priors, each read from / written to
     the reference's cache location. ``msa`` is the MSAProcessing of the retrieved alignment (focus columns, trimmed focus sequence)."""
+    from . import sharding
     params = json.load(open(EVE_model_parameters_location))
+    rank, _ = sharding.rank_world()
+    # Under torchrun every rank builds a scorer: rank 0 alone computes (and atomically writes) missing priors, the others wait at
+    # the barrier and then read the cache — no rank ever unpickles a half-written file, and the Monte-Carlo pass runs once.
+    if rank == 0:
+        for path in EVE_model_paths:
+            loc = cache_location(path, EVE_num_samples_log_proba)
+            os.makedirs(os.path.dirname(loc), exist_ok=True)
+            if not os.path.exists(loc):
+                print("Computing EVE log prior")
+                ck = torch.load(path, map_location="cpu")
+                single = eve_log_prior_single(ck["model_state_dict"], params, msa.focus_seq_trimmed, msa.focus_cols, full_sequence_len,
+                                              MSA_start, EVE_num_samples_log_proba, device, sampler=sampler).cpu()
+
+                def dump(tmp, obj=single):
+                    with open(tmp, "wb") as fh:
+                        pickle.dump(obj, fh)
+                sharding.atomic_write(loc, dump)
+    sharding.barrier_if_distributed()
     total = 0
     for path in EVE_model_paths:
         loc = cache_location(path, EVE_num_samples_log_proba)
-        os.makedirs(os.path.dirname(loc), exist_ok=True)
-        if not os.path.exists(loc):
-            print("Computing EVE log prior")
-            ck = torch.load(path, map_location="cpu")
-            single = eve_log_prior_single(ck["model_state_dict"], params, msa.focus_seq_trimmed, msa.focus_cols, full_sequence_len, MSA_start,
-                                          EVE_num_samples_log_proba, device, sampler=sampler)
-            with open(loc, "wb") as fh:
-                pickle.dump(single.cpu(), fh)
-        else:
-            print("Loading EVE log prior from disk")
-            with open(loc, "rb") as fh:
-                single = pickle.load(fh)
-            single = torch.as_tensor(single)
+        print("Loading EVE log prior from disk")
+        with open(loc, "rb") as fh:
+            single = torch.as_tensor(pickle.load(fh))
         total = total + single.to(device)
     return total / len(EVE_model_paths)

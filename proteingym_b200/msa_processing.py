@@ -132,12 +132,24 @@ class MSAProcessing:
             if (self.weights_location is not None) and (not os.path.isfile(self.weights_location)):
                 print("Provided weights location is invalid")
                 sys.exit(0)                                        # the reference's behaviour (msa_utils.py:363-365)
-            try:
-                self.weights = np.load(file=self.weights_location)
-            except Exception:
-                self.weights = self.compute_weights()
-                if self.weights_location is not None:
-                    np.save(file=self.weights_location, arr=self.weights)
+            from . import sharding
+            rank, world = sharding.rank_world()
+
+            def load_or_compute():
+                try:
+                    self.weights = np.load(file=self.weights_location)
+                except Exception:
+                    self.weights = self.compute_weights()
+                    if self.weights_location is not None:  # atomic: another rank / process may be reading this path
+                        sharding.atomic_write(self.weights_location, lambda tmp: np.save(file=open(tmp, "wb"), arr=self.weights))
+            if world > 1 and self.weights_location is not None:
+                if rank == 0:
+                    load_or_compute()
+                sharding.barrier_if_distributed()  # ranks > 0 read what rank 0 found or wrote
+                if rank != 0:
+                    load_or_compute()
+            else:
+                load_or_compute()
         else:
             self.weights = np.ones(tok.shape[0])
         self.Neff = np.sum(self.weights)

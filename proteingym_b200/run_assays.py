@@ -29,7 +29,7 @@ if __package__ in (None, ""):
 
 def main(argv=None):
     from proteingym_b200 import sharding
-    from proteingym_b200.checkpoint import load_esm_checkpoint
+    from proteingym_b200.checkpoint import checkpoint_column_name, load_esm_checkpoint
     from proteingym_b200.esm_engine import EsmScorer
     ap = argparse.ArgumentParser()
     ap.add_argument("--model-location", nargs="+", required=True)
@@ -59,13 +59,23 @@ def main(argv=None):
         if rank == 0:
             conf, state, name = load_esm_checkpoint(ckpt)
         if dist is not None:
-            box = [conf, os.path.basename(ckpt).split(".")[0]] if rank == 0 else [None, None]
+            box = [conf, name] if rank == 0 else [None, None]
             dist.broadcast_object_list(box, src=0)
             conf, name = box
             state = sharding.broadcast_state(state, src=0, device=torch.device("cuda", local))
-        costs = [sharding.assay_cost(len(str(mapping["target_seq"][i])), conf.layers, conf.embed_dim, conf.ffn_dim) for i in idx]
-        by_pos = world > 1 and (a.partition == "positions" or (a.partition == "auto" and len(idx) < world))
-        mine = list(idx) if by_pos else [idx[j] for j in sharding.lpt_assign(costs, world)[rank]]
+        if ci == 0:
+            # ONE partition for the whole run, from the first checkpoint's architecture: every column of an assay's CSV must be
+            # produced by the same rank (a per-checkpoint LPT could move an assay between ranks when architectures are mixed).
+            # Masked positions actually run = unique mutated positions <= min(L, number of mutants) when the mapping says how many.
+            def n_pos(i):
+                L = len(str(mapping["target_seq"][i]))
+                if "DMS_total_number_mutants" in mapping.columns and not pd.isna(mapping["DMS_total_number_mutants"][i]):
+                    return min(L, int(mapping["DMS_total_number_mutants"][i]))
+                return L
+            costs = [sharding.assay_cost(len(str(mapping["target_seq"][i])), conf.layers, conf.embed_dim, conf.ffn_dim, n_pos(i))
+                     for i in idx]
+            by_pos = world > 1 and (a.partition == "positions" or (a.partition == "auto" and len(idx) < world))
+            mine = list(idx) if by_pos else [idx[j] for j in sharding.lpt_assign(costs, world)[rank]]
         scorer = EsmScorer(conf, state, precision=a.precision, device=local)
         del state
         for i in mine:
@@ -84,7 +94,7 @@ def main(argv=None):
         if by_pos and rank != 0:  # every rank holds the same scores; one writer
             continue
         if "ESM1v" in a.model_type:
-            names = [os.path.basename(c).split(".")[0] for c in a.model_location]
+            names = [checkpoint_column_name(c) for c in a.model_location]
             df["Ensemble_ESM1v"] = sum(df[n] for n in names) / len(names)
         df.to_csv(os.path.join(a.dms_output, str(mapping["DMS_id"][i]) + ".csv"), index=False)
     rows = [(int(i), n, float(s), int(m), rank) for (i, n), (s, m) in summary.items()]

@@ -7,6 +7,28 @@ from __future__ import annotations
 import torch
 
 
+def rank_world():
+    """(rank, world) of the default process group, (0, 1) when torch.distributed is not initialised."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def barrier_if_distributed():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
+def atomic_write(path: str, write_fn):
+    """Write through a temporary file + os.replace so that a concurrent reader never sees a truncated file."""
+    import os
+    tmp = f"{path}.tmp.{os.getpid()}"
+    write_fn(tmp)
+    os.replace(tmp, path)
+
+
 def assay_cost(L: int, layers: int, d: int, ffn: int, n_positions: int | None = None, window: int = 1024) -> float:
     """Algorithmic FLOPs of one masked-marginal assay: P * F_fwd(T), T = min(L+2, window)."""
     T = min(L + 2, window)

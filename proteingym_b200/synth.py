@@ -44,32 +44,35 @@ ESM2_3B = EsmArch("esm2", 36, 2560, 40, 10240)
 
 
 def _uniform(g, shape, bound):
-    return (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
+    return (torch.rand(shape, generator=g, dtype=torch.float32, device=g.device) * 2 - 1) * bound
 
 
-def make_esm_state(arch: EsmArch, seed: int = 0, qk_gain: float = 2.0) -> dict:
+def make_esm_state(arch: EsmArch, seed: int = 0, qk_gain: float = 2.0, device=None) -> dict:
     """State dict with the key names of the reference modules (un-prefixed).
 
     Distributions follow the reference constructors' defaults (nn.Embedding N(0,1); nn.Linear U(+-1/sqrt(fan_in));
     q/k/v xavier-uniform with gain 1/sqrt(2), multihead_attention.py:138-155) except that biases and LayerNorm affine
     terms are made non-trivial so a dropped bias shows up in parity tests, and q/k are scaled by ``qk_gain`` so the
     attention softmax is far from uniform.
+
+    ``device`` (default CPU) is where the tensors are drawn. The CPU stream is the one every golden fixture was generated from;
+    a CUDA device gives the same distributions from a different stream in a fraction of the time (bench workloads at 3B size).
     """
-    g = torch.Generator().manual_seed(seed)
+    g = torch.Generator(device=device if device is not None else "cpu").manual_seed(seed)
     d, f, V = arch.embed_dim, arch.ffn_dim, arch.vocab
     st = {}
     # nn.Embedding's N(0,1) would give tied-output logits of std sqrt(d) (~36 at d=1280), far from a trained model's;
     # 0.1 keeps log-prob differences in the single digits like real ESM checkpoints.
-    emb = 0.1 * torch.randn((V, d), generator=g)
+    emb = 0.1 * torch.randn((V, d), generator=g, device=g.device)
     emb[1].zero_()  # padding_idx row (nn.Embedding(padding_idx=1))
     st["embed_tokens.weight"] = emb
     if arch.kind == "esm1v":
-        pos = 0.1 * torch.randn((arch.max_positions + 2, d), generator=g)
+        pos = 0.1 * torch.randn((arch.max_positions + 2, d), generator=g, device=g.device)
         pos[1].zero_()
         st["embed_positions.weight"] = pos
         if arch.emb_layer_norm_before:
-            st["emb_layer_norm_before.weight"] = 1 + 0.1 * torch.randn(d, generator=g)
-            st["emb_layer_norm_before.bias"] = 0.05 * torch.randn(d, generator=g)
+            st["emb_layer_norm_before.weight"] = 1 + 0.1 * torch.randn(d, generator=g, device=g.device)
+            st["emb_layer_norm_before.bias"] = 0.05 * torch.randn(d, generator=g, device=g.device)
     for i in range(arch.layers):
         p = f"layers.{i}."
         xb = math.sqrt(3.0 / (2 * d))  # xavier_uniform gain 1/sqrt(2): sqrt(6/(2d))/sqrt(2)
@@ -78,24 +81,24 @@ def make_esm_state(arch: EsmArch, seed: int = 0, qk_gain: float = 2.0) -> dict:
             st[p + f"self_attn.{nm}_proj.bias"] = _uniform(g, (d,), 1 / math.sqrt(d)) * gain
         st[p + "self_attn.out_proj.weight"] = _uniform(g, (d, d), math.sqrt(6.0 / (2 * d)))
         st[p + "self_attn.out_proj.bias"] = _uniform(g, (d,), 1 / math.sqrt(d))
-        st[p + "self_attn_layer_norm.weight"] = 1 + 0.1 * torch.randn(d, generator=g)
-        st[p + "self_attn_layer_norm.bias"] = 0.05 * torch.randn(d, generator=g)
+        st[p + "self_attn_layer_norm.weight"] = 1 + 0.1 * torch.randn(d, generator=g, device=g.device)
+        st[p + "self_attn_layer_norm.bias"] = 0.05 * torch.randn(d, generator=g, device=g.device)
         st[p + "fc1.weight"] = _uniform(g, (f, d), 1 / math.sqrt(d))
         st[p + "fc1.bias"] = _uniform(g, (f,), 1 / math.sqrt(d))
         st[p + "fc2.weight"] = _uniform(g, (d, f), 1 / math.sqrt(f))
         st[p + "fc2.bias"] = _uniform(g, (d,), 1 / math.sqrt(f))
-        st[p + "final_layer_norm.weight"] = 1 + 0.1 * torch.randn(d, generator=g)
-        st[p + "final_layer_norm.bias"] = 0.05 * torch.randn(d, generator=g)
+        st[p + "final_layer_norm.weight"] = 1 + 0.1 * torch.randn(d, generator=g, device=g.device)
+        st[p + "final_layer_norm.bias"] = 0.05 * torch.randn(d, generator=g, device=g.device)
         if arch.kind == "esm2":
             hd = d // arch.heads
-            st[p + "self_attn.rot_emb.inv_freq"] = 1.0 / (10000 ** (torch.arange(0, hd, 2).float() / hd))
-    st["emb_layer_norm_after.weight"] = 1 + 0.1 * torch.randn(d, generator=g)
-    st["emb_layer_norm_after.bias"] = 0.05 * torch.randn(d, generator=g)
+            st[p + "self_attn.rot_emb.inv_freq"] = (1.0 / (10000 ** (torch.arange(0, hd, 2).float() / hd))).to(g.device)
+    st["emb_layer_norm_after.weight"] = 1 + 0.1 * torch.randn(d, generator=g, device=g.device)
+    st["emb_layer_norm_after.bias"] = 0.05 * torch.randn(d, generator=g, device=g.device)
     st["lm_head.dense.weight"] = _uniform(g, (d, d), 1 / math.sqrt(d))
     st["lm_head.dense.bias"] = _uniform(g, (d,), 1 / math.sqrt(d))
-    st["lm_head.layer_norm.weight"] = 1 + 0.1 * torch.randn(d, generator=g)
-    st["lm_head.layer_norm.bias"] = 0.05 * torch.randn(d, generator=g)
-    st["lm_head.bias"] = 0.1 * torch.randn(V, generator=g)
+    st["lm_head.layer_norm.weight"] = 1 + 0.1 * torch.randn(d, generator=g, device=g.device)
+    st["lm_head.layer_norm.bias"] = 0.05 * torch.randn(d, generator=g, device=g.device)
+    st["lm_head.bias"] = 0.1 * torch.randn(V, generator=g, device=g.device)
     # tied: same tensor object, so torch.save keeps the aliasing like the released checkpoints do
     st["lm_head.weight"] = st["embed_tokens.weight"]
     return st

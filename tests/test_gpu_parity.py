@@ -134,7 +134,8 @@ def test_gemm_f16f8_matches_fp64(M, N, K, epi, out_fmt):
     whi = w_op[:, :2 * K].contiguous().view(torch.float16)
     assert torch.equal(whi, W.to(torch.float16))
     amax = whi.float().abs().amax(dim=1).double()
-    assert torch.all(torch.log2(t) == torch.floor(torch.log2(t))) and torch.all(amax * t <= 224.0) and torch.all(amax * t > 112.0)
+    mant, _ = torch.frexp(t)
+    assert torch.all(mant == 0.5) and torch.all(amax * t <= 224.0) and torch.all(amax * t > 112.0)  # powers of two, (112, 224]
     assert torch.equal(w_op[:, 2 * K:3 * K], q8(whi.float() * t[:, None].float()))
     assert torch.equal(w_op[:, 3 * K:], q8((W - whi.float()) * (2048.0 * t[:, None].float())))
     ahi, alo8, ahi8 = unpack_f8(a_op, K, sA)
