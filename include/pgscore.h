@@ -130,6 +130,25 @@ typedef struct pg_ar_fusion {
 int pg_ar_loglik_fused(pg_handle h, const int32_t* ids, const int32_t* lens, int32_t B, int32_t T, const pg_ar_fusion* f,
                        float* out_sum_logp, pg_stream stream);
 
+/* Exact wild-type-prefix reuse (north_star: "positions share a single prefix/KV pass"; the reference carries the layer_past /
+ * use_cache plumbing, model_pytorch.py:209-237, 441-458, and never uses it in scoring_utils.py:89-132). In a causal decoder with
+ * causal depthwise convolutions every hidden state of a mutant before its first changed token equals the wild type's, so only rows
+ * >= start need the transformer; keys / values of rows < start and the 6 rows of conv look-back come from the wild type's pass.
+ *   pg_ar_prefix_begin : forward of ONE sequence ids[T] (the wild type in the window being scored), recording every layer's raw and
+ *                        conv'd q/k/v rows inside the handle. out_tok_logp [T] fp32 (device): log p(ids[t+1] | ids[<=t]) for
+ *                        t < T-1 (0 at T-1), fused with the priors in f like pg_ar_loglik_fused (f->prior_row is [1, T]);
+ *                        f->out_logprobs [T, vocab] receives the full fused rows when non-NULL (the host needs row start-1 to score
+ *                        a mutant whose first changed token sits exactly at `start`).
+ *   pg_ar_loglik_prefix: B right-padded suffixes ids[B, T] = tokens start .. start+T-1 of sequences that share tokens 0 .. start-1
+ *                        with the recorded wild type; lens[B] = real tokens in each suffix; start = a positive multiple of 128 (the
+ *                        attention tile), < the recorded length. out_sum_logp[b] = sum over the suffix rows of
+ *                        log p(token t+1 | tokens <= t), t >= start. Rows are bit-identical to what pg_ar_loglik computes for the
+ *                        same sequences; only the summation is split (prefix part from the wild type's rows + this suffix part).
+ * The record lives until the next pg_ar_prefix_begin on the handle. */
+int pg_ar_prefix_begin(pg_handle h, const int32_t* ids, int32_t T, const pg_ar_fusion* f, float* out_tok_logp, pg_stream stream);
+int pg_ar_loglik_prefix(pg_handle h, const int32_t* ids, const int32_t* lens, int32_t B, int32_t T, int32_t start,
+                        const pg_ar_fusion* f, float* out_sum_logp, pg_stream stream);
+
 /* Replaces label_row over the whole DMS frame (compute_fitness.py:240-250, :505-514):
  *   score[m] = sum_{s in [row_offsets[m], row_offsets[m+1])} table[site_row[s], site_mt[s]] - table[site_row[s], site_wt[s]]
  * table [n_rows, vocab] fp32; site_* int32 CSR arrays (device); out_scores [M] fp32. Fixed summation order per mutant. */

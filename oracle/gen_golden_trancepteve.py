@@ -13,6 +13,7 @@ import pickle
 import shutil
 import sys
 import tempfile
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -168,6 +169,43 @@ def run_tranception_cases():
     print(f"[gen_golden_trancepteve] {name}: {len(scores)} rows")
 
 
+def run_true_size_tranception_cases():
+    """BASELINE config 4 architecture at TRUE SIZE (Tranception-L: 36 x 1280, 20 heads, ffn 5120, n_ctx 1024) under the real
+    TranceptionLMHeadModel: substitutions incl. multi-mutants, indels (ragged lengths), and a protein longer than n_ctx - 2 (optimal
+    windows). Files use the flat tranception_* layout of gen_golden_tranception.py so the same GPU test reads them."""
+    arch = synth.TRANCEPTION_L
+    cases = []
+    seq = synth.random_protein(180, 51)
+    muts = synth.sample_mutants(seq, 60, seed=7, multi_frac=0.3)
+    df = pd.DataFrame({"mutant": muts, "DMS_score": 0.0})
+    df["mutated_sequence"] = [synth.apply_mutant(seq, m) for m in muts]
+    cases.append(("tranception_L_subs", seq, df, False))
+    seq2 = synth.random_protein(70, 52)
+    ind = synth.random_indels(seq2, 40, seed=8) + [seq2]
+    cases.append(("tranception_L_indels", seq2, pd.DataFrame({"mutant": ind, "mutated_sequence": ind, "DMS_score": 0.0}), True))
+    seq3 = synth.random_protein(1060, 53)
+    muts3 = synth.sample_mutants(seq3, 6, seed=9, multi_frac=0.34)
+    df3 = pd.DataFrame({"mutant": muts3, "DMS_score": 0.0})
+    df3["mutated_sequence"] = [synth.apply_mutant(seq3, m) for m in muts3]
+    cases.append(("tranception_L_long", seq3, df3, False))
+    for name, target, dms, indel in cases:
+        if len(sys.argv) > 2 and name not in sys.argv[2:]:
+            continue
+        model = build_tranception(arch, target)
+        t0 = time.time()
+        with torch.no_grad():
+            scores = model.score_mutants(DMS_data=dms, target_seq=target, scoring_mirror=True, batch_size_inference=10, num_workers=0,
+                                         indel_mode=indel)
+        scores.to_csv(os.path.join(GOLD, f"{name}_reference_scores.csv"), index=False)
+        dms.to_csv(os.path.join(GOLD, f"{name}_dms.csv"), index=False)
+        with open(os.path.join(GOLD, f"{name}_meta.json"), "w") as fh:
+            json.dump({"name": name, "arch": arch.__dict__, "seed": 5, "target_seq": target, "indel_mode": indel, "scoring_window": "optimal",
+                       "torch": torch.__version__, "model": "tranception.model_pytorch.TranceptionLMHeadModel (unmodified)",
+                       "seconds": time.time() - t0}, fh, indent=1)
+        print(f"[gen_golden_trancepteve] {name}: {len(scores)} rows in {time.time() - t0:.0f} s", flush=True)
+        del model
+
+
 def dump_cli_flags():
     """Option surface of the reference's two Tranception-family scripts (their parsers are built inside main(): stop main() at
     parse_args and dump the parser's actions) -> tests/golden/{tranception,trancepteve}_cli_flags.json."""
@@ -212,9 +250,11 @@ def main():
         return dump_cli_flags()
     if len(sys.argv) > 1 and sys.argv[1] == "tranception":
         return run_tranception_cases()
+    if len(sys.argv) > 1 and sys.argv[1] == "truesize":
+        return run_true_size_tranception_cases()
     for name, case in CASES.items():
-        if len(sys.argv) > 1 and name not in sys.argv[1:]:
-            continue
+        if (len(sys.argv) > 1 and name not in sys.argv[1:]) or (len(sys.argv) == 1 and case.get("true_size")):
+            continue  # true-size cases only on request
         run_case(name, case)
 
 

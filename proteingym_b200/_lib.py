@@ -61,6 +61,9 @@ SIGNATURES = {
                                C.c_void_p]),
     "pg_ar_loglik_fused": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(PgArFusion), C.c_void_p,
                                      C.c_void_p]),
+    "pg_ar_prefix_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(PgArFusion), C.c_void_p, C.c_void_p]),
+    "pg_ar_loglik_prefix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(PgArFusion),
+                                      C.c_void_p, C.c_void_p]),
     "pg_gemm": (C.c_int, [C.POINTER(PgGemmArgs), C.c_void_p]),
     "pg_layernorm_f16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_void_p]),

@@ -177,6 +177,11 @@ struct pg_handle_s {
   // Tranception
   __half* qkv2 = nullptr;
   float *tok_logp = nullptr, *slopes = nullptr;
+  // exact wild-type-prefix reuse (pg_ar_prefix_begin / pg_ar_loglik_prefix): per layer, the wild type's raw q/k/v rows (conv
+  // look-back) and conv'd q/k/v rows (keys / values of the shared prefix), [layers][prefix_T][3d*np] fp16 each
+  __half *raw_cache = nullptr, *kv_cache = nullptr;
+  int prefix_T = 0;        // rows recorded by the last pg_ar_prefix_begin (0 = none)
+  int prefix_cap = 0;      // rows the caches can hold
   // compact buffers for the pruned last layer (one row per sequence)
   float* xc = nullptr;
   __half *cabuf = nullptr, *cfbuf = nullptr;
@@ -312,7 +317,10 @@ int forward_rows(pg_handle h, const int32_t* tokens, int n_tokens, const int32_t
 
 // Tranception decoder stack over B right-padded sequences of T tokens (model_pytorch.py:526-612): no padding mask is needed
 // because pads sit to the right of every real token and attention is causal.
-int forward_tranception(pg_handle h, const int32_t* ids, int B, int T, cudaStream_t s) {
+// mode 0: plain forward. mode 1 (B == 1): also record every layer's raw and conv'd q/k/v rows into the prefix caches.
+// mode 2: the B sequences are rows [start, start + T) of sequences whose first `start` rows (multiple of 128) equal the recorded
+// wild type's: depthwise-conv look-back and the keys / values of the prefix come from the caches.
+int forward_tranception(pg_handle h, const int32_t* ids, int B, int T, cudaStream_t s, int mode = 0, int start = 0) {
   const pg_model_desc& D = h->desc;
   const int d = D.embed_dim, f = D.ffn_dim, np = h->np;
   const int afmt = h->nseg == 2 ? 2 : (np == 2 ? 1 : 0);
@@ -334,12 +342,20 @@ int forward_tranception(pg_handle h, const int32_t* ids, int B, int T, cudaStrea
     q.out = h->qkv; q.out_fmt = qfmt;
     rc = run_lin(h, CAT_GEMM_QKV, q, s);
     if (rc) return rc;
-    { ProfScope ps(CAT_OTHER, s); rc = launch_qkv_conv(h->qkv, h->qkv2, ldq, np == 2 ? 3 * d : 0, B, T, D.heads, L.conv_taps, 0.125f, s); }
+    const size_t layer_off = static_cast<size_t>(l) * h->prefix_cap * ldq;
+    if (mode == 1)
+      PG_CUDA_OK(cudaMemcpyAsync(h->raw_cache + layer_off, h->qkv, static_cast<size_t>(T) * ldq * sizeof(__half), cudaMemcpyDeviceToDevice, s));
+    { ProfScope ps(CAT_OTHER, s);
+      rc = launch_qkv_conv(h->qkv, h->qkv2, ldq, np == 2 ? 3 * d : 0, B, T, D.heads, L.conv_taps, 0.125f, s,
+                           mode == 2 ? h->raw_cache + layer_off + static_cast<size_t>(start - 6) * ldq : nullptr); }
     if (rc) return rc;
+    if (mode == 1)
+      PG_CUDA_OK(cudaMemcpyAsync(h->kv_cache + layer_off, h->qkv2, static_cast<size_t>(T) * ldq * sizeof(__half), cudaMemcpyDeviceToDevice, s));
     AttnLaunch a{};
     a.qkv = h->qkv2; a.ld = ldq; a.lo_off = np == 2 ? 3 * d : 0;
     a.out = h->abuf; a.ldo = ldd; a.out_lo_off = np == 2 ? d : 0; a.out_fmt = afmt; a.out_scale = S_ATT;
     a.B = B; a.T = T; a.heads = D.heads; a.nseg = np == 2 ? 3 : 1; a.causal = 1; a.alibi_slopes = h->slopes;
+    if (mode == 2) { a.prefix = h->kv_cache + layer_off; a.prefix_len = start; }
     { ProfScope ps(CAT_ATTN, s); rc = launch_attention_tc(a, s); }
     if (rc) return rc;
     Lin o{h->abuf, ldd, S_ATT, L.wo, L.io, L.bo, rows, d, d, 2};
@@ -661,6 +677,18 @@ int pg_forward_logprobs(pg_handle h, const int32_t* tokens, int32_t n_tokens, in
   return PG_OK;
 }
 
+static int ar_fusion_args(pg_handle h, const pg_ar_fusion* f, ArFusion* base) {
+  if (!f) return PG_OK;
+  if ((f->log_prior == nullptr) != (f->prior_row == nullptr)) return fail(h, PG_ERR_ARG, "pg_ar_loglik: log_prior and prior_row go together");
+  if ((f->log_prior2 == nullptr) != (f->prior_row2 == nullptr)) return fail(h, PG_ERR_ARG, "pg_ar_loglik: log_prior2 and prior_row2 go together");
+  if (f->log_prior2 && !f->log_prior) return fail(h, PG_ERR_ARG, "pg_ar_loglik: the second prior needs the first (it is fused inside the MSA overlap)");
+  if (f->first_col < 0 || f->first_col > h->desc.vocab) return fail(h, PG_ERR_ARG, "pg_ar_loglik: first_col outside the vocabulary");
+  base->log_prior = f->log_prior; base->prior_row = f->prior_row; base->alpha = f->alpha;
+  base->log_prior2 = f->log_prior2; base->prior_row2 = f->prior_row2; base->beta = f->beta;
+  base->first_col = f->first_col; base->out_logprobs = f->out_logprobs;
+  return PG_OK;
+}
+
 int pg_ar_loglik_fused(pg_handle h, const int32_t* ids, const int32_t* lens, int32_t B, int32_t T, const pg_ar_fusion* f,
                        float* out_sum_logp, pg_stream stream) {
   if (!h) return set_error(PG_ERR_ARG, "pg_ar_loglik: null handle");
@@ -670,15 +698,7 @@ int pg_ar_loglik_fused(pg_handle h, const int32_t* ids, const int32_t* lens, int
   if (B == 0) return PG_OK;
   if (!ids || !lens || !out_sum_logp) return fail(h, PG_ERR_ARG, "pg_ar_loglik: null buffer");
   ArFusion base;
-  if (f) {
-    if ((f->log_prior == nullptr) != (f->prior_row == nullptr)) return fail(h, PG_ERR_ARG, "pg_ar_loglik: log_prior and prior_row go together");
-    if ((f->log_prior2 == nullptr) != (f->prior_row2 == nullptr)) return fail(h, PG_ERR_ARG, "pg_ar_loglik: log_prior2 and prior_row2 go together");
-    if (f->log_prior2 && !f->log_prior) return fail(h, PG_ERR_ARG, "pg_ar_loglik: the second prior needs the first (it is fused inside the MSA overlap)");
-    if (f->first_col < 0 || f->first_col > h->desc.vocab) return fail(h, PG_ERR_ARG, "pg_ar_loglik: first_col outside the vocabulary");
-    base.log_prior = f->log_prior; base.prior_row = f->prior_row; base.alpha = f->alpha;
-    base.log_prior2 = f->log_prior2; base.prior_row2 = f->prior_row2; base.beta = f->beta;
-    base.first_col = f->first_col; base.out_logprobs = f->out_logprobs;
-  }
+  { int frc = ar_fusion_args(h, f, &base); if (frc) return frc; }
   if (T > h->desc.max_positions) return fail(h, PG_ERR_ARG, "pg_ar_loglik: sequence longer than n_ctx");
   if (T > h->max_rows) return fail(h, PG_ERR_ARG, "pg_ar_loglik: sequence longer than workspace");
   PG_CUDA_OK(cudaSetDevice(h->desc.device));
@@ -696,6 +716,73 @@ int pg_ar_loglik_fused(pg_handle h, const int32_t* ids, const int32_t* lens, int
     if (fc.prior_row2) fc.prior_row2 += off;
     if (fc.out_logprobs) fc.out_logprobs += off * h->desc.vocab;
     rc = launch_ar_head(h->x, h->desc.embed_dim, Bc, T, h->desc.vocab, idc, lens + b0, h->lnag, h->lnab, h->embed, fc, h->tok_logp,
+                        out_sum_logp + b0, s);
+    if (rc) return fail(h, rc, tls_error());
+  }
+  return PG_OK;
+}
+
+int pg_ar_prefix_begin(pg_handle h, const int32_t* ids, int32_t T, const pg_ar_fusion* f, float* out_tok_logp, pg_stream stream) {
+  if (!h) return set_error(PG_ERR_ARG, "pg_ar_prefix_begin: null handle");
+  if (!h->loaded) return fail(h, PG_ERR_STATE, "pg_ar_prefix_begin: weights not loaded");
+  if (h->desc.arch != PG_ARCH_TRANCEPTION) return fail(h, PG_ERR_STATE, "pg_ar_prefix_begin: handle is not a Tranception model");
+  if (!ids || !out_tok_logp || T < 2) return fail(h, PG_ERR_ARG, "pg_ar_prefix_begin: bad arguments");
+  if (T > h->desc.max_positions || T > h->max_rows) return fail(h, PG_ERR_ARG, "pg_ar_prefix_begin: sequence longer than n_ctx / workspace");
+  ArFusion fu;
+  int rc = ar_fusion_args(h, f, &fu);
+  if (rc) return rc;
+  PG_CUDA_OK(cudaSetDevice(h->desc.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t ldq = static_cast<size_t>(3) * h->desc.embed_dim * h->np;
+  if (h->prefix_cap < h->desc.max_positions) {  // first use: [layers][n_ctx][3d*np] fp16, twice
+    const size_t n = static_cast<size_t>(h->desc.layers) * h->desc.max_positions * ldq;
+    rc = dev_alloc(h, &h->raw_cache, n);
+    if (!rc) rc = dev_alloc(h, &h->kv_cache, n);
+    if (rc) return rc;
+    h->prefix_cap = h->desc.max_positions;
+  }
+  h->prefix_T = 0;
+  rc = forward_tranception(h, ids, 1, T, s, 1, 0);
+  if (rc) return fail(h, rc, tls_error());
+  // per-token log p(ids[t+1] | ids[<=t]) of the wild type, t = 0 .. T-2 (and the fused rows in f->out_logprobs when asked for)
+  int32_t* len_dev = h->row_sel;
+  PG_CUDA_OK(cudaMemcpyAsync(len_dev, &T, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  { ProfScope ps(CAT_HEAD, s, 2);
+    rc = launch_ar_head(h->x, h->desc.embed_dim, 1, T, h->desc.vocab, ids, len_dev, h->lnag, h->lnab, h->embed, fu, out_tok_logp, h->tok_logp, s); }
+  if (rc) return fail(h, rc, tls_error());
+  h->prefix_T = T;
+  return PG_OK;
+}
+
+int pg_ar_loglik_prefix(pg_handle h, const int32_t* ids, const int32_t* lens, int32_t B, int32_t T, int32_t start, const pg_ar_fusion* f,
+                        float* out_sum_logp, pg_stream stream) {
+  if (!h) return set_error(PG_ERR_ARG, "pg_ar_loglik_prefix: null handle");
+  if (!h->loaded) return fail(h, PG_ERR_STATE, "pg_ar_loglik_prefix: weights not loaded");
+  if (h->desc.arch != PG_ARCH_TRANCEPTION) return fail(h, PG_ERR_STATE, "pg_ar_loglik_prefix: handle is not a Tranception model");
+  if (h->prefix_T <= 0) return fail(h, PG_ERR_STATE, "pg_ar_loglik_prefix: no wild-type prefix recorded (call pg_ar_prefix_begin first)");
+  if (start <= 0 || start % 128 || start >= h->prefix_T) return fail(h, PG_ERR_ARG, "pg_ar_loglik_prefix: start must be a positive multiple of 128 below the recorded length");
+  if (B < 0 || T <= 0) return fail(h, PG_ERR_ARG, "pg_ar_loglik_prefix: bad B/T");
+  if (B == 0) return PG_OK;
+  if (!ids || !lens || !out_sum_logp) return fail(h, PG_ERR_ARG, "pg_ar_loglik_prefix: null buffer");
+  if (start + T > h->desc.max_positions) return fail(h, PG_ERR_ARG, "pg_ar_loglik_prefix: sequence longer than n_ctx");
+  if (T > h->max_rows) return fail(h, PG_ERR_ARG, "pg_ar_loglik_prefix: suffix longer than workspace");
+  ArFusion base;
+  int rc = ar_fusion_args(h, f, &base);
+  if (rc) return rc;
+  PG_CUDA_OK(cudaSetDevice(h->desc.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long per = h->max_rows / T;
+  for (int b0 = 0; b0 < B; b0 += static_cast<int>(per)) {
+    const int Bc = (B - b0) < per ? (B - b0) : static_cast<int>(per);
+    const long long off = static_cast<long long>(b0) * T;
+    rc = forward_tranception(h, ids + off, Bc, T, s, 2, start);
+    if (rc) return fail(h, rc, tls_error());
+    ProfScope ps(CAT_HEAD, s, 2);
+    ArFusion fc = base;
+    if (fc.prior_row) fc.prior_row += off;
+    if (fc.prior_row2) fc.prior_row2 += off;
+    if (fc.out_logprobs) fc.out_logprobs += off * h->desc.vocab;
+    rc = launch_ar_head(h->x, h->desc.embed_dim, Bc, T, h->desc.vocab, ids + off, lens + b0, h->lnag, h->lnab, h->embed, fc, h->tok_logp,
                         out_sum_logp + b0, s);
     if (rc) return fail(h, rc, tls_error());
   }

@@ -42,7 +42,8 @@ struct Smem3 {
 };
 
 struct Attn3Params {
-  int B, T, heads, nqt, nkb;
+  int B, T, heads, nqt, nkb;   // T = full sequence length (prefix + own rows); nqt = query tiles of the own rows; nkb = key blocks of T
+  int Tq, s_blocks;            // own rows per sequence; shared-prefix length / 128 (0 = no prefix: Tq == T)
   int d;
   long long lo_off;
   __half* out; long long ldo; long long out_lo_off;
@@ -63,7 +64,8 @@ __device__ __forceinline__ uint32_t cvt2h(float lo_elem, float hi_elem) {
 }
 
 template <int NP>
-__global__ void __launch_bounds__(384, 1) attn_tc3_kernel(const __grid_constant__ CUtensorMap tm, const Attn3Params p) {
+__global__ void __launch_bounds__(384, 1) attn_tc3_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmP,
+                                                          const Attn3Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
@@ -127,18 +129,21 @@ __global__ void __launch_bounds__(384, 1) attn_tc3_kernel(const __grid_constant_
       uint32_t phase = 0;
       int it = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-        const int qt = item % p.nqt, bh = item / p.nqt;
+        const int qt_l = item % p.nqt, bh = item / p.nqt;
+        const int qt = qt_l + p.s_blocks;  // tile index within the full sequence
         const int h = bh % p.heads, b = bh / p.heads;
-        const int row0 = b * p.T;
+        const int row0 = b * p.Tq;
         const int cq = h * 64, ck = p.d + h * 64, cv = 2 * p.d + h * 64;
         mbar_wait(q_empty, (it & 1) ^ 1);
         mbar_arrive_expect_tx(q_full, NP * TILE);
-        for (int pl = 0; pl < NP; ++pl) tma_load_2d(sQ + pl * TILE, &tm, q_full, cq + pl * static_cast<int>(p.lo_off), row0 + qt * QT);
-        auto load_block = [&](int col, int j) {
+        for (int pl = 0; pl < NP; ++pl) tma_load_2d(sQ + pl * TILE, &tm, q_full, cq + pl * static_cast<int>(p.lo_off), row0 + qt_l * QT);
+        auto load_block = [&](int col, int j) {  // key block j of the full sequence: shared prefix rows or this sequence's own rows
           mbar_wait(&kv_empty[slot], phase ^ 1);
           mbar_arrive_expect_tx(&kv_full[slot], NP * TILE);
+          const CUtensorMap* src = j < p.s_blocks ? &tmP : &tm;
+          const int r = j < p.s_blocks ? j * KT : row0 + (j - p.s_blocks) * KT;
           for (int pl = 0; pl < NP; ++pl)
-            tma_load_2d(sKV + (slot * NP + pl) * TILE, &tm, &kv_full[slot], col + pl * static_cast<int>(p.lo_off), row0 + j * KT);
+            tma_load_2d(sKV + (slot * NP + pl) * TILE, src, &kv_full[slot], col + pl * static_cast<int>(p.lo_off), r);
           if (++slot == NSLOT) { slot = 0; phase ^= 1; }
         };
         const int nkb = item_nkb(qt);
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc3_kernel(const __grid_constant_
       const uint32_t q_addr = smem_u32(sQ);
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
         mbar_wait(q_full, it & 1);
-        const int nkb = item_nkb(item % p.nqt);
+        const int nkb = item_nkb(item % p.nqt + p.s_blocks);
         int jq = 0;  // next key block of this item whose QK has not been issued
         auto issue_qk = [&]() {
           const uint32_t buf = qkn % NBUF;
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc3_kernel(const __grid_constant_
     uint32_t n = 0;  // running key-block number (same count as the MMA thread's)
     int it = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-      const int qt = item % p.nqt, bh = item / p.nqt;
+      const int qt = item % p.nqt + p.s_blocks, bh = item / p.nqt;
       const int h = bh % p.heads, b = bh / p.heads;
       const int nkb = item_nkb(qt);
       const float slope = p.alibi_slopes ? p.alibi_slopes[h] : 0.f;
@@ -365,7 +370,8 @@ __global__ void __launch_bounds__(384, 1) attn_tc3_kernel(const __grid_constant_
       const int qidx = qt * QT + row;
       if (live && qidx < p.T) {
         const float rl = 1.f / l;
-        __half* orow = p.out + (static_cast<long long>(b) * p.T + qidx) * p.ldo + h * 64 + g * 32;
+        const long long orow_idx = static_cast<long long>(b) * p.Tq + (qidx - p.s_blocks * QT);
+        __half* orow = p.out + orow_idx * p.ldo + h * 64 + g * 32;
         uint32_t hi[16], lo[16];
         float lf[32];
 #pragma unroll
@@ -385,7 +391,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc3_kernel(const __grid_constant_
 #pragma unroll
           for (int u = 0; u < 4; ++u) l4[u] = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
         } else if (p.out_fmt == 2) {
-          uint8_t* f8 = reinterpret_cast<uint8_t*>(p.out + (static_cast<long long>(b) * p.T + qidx) * p.ldo + p.out_lo_off) + h * 64 + g * 32;
+          uint8_t* f8 = reinterpret_cast<uint8_t*>(p.out + orow_idx * p.ldo + p.out_lo_off) + h * 64 + g * 32;
           const float sh = p.out_scale, sl = p.out_scale * 2048.f;
           uint32_t w8l[8], w8h[8];
 #pragma unroll
@@ -421,9 +427,13 @@ int launch_attention_tc3(const AttnLaunch& a, cudaStream_t s) {
   if (a.ld % 8 || a.lo_off % 8 || a.ldo % 8 || a.out_lo_off % 8 || (reinterpret_cast<uintptr_t>(a.out) & 15))
     return set_error(PG_ERR_ARG, "attention_tc3: pitches must be multiples of 8 elements and out 16-byte aligned");
   if (a.q_begin != 0) return set_error(PG_ERR_ARG, "attention_tc3: q_begin is only supported by the mma.sync kernel");
+  if (a.prefix && (!a.causal || a.prefix_len <= 0 || a.prefix_len % KT))
+    return set_error(PG_ERR_ARG, "attention_tc3: a shared prefix needs causal attention and a length that is a multiple of 128");
   Attn3Params p{};
-  p.B = a.B; p.T = a.T; p.heads = a.heads; p.d = a.heads * 64;
-  p.nqt = (a.T + QT - 1) / QT; p.nkb = (a.T + KT - 1) / KT;
+  p.B = a.B; p.heads = a.heads; p.d = a.heads * 64;
+  p.Tq = a.T; p.s_blocks = a.prefix ? a.prefix_len / KT : 0;
+  p.T = a.T + p.s_blocks * KT;
+  p.nqt = (a.T + QT - 1) / QT; p.nkb = (p.T + KT - 1) / KT;
   p.lo_off = a.lo_off; p.out = a.out; p.ldo = a.ldo; p.out_lo_off = a.out_lo_off;
   p.causal = a.causal; p.alibi_slopes = a.alibi_slopes;
   p.out_fmt = a.out_fmt < 0 ? (a.out_lo_off > 0 ? 1 : 0) : a.out_fmt;
@@ -433,9 +443,14 @@ int launch_attention_tc3(const AttnLaunch& a, cudaStream_t s) {
   const int np = a.nseg == 3 ? 2 : 1;
   const uint64_t width = static_cast<uint64_t>(3) * p.d * np;
   if (np == 2 && a.lo_off != 3ll * p.d) return set_error(PG_ERR_ARG, "attention_tc3: lo planes must follow the hi planes (lo_off == 3*d)");
-  CUtensorMap tm;
+  CUtensorMap tm, tmP;
   int rc = make_tmap_f16_2d(&tm, a.qkv, static_cast<uint64_t>(a.B) * a.T, width, a.ld, 128, 64);
   if (rc) return rc;
+  tmP = tm;
+  if (a.prefix) {
+    rc = make_tmap_f16_2d(&tmP, a.prefix, static_cast<uint64_t>(a.prefix_len), width, a.ld, 128, 64);
+    if (rc) return rc;
+  }
   const long long nitems = static_cast<long long>(a.B) * a.heads * p.nqt;
   const int grid = nitems < num_sms() ? static_cast<int>(nitems) : num_sms();
   int dev = 0;
@@ -446,8 +461,8 @@ int launch_attention_tc3(const AttnLaunch& a, cudaStream_t s) {
     PG_CUDA_OK(cudaFuncSetAttribute(attn_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem3<2>::TOTAL));
     attr_set[dev] = true;
   }
-  if (np == 1) attn_tc3_kernel<1><<<grid, 384, Smem3<1>::TOTAL, s>>>(tm, p);
-  else attn_tc3_kernel<2><<<grid, 384, Smem3<2>::TOTAL, s>>>(tm, p);
+  if (np == 1) attn_tc3_kernel<1><<<grid, 384, Smem3<1>::TOTAL, s>>>(tm, tmP, p);
+  else attn_tc3_kernel<2><<<grid, 384, Smem3<2>::TOTAL, s>>>(tm, tmP, p);
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;
 }

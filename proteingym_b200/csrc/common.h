@@ -67,6 +67,10 @@ struct AttnLaunch {
   int q_begin = 0;  // first query row handled by this launch (mma.sync kernel only): rows [q_begin, T)
   int out_fmt = -1;        // -1: 1 if out_lo_off > 0 else 0; 2: e4m3 planes with out_scale (tcgen05 kernel only)
   float out_scale = 0.f;
+  // Exact prefix reuse (causal, tcgen05 kernel only): the B sequences hold rows [prefix_len, prefix_len + T) of longer sequences
+  // whose first prefix_len rows (a multiple of 128) are shared; their K and V live in `prefix` (one sequence, same pitch / planes).
+  const __half* prefix = nullptr;
+  int prefix_len = 0;
 };
 int launch_attention(const AttnLaunch& a, cudaStream_t s);
 
@@ -122,7 +126,7 @@ int launch_attn_single_query(const __half* qkv, int64_t ld, int64_t lo_off, cons
 int launch_gather_rows(const float* x, const int32_t* row_sel, int B, int T, int d, float* xc, cudaStream_t s);
 int launch_gather_embed(const int32_t* ids, const float* wte, long long rows, int d, int vocab, float* x, cudaStream_t s);
 int launch_qkv_conv(const __half* in, __half* out, int64_t ld, int64_t lo_off, int B, int T, int heads, const float* taps,
-                    float qscale, cudaStream_t s);
+                    float qscale, cudaStream_t s, const __half* prefix = nullptr);
 // Retrieval-prior fusion arguments of the autoregressive head (device pointers; see pg_ar_fusion in include/pgscore.h).
 struct ArFusion {
   const float* log_prior = nullptr; const int32_t* prior_row = nullptr; float alpha = 0.f;

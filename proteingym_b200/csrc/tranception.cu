@@ -162,9 +162,12 @@ __global__ void qkv_conv_kernel(const __half* __restrict__ in, __half* __restric
 // the 64 channels of one head, hence uniform in its conv group. Same FMA order as qkv_conv_kernel: bit-identical results.
 constexpr int CV_T = 64;
 constexpr int CV_C = 256;
+// `prefix` (optional): the 6 raw q/k/v rows that precede row 0 of every sequence (same pitch and planes) — the look-back of a
+// suffix whose earlier rows were computed elsewhere (exact wild-type-prefix reuse); null = start of sequence (zeros).
 template <int NP>
 __global__ void __launch_bounds__(128) qkv_conv2_kernel(const __half* __restrict__ in, __half* __restrict__ out, long long ld,
-                                                        long long lo_off, int T, int heads, const float* __restrict__ taps, float qscale) {
+                                                        long long lo_off, int T, int heads, const float* __restrict__ taps, float qscale,
+                                                        const __half* __restrict__ prefix) {
   extern __shared__ __align__(16) uint8_t cv_smem[];
   constexpr int ROWS = CV_T + 6;
   constexpr int ROWB = CV_C * 2;                      // bytes per staged row and plane
@@ -177,8 +180,12 @@ __global__ void __launch_bounds__(128) qkv_conv2_kernel(const __half* __restrict
     const int r = (id / (ROWB / 16)) % ROWS;
     const int pl = id / ((ROWB / 16) * ROWS);
     const int t = t0 - 6 + r;
-    const bool ok = t >= 0 && t < T;
+    bool ok = t >= 0 && t < T;
     const __half* g = in + (ok ? (row0 + t) * ld + c0 + ch * 8 + pl * lo_off : 0);
+    if (t < 0 && prefix != nullptr) {
+      ok = true;
+      g = prefix + static_cast<long long>(6 + t) * ld + c0 + ch * 8 + pl * lo_off;
+    }
     cp_async_16(sbase + (pl * ROWS + r) * ROWB + ch * 16, g, ok ? 16u : 0u);
   }
   cp_async_commit();
@@ -338,7 +345,7 @@ int launch_gather_embed(const int32_t* ids, const float* wte, long long rows, in
 }
 
 int launch_qkv_conv(const __half* in, __half* out, int64_t ld, int64_t lo_off, int B, int T, int heads, const float* taps,
-                    float qscale, cudaStream_t s) {
+                    float qscale, cudaStream_t s, const __half* prefix) {
   const long long n = static_cast<long long>(B) * ((T + CONV_TB - 1) / CONV_TB) * (3 * heads * 64 / 8);
   if (n <= 0) return PG_OK;
   if (heads % 4) return set_error(PG_ERR_ARG, "qkv_conv: heads must be a multiple of 4");
@@ -355,11 +362,12 @@ int launch_qkv_conv(const __half* in, __half* out, int64_t ld, int64_t lo_off, i
       PG_CUDA_OK(cudaFuncSetAttribute(qkv_conv2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (CV_T + 6) * CV_C * 2));
       attr[dev] = true;
     }
-    if (np == 2) qkv_conv2_kernel<2><<<grid, 128, smem, s>>>(in, out, ld, lo_off, T, heads, taps, qscale);
-    else qkv_conv2_kernel<1><<<grid, 128, smem, s>>>(in, out, ld, lo_off, T, heads, taps, qscale);
+    if (np == 2) qkv_conv2_kernel<2><<<grid, 128, smem, s>>>(in, out, ld, lo_off, T, heads, taps, qscale, prefix);
+    else qkv_conv2_kernel<1><<<grid, 128, smem, s>>>(in, out, ld, lo_off, T, heads, taps, qscale, prefix);
     PG_CUDA_OK(cudaGetLastError());
     return PG_OK;
   }
+  if (prefix) return set_error(PG_ERR_UNSUPPORTED, "qkv_conv: prefix look-back is only implemented in the tiled kernel");
   qkv_conv_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(in, out, ld, lo_off, B, T, heads, taps, qscale);
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;

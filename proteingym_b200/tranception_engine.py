@@ -302,20 +302,145 @@ class TranceptionScorer:
         out = pd.DataFrame(recs, columns=["mutated_sequence", "sliced_mutated_sequence", "window_start", "window_end"])
         return out.drop_duplicates().reset_index(drop=True)
 
+    # ------------------------------------------------------------------------------------------------------------
+    # Exact wild-type-prefix reuse (include/pgscore.h: pg_ar_prefix_begin / pg_ar_loglik_prefix). A mutant slice that has the same
+    # length as the wild type cut with the same window shares every token before its first change with it; with the attention tile
+    # of 128 rows, all rows before start = 128 * (first_changed_token // 128) are taken from ONE wild-type pass per window.
+    prefix_reuse = os.environ.get("PG_PREFIX_REUSE", "1") != "0"
+    PREFIX_TILE = 128
+    reuse_rows = None  # [token rows a plain pass would run, token rows actually run], accumulated over calls (bench / tests)
+
+    def _logprobs_with_reuse(self, strings, windows, wts, flip, prior_kw):
+        """``sequence_logprobs(strings)`` where ``wts[i]`` is the wild-type string scored in the same window as strings[i] (or None).
+        Strings eligible for reuse are grouped by (wild type, start) and scored as suffixes; the rest take the plain path."""
+        n = len(strings)
+        out = np.zeros(n, dtype=np.float32)
+        tile = self.PREFIX_TILE
+        groups, plain = {}, []
+        for i, (x, w) in enumerate(zip(strings, wts)):
+            start = 0
+            if (self.prefix_reuse and w is not None and x != w and len(x) == len(w) and len(x) + 2 > tile
+                    and not any(c in "XBJZ" for c in x) and not any(c in "XBJZ" for c in w)):  # those are re-drawn at random per call
+                diff = next((k for k, (c, e) in enumerate(zip(x, w)) if c != e), len(x))
+                start = ((1 + diff) // tile) * tile            # token index of the first change is 1 + diff ([CLS] is token 0)
+            if start > 0:
+                groups.setdefault((w, windows[i], start), []).append(i)
+            else:
+                plain.append(i)
+        rows_full = sum(len(x) + 2 for x in strings)
+        rows_run = sum(len(strings[i]) + 2 for i in plain)
+        if plain:
+            out[plain] = self.sequence_logprobs([strings[i] for i in plain], windows=[windows[i] for i in plain], flip=flip, **prior_kw)
+        by_wt = {}
+        for (w, win, start), members in groups.items():
+            by_wt.setdefault((w, win), []).append((start, members))
+        for (w, win), lst in by_wt.items():
+            rows_run += len(w) + 2
+            wt_tok, wt_rows = self._prefix_begin(w, win, flip, prior_kw)
+            csum = np.concatenate([[0.0], np.cumsum(wt_tok.astype(np.float64))])    # csum[k] = sum of rows 0 .. k-1
+            for start, members in sorted(lst):
+                rows_run += len(members) * (len(w) + 2 - start)
+                suffix = self._prefix_suffix([strings[i] for i in members], win, start, flip, prior_kw)
+                for i, sfx in zip(members, suffix):
+                    tok_s = TOK.get(strings[i][start - 1], 0)                         # token `start` of [CLS] x [SEP] is character start-1
+                    out[i] = np.float32(csum[start - 1] + float(wt_rows[start - 1, tok_s]) + float(sfx))
+        if self.reuse_rows is None:
+            self.reuse_rows = [0, 0]
+        self.reuse_rows[0] += rows_full
+        self.reuse_rows[1] += rows_run
+        return out
+
+    def _fusion(self, prior_kw, win, T, flip, n=1):
+        """(PgArFusion, keep-alive tensors, prow, prow2) for ``n`` identical rows of T tokens in window ``win``."""
+        prior, prior2 = prior_kw.get("prior"), prior_kw.get("prior2")
+        keep = []
+        if prior is None:
+            return None, keep, None, None
+        msa_start = prior_kw.get("msa_start", 0)
+        msa_end = prior_kw.get("msa_end")
+        msa_end = prior.shape[0] if msa_end is None else msa_end
+        beta = prior_kw.get("beta", 0.0)
+        nonfocus = None
+        if prior2 is not None and prior_kw.get("nonfocus_fallback") and beta > 0:
+            nonfocus = np.asarray(prior2)[:, 5:].min(axis=1) == -np.inf
+        prow = np.full((T,), -1, dtype=np.int32)
+        prow2 = np.full((T,), -1, dtype=np.int32) if prior2 is not None else None
+        prior_rows(prow, prow2, win[0], win[1], msa_start, msa_end, flip, nonfocus)
+        return (prior, prior2, beta), keep, prow, prow2
+
+    def _prefix_begin(self, wt, win, flip, prior_kw):
+        """Wild-type pass that records the prefix caches -> (token log-probs [T], fused rows [T, vocab]) as numpy."""
+        T = len(wt) + 2
+        ids, _ = tokenize_batch([replace_ambiguous(wt)], T)
+        d_ids = torch.from_numpy(ids).to(self.device)
+        meta, _, prow, prow2 = self._fusion(prior_kw, win, T, flip)
+        d_tok = torch.zeros(T, dtype=torch.float32, device=self.device)
+        d_rows = torch.zeros((T, self.vocab), dtype=torch.float32, device=self.device)
+        f, keep = self._fusion_struct(meta, prow[None] if prow is not None else None, prow2[None] if prow2 is not None else None, prior_kw, d_rows)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.pg_ar_prefix_begin(self.handle, d_ids.data_ptr(), T, C.byref(f), d_tok.data_ptr(), stream), self.handle)
+        return d_tok.cpu().numpy(), d_rows.cpu().numpy()
+
+    def _fusion_struct(self, meta, prow, prow2, prior_kw, d_rows=None):
+        keep = []
+
+        def dev(a, dt):
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.device)
+            keep.append(t)
+            return t
+        f = _lib.PgArFusion()
+        f.alpha = float(prior_kw.get("alpha", 0.6))
+        f.first_col = int(prior_kw.get("first_col", 0))
+        if meta is not None:
+            prior, prior2, beta = meta
+            f.log_prior = dev(prior, np.float32).data_ptr()
+            f.prior_row = dev(prow, np.int32).data_ptr()
+            if prior2 is not None:
+                f.log_prior2 = dev(prior2, np.float32).data_ptr()
+                f.prior_row2 = dev(prow2, np.int32).data_ptr()
+                f.beta = float(beta)
+        if d_rows is not None:
+            f.out_logprobs = d_rows.data_ptr()
+        return f, keep
+
+    def _prefix_suffix(self, seqs, win, start, flip, prior_kw, chunk_rows=1 << 17):
+        """Suffix sums (rows >= start) of equal-length strings sharing tokens 0 .. start-1 with the recorded wild type."""
+        T = len(seqs[0]) + 2
+        Ts = T - start
+        meta, _, prow, prow2 = self._fusion(prior_kw, win, T, flip)
+        out = np.zeros(len(seqs), dtype=np.float32)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        per = max(1, chunk_rows // Ts)
+        for i in range(0, len(seqs), per):
+            part = seqs[i:i + per]
+            ids, _ = tokenize_batch([replace_ambiguous(x) for x in part], T)
+            d_ids = torch.from_numpy(np.ascontiguousarray(ids[:, start:])).to(self.device)
+            d_lens = torch.full((len(part),), Ts, dtype=torch.int32, device=self.device)
+            pr = np.repeat(prow[None, start:], len(part), axis=0) if prow is not None else None
+            pr2 = np.repeat(prow2[None, start:], len(part), axis=0) if prow2 is not None else None
+            f, keep = self._fusion_struct(meta, pr, pr2, prior_kw)
+            d_out = torch.empty(len(part), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.pg_ar_loglik_prefix(self.handle, d_ids.data_ptr(), d_lens.data_ptr(), len(part), Ts, start, C.byref(f),
+                                                    d_out.data_ptr(), stream), self.handle)
+            out[i:i + len(part)] = d_out.cpu().numpy()
+        return out
+
     shard = None  # (rank, world) with an initialised torch.distributed group: split the sequence rows of each direction over the ranks
 
-    def _sharded_logprobs(self, strings, windows, reverse, prior_kw):
+    def _sharded_logprobs(self, strings, windows, reverse, prior_kw, wts=None):
         """``sequence_logprobs`` over all ``strings``; with ``self.shard`` set, every rank scores a strided subset (rows are sorted
         by length inside sequence_logprobs, so a stride balances the padded work) and one all-gather completes the vector
         (the mutant row is the unit for Tranception). A sequence's value does not depend on what it is batched with,
         so the result is the same for any world size."""
+        if wts is None:
+            wts = [None] * len(strings)
         if self.shard is None or self.shard[1] <= 1:
-            return self.sequence_logprobs(strings, windows=windows, flip=reverse, **prior_kw)
+            return self._logprobs_with_reuse(strings, windows, wts, reverse, prior_kw)
         import torch.distributed as dist
         rank, world = self.shard
         n = len(strings)
         mine = list(range(rank, n, world))
-        local = self.sequence_logprobs([strings[i] for i in mine], windows=[windows[i] for i in mine], flip=reverse, **prior_kw)
+        local = self._logprobs_with_reuse([strings[i] for i in mine], [windows[i] for i in mine], [wts[i] for i in mine], reverse, prior_kw)
         width = (n + world - 1) // world
         dev = self.device if dist.get_backend() == "nccl" else torch.device("cpu")
         buf = torch.zeros(width, dtype=torch.float32, device=dev)
@@ -332,7 +457,12 @@ class TranceptionScorer:
         strings = [s[::-1] for s in sl["sliced_mutated_sequence"]] if reverse else list(sl["sliced_mutated_sequence"])
         windows = list(zip(sl["window_start"], sl["window_end"]))
         sc = sl.copy()
-        sc["score"] = self._sharded_logprobs(strings, windows, reverse, prior_kw).astype(np.float32)
+        # wild type cut with the same window, in scoring direction (None when the slice has no such partner, e.g. sliding windows)
+        wt_by_win = {(a, b): (x[::-1] if reverse else x) for ms, x, a, b in zip(sl["mutated_sequence"], sl["sliced_mutated_sequence"],
+                                                                                sl["window_start"], sl["window_end"]) if ms == target_seq}
+        wts = [None if ms == target_seq or scoring_window != "optimal" else wt_by_win.get((a, b))
+               for ms, a, b in zip(sl["mutated_sequence"], sl["window_start"], sl["window_end"])]
+        sc["score"] = self._sharded_logprobs(strings, windows, reverse, prior_kw, wts).astype(np.float32)
         if scoring_window == "sliding":
             sc = sc[["mutated_sequence", "score"]].groupby("mutated_sequence").sum().reset_index()
         sc["score"] = sc["score"] / sc["mutated_sequence"].map(len)

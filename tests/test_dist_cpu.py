@@ -115,7 +115,7 @@ def _worker_tranception_rows(rank, world, port, q):
     torch.set_num_threads(4)
     from conftest import GOLDEN
     from cpu_trancepteve import CpuTranceptEVE
-    from trancepteve_cases import CASES, make_inputs
+    from trancepteve_cases import SMALL_CASES as CASES, make_inputs
     name = "trancepteve_long"
     case = CASES[name]
     gd = os.path.join(GOLDEN, name)

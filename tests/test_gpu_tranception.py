@@ -56,6 +56,69 @@ def test_score_mutants_matches_reference_hybrid_golden(name):
         assert np.abs(got[c].to_numpy(dtype=np.float64) - ref[c].to_numpy(dtype=np.float64)).max() < TOL, c
 
 
+@pytest.mark.parametrize("name", ["tranception_L_subs", "tranception_L_indels", "tranception_L_long"])
+def test_true_size_tranception_l_matches_reference_class(name):
+    """BASELINE config 4 architecture at TRUE SIZE (36 x 1280, 20 heads): scores of the unmodified TranceptionLMHeadModel
+    (oracle/gen_golden_trancepteve.py truesize) — substitutions incl. multi-mutants, ragged indels, a > n_ctx protein."""
+    meta, arch, st, dms, ref = load(name)
+    for reuse in (True, False):
+        sc = make_scorer(arch, st, max_rows=32768)
+        sc.prefix_reuse = reuse
+        got = sc.score_mutants(dms, meta["target_seq"], indel_mode=meta["indel_mode"], scoring_window=meta["scoring_window"])
+        rows = sc.reuse_rows
+        sc.close()
+        assert list(got[got.columns[0]]) == list(ref[ref.columns[0]])
+        err = max(np.abs(got[c].to_numpy(dtype=np.float64) - ref[c].to_numpy(dtype=np.float64)).max()
+                  for c in ("avg_score_L_to_R", "avg_score_R_to_L", "avg_score"))
+        print(f"\n{name} (prefix reuse {reuse}, token rows run / plain = {rows}): max |score - reference| = {err:.2e}")
+        assert err < TOL
+
+
+@pytest.mark.parametrize("precision", ["f16f8", "f16"])
+def test_prefix_reuse_equals_plain_path(precision):
+    """Exact wild-type-prefix reuse (pg_ar_prefix_begin / pg_ar_loglik_prefix): same scores as the plain path — the rows are
+    bit-identical, only the per-sequence summation is split — and fewer token rows run. With and without a retrieval prior."""
+    arch = synth.TranceptionArch(2, 256, 4, 512)
+    st = synth.make_tranception_state(arch, 11)
+    seq = synth.random_protein(420, 6)  # T = 422: group starts 0, 128, 256, 384
+    muts = synth.sample_mutants(seq, 120, 4, multi_frac=0.25) + [f"{seq[127]}128{'A' if seq[127] != 'A' else 'C'}",
+                                                                  f"{seq[126]}127{'A' if seq[126] != 'A' else 'C'}"]  # first change at / next to a tile edge
+    dms = pd.DataFrame({"mutant": muts, "mutated_sequence": [synth.apply_mutant(seq, m) for m in muts]})
+    rng = np.random.RandomState(1)
+    prior = np.log(rng.dirichlet(np.ones(25), size=420)).astype(np.float32)
+    for kw in ({}, dict(log_prior=prior, retrieval_inference_weight=0.6, MSA_start=30, MSA_end=400)):
+        res = {}
+        for reuse in (True, False):
+            sc = make_scorer(arch, st, precision)
+            sc.prefix_reuse = reuse
+            res[reuse] = (sc.score_mutants(dms, seq, **kw), sc.reuse_rows)
+            sc.close()
+        a, b = res[True][0], res[False][0]
+        assert list(a["mutated_sequence"]) == list(b["mutated_sequence"])
+        for c in ("avg_score_L_to_R", "avg_score_R_to_L", "avg_score"):
+            assert np.abs(a[c].to_numpy(dtype=np.float64) - b[c].to_numpy(dtype=np.float64)).max() < 2e-6, c
+        full, run = res[True][1]
+        assert run < 0.8 * full and res[False][1][1] == res[False][1][0]
+
+
+def test_prefix_reuse_rejects_bad_calls():
+    import ctypes as C
+    from proteingym_b200 import _lib
+    arch = synth.TranceptionArch(1, 256, 4, 256)
+    sc = make_scorer(arch, synth.make_tranception_state(arch, 2))
+    ids = torch.ones(300, dtype=torch.int32, device="cuda")
+    out = torch.zeros(300, device="cuda")
+    lens = torch.full((2,), 44, dtype=torch.int32, device="cuda")
+    lib = sc.lib
+    assert lib.pg_ar_loglik_prefix(sc.handle, ids.data_ptr(), lens.data_ptr(), 2, 44, 128, None, out.data_ptr(), None) == 3  # nothing recorded
+    _lib.check(lib.pg_ar_prefix_begin(sc.handle, ids.data_ptr(), 300, None, out.data_ptr(), None), sc.handle)
+    for start in (0, 100, 384):  # not positive / not a multiple of 128 / not below the recorded length
+        assert lib.pg_ar_loglik_prefix(sc.handle, ids.data_ptr(), lens.data_ptr(), 2, 44, start, None, out.data_ptr(), None) == 1
+    assert lib.pg_ar_loglik_prefix(sc.handle, ids.data_ptr(), lens.data_ptr(), 2, 44, 256, None, out.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    sc.close()
+
+
 def test_retrieval_fusion_matches_oracle():
     arch = synth.TranceptionArch(1, 256, 4, 256)
     st = synth.make_tranception_state(arch, 4)

@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN
-from trancepteve_cases import CASES, make_inputs
+from trancepteve_cases import SMALL_CASES as CASES, make_inputs
 
 from proteingym_b200 import eve_prior, synth
 from proteingym_b200.msa_processing import MSAProcessing

@@ -20,7 +20,13 @@ CASES = {
                                  msa_recal=False, eve_recal=False, eve_seeds=[], n_samples=0, gappy=[], n_mut=60),
     "trancepteve_long": dict(arch=(1, 256, 4, 256, 64), L=150, msa=(20, 140), n_msa=120, kind="TranceptEVE", seq_thr=0.5, col_thr=1.0,
                              msa_recal=False, eve_recal=True, eve_seeds=[0], n_samples=2, gappy=[], n_mut=50),
+    # BASELINE config 5 at TRUE SIZE: Tranception-L (36 x 1280, 20 heads, ffn 5120) under the real TrancepteveLMHeadModel, both
+    # recalibrations on. GPU tests only (true_size: the CPU host-logic tests run the small cases).
+    "trancepteve_L_true": dict(arch=(36, 1280, 20, 5120, 1024), L=120, msa=(10, 110), n_msa=200, kind="TranceptEVE", seq_thr=0.5,
+                               col_thr=0.3, msa_recal=True, eve_recal=True, eve_seeds=[0], n_samples=3, gappy=[7, 33], n_mut=48,
+                               true_size=True),
 }
+SMALL_CASES = {n: c for n, c in CASES.items() if not c.get("true_size")}
 
 
 def make_inputs(case: dict, work: str, weights_file: str | None = None):
