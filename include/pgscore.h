@@ -200,7 +200,8 @@ typedef struct {
   void* out; int64_t ldo; int64_t out_lo_off;
   int32_t B, T, heads, nseg;
   int32_t causal; const float* alibi_slopes; /* NULL = none */
-  int32_t impl; /* 0 = the model's kernel (tcgen05/TMEM, P in place over S), 1 = mma.sync cross-check kernel */
+  int32_t impl; /* 0 = the model's kernel (tcgen05/TMEM, 2 CTAs per SM, 128x64 blocks), 1 = mma.sync cross-check kernel,
+                   2 = round-1 tcgen05 layout (1 CTA per SM, 128x128 blocks) */
   int32_t out_fmt; float out_scale; /* as pg_gemm_args (0 = auto); 2 only with impl 0 */
 } pg_attn_args;
 int pg_attention(const pg_attn_args* args, pg_stream stream);
@@ -228,7 +229,9 @@ int pg_profile_end(float* ms, int32_t* counts, int32_t ncat);
 
 /* Process-wide tuning knobs (benchmarks / numerics probes; defaults are the measured-best values):
  *   "gemm_kchunk"  longest run of K (elements) a hi*hi accumulation chunk covers before the epilogue adds it in RN fp32
- *                  (default 1024; 0 = no chunking). Also settable through the environment variable PG_GEMM_KCHUNK. */
+ *                  (default 1280; 0 = no chunking). Also settable through the environment variable PG_GEMM_KCHUNK.
+ *   "gemm_prefetch" k-blocks of L2 look-ahead the GEMM's TMA producer issues for the streamed A operand (default 8; 0 = off;
+ *                  PG_GEMM_PREFETCH). */
 int pg_set_tuning(const char* key, int32_t value);
 
 /* Build/version probe (also what the CPU-only test suite calls to check the library loads). */

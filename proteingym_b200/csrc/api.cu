@@ -18,6 +18,11 @@ int set_error(int code, const std::string& msg) {
   tls_error() = msg;
   return code;
 }
+int launch_attention_tc(const AttnLaunch& a, cudaStream_t s) {
+  static const bool old = getenv("PG_ATTN_TC3") != nullptr;
+  return old ? launch_attention_tc3(a, s) : launch_attention_tc4(a, s);
+}
+
 int num_sms() {  // of the current device (cached per ordinal: one process may hold handles on several GPUs)
   static int n[64] = {};
   int dev = 0;
@@ -808,6 +813,7 @@ int pg_score_mutants(const float* table, int32_t n_rows, int32_t vocab, const in
 int pg_set_tuning(const char* key, int32_t value) {
   if (!key) return set_error(PG_ERR_ARG, "pg_set_tuning: null key");
   if (std::string(key) == "gemm_kchunk") { set_gemm_kchunk(value); return PG_OK; }
+  if (std::string(key) == "gemm_prefetch") { set_gemm_prefetch(value); return PG_OK; }
   return set_error(PG_ERR_ARG, std::string("pg_set_tuning: unknown key ") + key);
 }
 
@@ -857,7 +863,8 @@ int pg_attention(const pg_attn_args* a, pg_stream stream) {
   l.out_fmt = a->out_fmt ? a->out_fmt : -1; l.out_scale = a->out_scale;
   ProfScope ps(CAT_OTHER, static_cast<cudaStream_t>(stream));
   if (a->impl == 0) return launch_attention_tc(l, static_cast<cudaStream_t>(stream));   // the model's kernel (tcgen05)
-  if (a->impl != 1) return set_error(PG_ERR_ARG, "pg_attention: impl must be 0 (tcgen05, the model's kernel) or 1 (mma.sync cross-check)");
+  if (a->impl == 2) return launch_attention_tc3(l, static_cast<cudaStream_t>(stream));  // round-1 tcgen05 layout (A/B reference)
+  if (a->impl != 1) return set_error(PG_ERR_ARG, "pg_attention: impl must be 0 (the model's tcgen05 kernel), 1 (mma.sync cross-check) or 2 (round-1 tcgen05 layout)");
   if (l.out_fmt == 2) return set_error(PG_ERR_UNSUPPORTED, "pg_attention: the mma.sync cross-check kernel writes fp16 planes only");
   return launch_attention(l, static_cast<cudaStream_t>(stream));
 }

@@ -53,7 +53,8 @@ struct GemmLaunch {
   float out_scale = 0.f;          // out_fmt 2: s of the GEMM that will consume `out`
 };
 int launch_gemm(const GemmLaunch& g, cudaStream_t s);
-void set_gemm_kchunk(int v);  // tuning: see gemm_tc.cu
+void set_gemm_kchunk(int v);    // tuning: see gemm_tc.cu
+void set_gemm_prefetch(int v);
 
 // fmt / scale as above (fmt 0 when lo_off == 0).
 int launch_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int rows, int d, __half* out,
@@ -116,8 +117,9 @@ int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
 // General form: elem_bytes 2 (fp16) / 4 (fp32) / 1 (bytes), swizzle 128 or 64 bytes. Encoded maps are cached per host thread.
 int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
                  int elem_bytes, int swizzle);
-int launch_attention_tc3(const AttnLaunch& a, cudaStream_t s);  // tcgen05/TMEM attention (attention_tc3.cu): the model's kernel
-inline int launch_attention_tc(const AttnLaunch& a, cudaStream_t s) { return launch_attention_tc3(a, s); }
+int launch_attention_tc4(const AttnLaunch& a, cudaStream_t s);  // tcgen05/TMEM attention, 2 CTAs/SM, 128x64 blocks (attention_tc4.cu): the model's kernel
+int launch_attention_tc3(const AttnLaunch& a, cudaStream_t s);  // round-1 layout: 1 CTA/SM, 128x128 blocks, row split over two threads (attention_tc3.cu)
+int launch_attention_tc(const AttnLaunch& a, cudaStream_t s);   // the model's dispatch: tc4 unless PG_ATTN_TC3=1 (A/B switch)
 }  // namespace pg
 
 namespace pg {

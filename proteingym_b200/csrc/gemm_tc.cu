@@ -15,7 +15,7 @@
 // accumulation steps (DESIGN.md "hardware finding"). The K loop is therefore cut into CHUNKS: each chunk accumulates into one of
 // the two TMEM buffers from zero, and the epilogue warps add the chunks in registers in round-to-nearest fp32 (fixed order, so
 // results stay deterministic). The small-magnitude cross terms form chunk 0 (their own truncation is irrelevant), the hi*hi
-// product is split into pieces of <= kchunk (default 1024) along K. The same double-buffered TMEM that used to overlap the
+// product is split into pieces of <= kchunk (default 1280) along K. The same double-buffered TMEM that used to overlap the
 // epilogue of tile i with the MMAs of tile i+1 now also overlaps the read-out of chunk c with the MMAs of chunk c+1.
 //
 // Structure (one persistent CTA per SM, 384 threads, no clusters):
@@ -73,6 +73,7 @@ struct GemmKParams {
   float out_scale;        // out_fmt 2: s of the consuming GEMM (hi8 = e4m3(hi*s), lo8 = e4m3(lo*2^11*s))
   const float* rot_cos; const float* rot_sin; int rot_T; int rot_dim;
   int tiles_m, tiles_n;
+  int prefetch;           // k-blocks of L2 look-ahead for the A operand (0 = off)
 };
 
 // Exact-erf GELU (esm/modules.py:17-24): 0.5*x*(1+erf(x/sqrt2)) = 0.5*x + 0.5*|x|*erf(|x|/sqrt2).
@@ -305,6 +306,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
+        // L2 look-ahead cursor: walks the same (tile, segment, k-block) stream p.prefetch steps ahead of the loads and asks L2 for
+        // the A tile. A is streamed from HBM exactly once (the weights stay L2-resident), and the 4-stage ring alone covers only
+        // ~2000 cycles of latency: without the look-ahead the MMA thread waits on `full` a fifth of the time (ncu, r02).
+        int pf_tile = blockIdx.x, pf_s = 0, pf_kb = 0;
+        auto pf_step = [&]() {
+          if (pf_tile >= ntiles) return;
+          const GemmSeg sg = p.seg[pf_s];
+          tma_prefetch_l2_2d(sg.kind ? &tmA8 : &tmA, sg.a_col + pf_kb * (sg.kind ? 2 * BK : BK), (pf_tile / p.tiles_n) * BM);
+          if (++pf_kb == sg.nkb) {
+            pf_kb = 0;
+            if (++pf_s == p.nsegs) { pf_s = 0; pf_tile += gridDim.x; }
+          }
+        };
+        for (int i = 0; i < p.prefetch; ++i) pf_step();
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
           const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
           for (int s = 0; s < p.nsegs; ++s) {
@@ -313,6 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const CUtensorMap* mb = sg.kind ? &tmB8 : &tmB;
             const int step = sg.kind ? 2 * BK : BK;  // 128 B of a row: 64 fp16 or 128 e4m3
             for (int kb = 0; kb < sg.nkb; ++kb) {
+              if (p.prefetch) pf_step();
               mbar_wait(&empty[stage], phase ^ 1);
               mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
               tma_load_2d(smA + stage * A_BYTES, ma, &full[stage], sg.a_col + kb * step, m_blk * BM);
@@ -510,17 +526,25 @@ int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
   return make_tmap_2d(m, ptr, rows, cols, ld, box_rows, box_cols, 2, 128);
 }
 
-// Longest run of K one hi*hi chunk accumulates before the epilogue takes it over (see the header). Default 1024; the environment
+// Longest run of K one hi*hi chunk accumulates before the epilogue takes it over (see the header). Default 1280; the environment
 // variable PG_GEMM_KCHUNK or pg_set_tuning("gemm_kchunk", v) override it; 0 = no chunking (round-1 behaviour, for the probe).
-static int g_kchunk = -1;
+static int g_kchunk = -1, g_prefetch = -1;
 int gemm_kchunk() {
   if (g_kchunk < 0) {
     const char* e = getenv("PG_GEMM_KCHUNK");
-    g_kchunk = e ? atoi(e) : 1024;
+    g_kchunk = e ? atoi(e) : 1280;
   }
   return g_kchunk < BK ? (1 << 30) : g_kchunk;
 }
 void set_gemm_kchunk(int v) { g_kchunk = v < 0 ? 0 : v; }
+int gemm_prefetch() {
+  if (g_prefetch < 0) {
+    const char* e = getenv("PG_GEMM_PREFETCH");
+    g_prefetch = e ? atoi(e) : 8;
+  }
+  return g_prefetch;
+}
+void set_gemm_prefetch(int v) { g_prefetch = v < 0 ? 0 : (v > 64 ? 64 : v); }
 
 int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(PG_ERR_ARG, "gemm: empty problem");
@@ -609,6 +633,7 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   p.rot_cos = g.rot_cos; p.rot_sin = g.rot_sin; p.rot_T = g.rot_T; p.rot_dim = g.rot_dim;
   p.tiles_m = (g.M + BM - 1) / BM;
   p.tiles_n = (g.N + BN - 1) / BN;
+  p.prefetch = gemm_prefetch();
   const int ntiles = p.tiles_m * p.tiles_n;
   const int grid = ntiles < num_sms() ? ntiles : num_sms();
   switch (g.epi) {

@@ -1,5 +1,5 @@
 """Run the attention parity cases of tests/test_gpu_parity.py (fp64 reference; causal + ALiBi included) and the throughput probe
-for ONE implementation id of pg_attention (1 mma.sync, 2 tcgen05, 3 tile-pair, 4 in-place P). Used to qualify an experimental
+for ONE implementation id of pg_attention (0 the model kernel: tcgen05 2 CTAs per SM; 1 mma.sync; 2 round-1 tcgen05 layout). Used to qualify an experimental
 kernel without putting it in the test suite: run it under `timeout`. Exit code 0 only if every case passes.
     python scripts/check_attention_impl.py 4"""
 import ctypes as C
@@ -20,7 +20,7 @@ CASES = [(2, 64, 2, 1, 0), (3, 100, 2, 1, 0), (2, 514, 4, 1, 0), (1, 1024, 2, 1,
 
 
 def main():
-    impl = int(sys.argv[1])
+    impl = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     ok = True
     for (B, T, H, nseg, causal) in CASES:
         try:
