@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, GPU session C: new attention kernel (2 CTAs/SM), L2 look-ahead in the GEMM, Tranception prefix reuse, true-size goldens.
 mkdir -p gpurun_out
-echo "== 1. kernel tests (attention impl 0/1/2, prefix reuse)"; timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tranception.py -m gpu -q -x -s -k "attention_matches or prefix or true_size_tranception" 2>&1 | grep -v "^$" | tail -25 | tee gpurun_out/c1_kernels.log
+echo "== 1. kernel tests (attention impl 0/1/2, prefix reuse)"; timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tranception.py -m gpu -q -s -k "attention_matches or prefix or true_size_tranception" 2>&1 | grep -v "^$" | tail -25 | tee gpurun_out/c1_kernels.log
 echo "== 2. bench A/B (3 steps, headline mode only)"
 for cfg in "" "PG_ATTN_TC3=1" "PG_GEMM_PREFETCH=0" "PG_GEMM_KCHUNK=1024" "PG_GEMM_PREFETCH=16"; do
   echo "-- $cfg"; env $cfg timeout 300 python bench.py --steps 3 --warmup 3 --no-other-workloads --no-cpu-baseline --no-other-modes 2> /dev/null | python -c "
