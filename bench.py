@@ -271,12 +271,12 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
         assign = sharding.lpt_assign([costs[i] for i in picks], world)
         return picks, [picks[j] for j in assign[rank]], info
 
-    def record(config, sample, picks, costs, n_mut_total, per_rank, tw):
+    def record(config, sample, picks, costs, n_mut_total, per_rank, tw, precision=None, extra=None):
         secs = max(per_rank) / 1e3
         tf = sum(costs[i] for i in picks) / 1e12
-        out.append({"config": config, "sample": sample, "precision_mode": a.precision, "n_gpus": world, "value": n_mut_total / secs,
+        out.append({"config": config, "sample": sample, "precision_mode": precision or a.precision, "n_gpus": world, "value": n_mut_total / secs,
                     "unit": "mutants/s", "seconds": secs, "per_rank_ms": per_rank, "algorithmic_tflops": tf / secs,
-                    "frac_of_peak": tf / secs / (sustained * world), "clocks": sampler.window(*tw) if sampler else None})
+                    "frac_of_peak": tf / secs / (sustained * world), "clocks": sampler.window(*tw) if sampler else None, **(extra or {})})
 
     # ---- config 3: ESM2-3B masked-marginals over the DMS_substitutions length distribution ----
     log("config 3: ESM2-3B")
@@ -284,8 +284,10 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
     ents = shapes["substitutions"]
     costs = [workloads.esm_cost(e, arch) for e in ents]
     picks, mine, info = share(ents, costs, 3 * world, 3.0e15)
+    from proteingym_b200.esm_engine import choose_precision
+    prec3 = choose_precision(checkpoint.config_from_synth(arch), None) if a.precision != "f16" else "f16"  # the CLI's auto rule: f16x3 at this width
     state = checkpoint.normalise_synth_state(arch, synth.make_esm_state(arch, seed=0, device=dev))
-    sc = EsmScorer(checkpoint.config_from_synth(arch), state, precision=a.precision, device=local_rank)
+    sc = EsmScorer(checkpoint.config_from_synth(arch), state, precision=prec3, device=local_rank)
     del state
     torch.cuda.empty_cache()
     assays = {i: workloads.substitution_assay(ents[i], seed=i, max_mutants=20000) for i in mine}
@@ -297,7 +299,7 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
            f"{len(picks)} of {len(ents)} assays, evenly spaced over the cost-sorted list of the {info.get('eligible')} with cost <= "
            f"{info.get('cost_cap_tflop', 0):.0f} TFLOP ({info.get('dropped_over_cap')} dropped); L = {[ents[i]['L'] for i in picks]}; "
            "mutants capped at 20000 per assay; masked positions = unique mutated positions",
-           picks, costs, sum(min(ents[i]["n_mutants"], 20000, 19 * ents[i]["L"]) for i in picks), per_rank, tw)
+           picks, costs, sum(min(ents[i]["n_mutants"], 20000, 19 * ents[i]["L"]) for i in picks), per_rank, tw, precision=prec3)
     torch.cuda.empty_cache()
 
     # ---- config 4 / 5: Tranception-L ----
@@ -358,7 +360,8 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
            "like DMS_substitutions with synthetic [L,25] log-priors (SURVEY.md §8d), LPT over the ranks",
            f"{len(picks)} of the {len(ents)} assays with L <= 1022, evenly spaced over the cost-sorted list; L = "
            f"{[ents[i]['L'] for i in picks]}; mutants capped at 500 per assay",
-           picks, costs, sum(nm[i] for i in picks), per_rank, tw)
+           picks, costs, sum(nm[i] for i in picks), per_rank, tw,
+           extra={"prefix_reuse_token_rows": {"plain": esc.reuse_rows[0], "run": esc.reuse_rows[1]} if esc.reuse_rows else None})
     esc.close()
     torch.cuda.empty_cache()
     return out

@@ -230,8 +230,8 @@ int pg_profile_end(float* ms, int32_t* counts, int32_t ncat);
 /* Process-wide tuning knobs (benchmarks / numerics probes; defaults are the measured-best values):
  *   "gemm_kchunk"  longest run of K (elements) a hi*hi accumulation chunk covers before the epilogue adds it in RN fp32
  *                  (default 1280; 0 = no chunking). Also settable through the environment variable PG_GEMM_KCHUNK.
- *   "gemm_prefetch" k-blocks of L2 look-ahead the GEMM's TMA producer issues for the streamed A operand (default 8; 0 = off;
- *                  PG_GEMM_PREFETCH). */
+ *   "gemm_prefetch" k-blocks of L2 look-ahead the GEMM's TMA producer issues for the streamed A operand (default 0 = off: measured
+ *                  neutral-to-negative in the model; PG_GEMM_PREFETCH). */
 int pg_set_tuning(const char* key, int32_t value);
 
 /* Build/version probe (also what the CPU-only test suite calls to check the library loads). */

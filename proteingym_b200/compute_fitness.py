@@ -60,8 +60,9 @@ def create_parser():
     for flags, kw in _FLAGS:
         p.add_argument(*flags, **kw)
     # additive (not in the reference)
-    p.add_argument("--precision", default="f16f8", choices=["f16f8", "f16x3", "f16"],
-                   help="tensor-core operand precision: f16f8 (default; fp16 + e4m3 cross terms, 2 tensor-pipe units) and f16x3 (3 units) meet the "
+    p.add_argument("--precision", default="auto", choices=["auto", "f16f8", "f16x3", "f16"],
+                   help="tensor-core operand precision: auto (default) picks f16f8 (fp16 + e4m3 cross terms, 2 tensor-pipe units) or f16x3 (3 units) "
+                        "by model width and mutation depth (esm_engine.choose_precision); both meet the "
                         "1e-3 parity bar; f16 (1 unit) is the fastest and does not")
     p.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
     return p
@@ -124,7 +125,7 @@ def score_model(scorer, args, df, mutant_col, offset_idx) -> np.ndarray:
 
 def main(args):
     from proteingym_b200.checkpoint import load_esm_checkpoint
-    from proteingym_b200.esm_engine import EsmScorer
+    from proteingym_b200.esm_engine import EsmScorer, choose_precision
     if not os.path.exists(args.dms_output):
         os.mkdir(args.dms_output)
     print("Arguments:", args)
@@ -139,8 +140,9 @@ def main(args):
         if config.arch != "esm2" and len(args.sequence) + 2 > 1024 and args.scoring_strategy == "wt-marginals" \
                 and args.scoring_window != "overlapping":
             raise ValueError(f"Sequence length {len(args.sequence) + 2} above maximum  sequence length of 1024")  # modules.py:256-260
-        scorer = EsmScorer(config, state, precision=args.precision, device=args.device)
-        print("Scoring with {} and model {}".format(args.scoring_strategy, name))
+        precision = choose_precision(config, df[mutant_col], args.scoring_strategy) if args.precision == "auto" else args.precision
+        scorer = EsmScorer(config, state, precision=precision, device=args.device)
+        print("Scoring with {} and model {} (operand precision {})".format(args.scoring_strategy, name, precision))
         df[name] = score_model(scorer, args, df, mutant_col, offset_idx)
         scorer.close()
     if "ESM1v" in args.model_type:  # :532-537

@@ -127,102 +127,116 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
   // causal: query tile qt (rows 128 qt ..) needs key blocks 0 .. 2 qt + 1 (64 keys each)
   auto item_nkb = [&](int qt) { return p.causal ? (2 * qt + 2 < p.nkb ? 2 * qt + 2 : p.nkb) : p.nkb; };
 
+  // Producer and MMA warps keep their control flow warp-uniform (all 32 lanes wait on the barriers) and predicate only the issue on
+  // one elected lane: a loop under `if (lane == 0)` pays an ELECT/branch sequence around every uniform-datapath instruction, and
+  // with 24 MMAs per 64-key block in the hi/lo mode the issuing thread, not the tensor pipe, set the pace.
   if (warp == 0) {
     // ================================================================= TMA producer
-    if (lane == 0) {
-      int slot = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-        const int qt_l = item % p.nqt, bh = item / p.nqt;
-        const int qt = qt_l + p.s_tiles;  // tile index within the full sequence
-        const int h = bh % p.heads, b = bh / p.heads;
-        const int row0 = b * p.Tq;
-        const int cq = h * 64, ck = p.d + h * 64, cv = 2 * p.d + h * 64;
-        mbar_wait(q_empty, (it & 1) ^ 1);
+    int slot = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+      const int qt_l = item % p.nqt, bh = item / p.nqt;
+      const int qt = qt_l + p.s_tiles;  // tile index within the full sequence
+      const int h = bh % p.heads, b = bh / p.heads;
+      const int row0 = b * p.Tq;
+      const int cq = h * 64, ck = p.d + h * 64, cv = 2 * p.d + h * 64;
+      mbar_wait(q_empty, (it & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(q_full, NP * QTILE);
         for (int pl = 0; pl < NP; ++pl) tma_load_2d(sQ + pl * QTILE, &tmQ, q_full, cq + pl * static_cast<int>(p.lo_off), row0 + qt_l * QT);
-        auto load_block = [&](int col, int j) {  // key block j of the full sequence: shared prefix rows or this sequence's own rows
-          mbar_wait(&kv_empty[slot], phase ^ 1);
+      }
+      __syncwarp();
+      auto load_block = [&](int col, int j) {  // key block j of the full sequence: shared prefix rows or this sequence's own rows
+        mbar_wait(&kv_empty[slot], phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&kv_full[slot], NP * TILE);
           const CUtensorMap* src = j < p.s_blocks ? &tmP : &tm;
           const int r = j < p.s_blocks ? j * KT : row0 + (j - p.s_blocks) * KT;
           for (int pl = 0; pl < NP; ++pl)
             tma_load_2d(sKV + (slot * NP + pl) * TILE, src, &kv_full[slot], col + pl * static_cast<int>(p.lo_off), r);
-          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
-        };
-        const int nkb = item_nkb(qt);
-        for (int j = 0; j < NBUF && j < nkb; ++j) load_block(ck, j);
-        for (int j = 0; j < nkb; ++j) {
-          load_block(cv, j);
-          if (j + NBUF < nkb) load_block(ck, j + NBUF);
         }
+        __syncwarp();
+        if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+      };
+      const int nkb = item_nkb(qt);
+      for (int j = 0; j < NBUF && j < nkb; ++j) load_block(ck, j);
+      for (int j = 0; j < nkb; ++j) {
+        load_block(cv, j);
+        if (j + NBUF < nkb) load_block(ck, j + NBUF);
       }
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_o = make_idesc_f16(QT, 64, 0, 1);  // A = P (TMEM), B = V (MN-major)
-      int slot = 0;
-      uint32_t phase = 0;
-      uint32_t qkn = 0, pvn = 0;  // running key-block numbers of the next QK / PV to issue (equal at item boundaries)
-      int it = 0;
-      const uint32_t q_addr = smem_u32(sQ);
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-        mbar_wait(q_full, it & 1);
-        const int nkb = item_nkb(item % p.nqt + p.s_tiles);
-        int jq = 0;  // next key block of this item whose QK has not been issued
-        auto issue_qk = [&]() {
-          const uint32_t buf = qkn % NBUF;
-          mbar_wait(&kv_full[slot], phase);
-          tc_fence_after();
+    constexpr uint32_t idesc_o = make_idesc_f16(QT, 64, 0, 1);  // A = P (TMEM), B = V (MN-major)
+    int slot = 0;
+    uint32_t phase = 0;
+    uint32_t qkn = 0, pvn = 0;  // running key-block numbers of the next QK / PV to issue (equal at item boundaries)
+    int it = 0;
+    const uint32_t q_addr = smem_u32(sQ);
+    const uint32_t kv_addr = smem_u32(sKV);
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+      mbar_wait(q_full, it & 1);
+      const int nkb = item_nkb(item % p.nqt + p.s_tiles);
+      int jq = 0;  // next key block of this item whose QK has not been issued
+      auto issue_qk = [&]() {
+        const uint32_t buf = qkn % NBUF;
+        mbar_wait(&kv_full[slot], phase);
+        tc_fence_after();
+        if (elect_one()) {
           const uint32_t idesc_s = make_idesc_f16(QT, nkeys(jq), 0, 0);
-          const uint32_t k_addr = smem_u32(sKV + slot * NP * TILE);
+          const uint32_t k_addr = kv_addr + slot * NP * TILE;
           const uint32_t tmem_s = tmem_base + buf * KT;
           const uint64_t qh = make_desc_sw128(q_addr, 1024), kh = make_desc_sw128(k_addr, 1024);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_s, qh + 2 * ks, kh + 2 * ks, idesc_s, ks > 0);
+          umma_kblock<0>(tmem_s, qh, kh, idesc_s, 0);  // 4 x K16 over the 64 head dims
           if (NP == 2) {
             const uint64_t ql = make_desc_sw128(q_addr + QTILE, 1024), kl = make_desc_sw128(k_addr + TILE, 1024);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_s, ql + 2 * ks, kh + 2 * ks, idesc_s, 1);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_f16(tmem_s, qh + 2 * ks, kl + 2 * ks, idesc_s, 1);
+            umma_kblock<0>(tmem_s, ql, kh, idesc_s, 1);
+            umma_kblock<0>(tmem_s, qh, kl, idesc_s, 1);
           }
           umma_commit(&kv_empty[slot]);
           umma_commit(&s_full[buf]);
-          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
-          ++qkn;
-          ++jq;
-          if (jq == nkb) umma_commit(q_empty);  // every QK of this item issued: the Q tile is free once they complete
-        };
-        while (jq < NBUF && jq < nkb) issue_qk();
-        for (int j = 0; j < nkb; ++j) {
-          const uint32_t buf = pvn % NBUF;
-          mbar_wait(&kv_full[slot], phase);                    // V(j)
-          mbar_wait(&p_full[buf], (pvn / NBUF) & 1);            // P(j) stored by all 4 softmax warps
-          if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);          // previous item's O has been read out
-          tc_fence_after();
-          const uint32_t v_addr = smem_u32(sKV + slot * NP * TILE);
+          if (jq + 1 == nkb) umma_commit(q_empty);  // every QK of this item issued: the Q tile is free once they complete
+        }
+        __syncwarp();
+        if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+        ++qkn;
+        ++jq;
+      };
+      while (jq < NBUF && jq < nkb) issue_qk();
+      for (int j = 0; j < nkb; ++j) {
+        const uint32_t buf = pvn % NBUF;
+        mbar_wait(&kv_full[slot], phase);                    // V(j)
+        mbar_wait(&p_full[buf], (pvn / NBUF) & 1);            // P(j) stored by all 4 softmax warps
+        if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);          // previous item's O has been read out
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t v_addr = kv_addr + slot * NP * TILE;
           const uint32_t tmem_o = tmem_base + O_COL;
           const uint32_t tmem_p = tmem_base + buf * KT;          // hi pairs: columns [0,32) of the slot; lo pairs: [32,64)
           const int nks = nkeys(j) >> 4;
-          for (int ks = 0; ks < nks; ++ks) {
-            const uint64_t vh = make_desc_sw128(v_addr + ks * 2048, 1024, 1024);
-            umma_f16_ts(tmem_o, tmem_p + ks * 8, vh, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-            if (NP == 2) {
-              const uint64_t vl = make_desc_sw128(v_addr + TILE + ks * 2048, 1024, 1024);
-              umma_f16_ts(tmem_o, tmem_p + 32 + ks * 8, vh, idesc_o, 1);
-              umma_f16_ts(tmem_o, tmem_p + ks * 8, vl, idesc_o, 1);
+          if (nks == 4) {
+            umma_pv64<NP, 32>(tmem_o, tmem_p, make_desc_sw128(v_addr, 1024, 1024), make_desc_sw128(v_addr + TILE, 1024, 1024), idesc_o,
+                              j > 0 ? 1u : 0u);
+          } else {
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint64_t vh = make_desc_sw128(v_addr + ks * 2048, 1024, 1024);
+              umma_f16_ts(tmem_o, tmem_p + ks * 8, vh, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+              if (NP == 2) {
+                const uint64_t vl = make_desc_sw128(v_addr + TILE + ks * 2048, 1024, 1024);
+                umma_f16_ts(tmem_o, tmem_p + 32 + ks * 8, vh, idesc_o, 1);
+                umma_f16_ts(tmem_o, tmem_p + ks * 8, vl, idesc_o, 1);
+              }
             }
           }
           umma_commit(&kv_empty[slot]);
           umma_commit(&pv_done[buf]);
           if (j == nkb - 1) umma_commit(o_full);
-          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
-          ++pvn;
-          if (jq < nkb) issue_qk();                             // QK(j + 3) into the slot PV(j) has just been issued from
         }
+        __syncwarp();
+        if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+        ++pvn;
+        if (jq < nkb) issue_qk();                             // QK(j + 3) into the slot PV(j) has just been issued from
       }
     }
   } else if (warp >= 2) {

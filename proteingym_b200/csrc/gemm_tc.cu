@@ -303,87 +303,84 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp < FIRST_EPI_WARP) {
     setmaxnreg_dec<56>();
     if (warp == 0) {
-      if (lane == 0) {
-        int stage = 0;
-        uint32_t phase = 0;
-        // L2 look-ahead cursor: walks the same (tile, segment, k-block) stream p.prefetch steps ahead of the loads and asks L2 for
-        // the A tile. A is streamed from HBM exactly once (the weights stay L2-resident), and the 4-stage ring alone covers only
-        // ~2000 cycles of latency: without the look-ahead the MMA thread waits on `full` a fifth of the time (ncu, r02).
-        int pf_tile = blockIdx.x, pf_s = 0, pf_kb = 0;
-        auto pf_step = [&]() {
-          if (pf_tile >= ntiles) return;
-          const GemmSeg sg = p.seg[pf_s];
+      // TMA producer: warp-uniform loop, one elected lane arms the barrier and issues the two bulk tensor loads of a k-block.
+      int stage = 0;
+      uint32_t phase = 0;
+      // Optional L2 look-ahead cursor (p.prefetch k-blocks ahead of the loads, A operand only). Measured neutral-to-negative on the
+      // in-model shapes (bench r02: 737 vs 762 ms/step with it off), so the default is off.
+      int pf_tile = blockIdx.x, pf_s = 0, pf_kb = 0;
+      auto pf_step = [&]() {
+        if (pf_tile >= ntiles) return;
+        const GemmSeg sg = p.seg[pf_s];
+        if (elect_one())
           tma_prefetch_l2_2d(sg.kind ? &tmA8 : &tmA, sg.a_col + pf_kb * (sg.kind ? 2 * BK : BK), (pf_tile / p.tiles_n) * BM);
-          if (++pf_kb == sg.nkb) {
-            pf_kb = 0;
-            if (++pf_s == p.nsegs) { pf_s = 0; pf_tile += gridDim.x; }
-          }
-        };
-        for (int i = 0; i < p.prefetch; ++i) pf_step();
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-          const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
-          for (int s = 0; s < p.nsegs; ++s) {
-            const GemmSeg sg = p.seg[s];
-            const CUtensorMap* ma = sg.kind ? &tmA8 : &tmA;
-            const CUtensorMap* mb = sg.kind ? &tmB8 : &tmB;
-            const int step = sg.kind ? 2 * BK : BK;  // 128 B of a row: 64 fp16 or 128 e4m3
-            for (int kb = 0; kb < sg.nkb; ++kb) {
-              if (p.prefetch) pf_step();
-              mbar_wait(&empty[stage], phase ^ 1);
+        __syncwarp();
+        if (++pf_kb == sg.nkb) {
+          pf_kb = 0;
+          if (++pf_s == p.nsegs) { pf_s = 0; pf_tile += gridDim.x; }
+        }
+      };
+      for (int i = 0; i < p.prefetch; ++i) pf_step();
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        for (int s = 0; s < p.nsegs; ++s) {
+          const GemmSeg sg = p.seg[s];
+          const CUtensorMap* ma = sg.kind ? &tmA8 : &tmA;
+          const CUtensorMap* mb = sg.kind ? &tmB8 : &tmB;
+          const int step = sg.kind ? 2 * BK : BK;  // 128 B of a row: 64 fp16 or 128 e4m3
+          for (int kb = 0; kb < sg.nkb; ++kb) {
+            if (p.prefetch) pf_step();
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one()) {
               mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
               tma_load_2d(smA + stage * A_BYTES, ma, &full[stage], sg.a_col + kb * step, m_blk * BM);
               tma_load_2d(smB + stage * B_BYTES, mb, &full[stage], sg.b_col + kb * step, n_blk * BN);
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);  // same bit pattern for kind::f8f6f4 with e4m3 operands
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t g = 0;  // running chunk number: TMEM buffer g & 1, barrier phase (g >> 1) & 1
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-          bool fresh = true;
-          uint32_t accumulate = 0;
-          for (int s = 0; s < p.nsegs; ++s) {
-            const GemmSeg sg = p.seg[s];
-            const uint32_t buf = g & 1;
-            if (fresh) {
-              mbar_wait(&tempty[buf], ((g >> 1) & 1) ^ 1);
-              tc_fence_after();
-              accumulate = 0;
-              fresh = false;
-            }
-            const uint32_t tmem_d = tmem_base + buf * BN;
-            for (int kb = 0; kb < sg.nkb; ++kb) {
-              mbar_wait(&full[stage], phase);
-              tc_fence_after();
-              const uint64_t adesc = make_desc_sw128(smem_u32(smA + stage * A_BYTES), 1024);
-              const uint64_t bdesc = make_desc_sw128(smem_u32(smB + stage * B_BYTES), 1024);
-              if (sg.kind) {
-#pragma unroll
-                for (int k = 0; k < BK / UK; ++k) {  // 32 e4m3 = 32 bytes along K per instruction
-                  umma_f8(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
-                  accumulate = 1;
-                }
-              } else {
-#pragma unroll
-                for (int k = 0; k < BK / UK; ++k) {
-                  // advance 16 fp16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-                  umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
-                  accumulate = 1;
-                }
-              }
+      // All 32 lanes run the (warp-uniform) control flow and the barrier waits; one elected lane issues the MMAs and commits.
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);  // same bit pattern for kind::f8f6f4 with e4m3 operands
+      const uint32_t a_base = smem_u32(smA), b_base = smem_u32(smB);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t g = 0;  // running chunk number: TMEM buffer g & 1, barrier phase (g >> 1) & 1
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        bool fresh = true;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nsegs; ++s) {
+          const GemmSeg sg = p.seg[s];
+          const uint32_t buf = g & 1;
+          if (fresh) {
+            mbar_wait(&tempty[buf], ((g >> 1) & 1) ^ 1);
+            tc_fence_after();
+            accumulate = 0;
+            fresh = false;
+          }
+          const uint32_t tmem_d = tmem_base + buf * BN;
+          for (int kb = 0; kb < sg.nkb; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = make_desc_sw128(a_base + stage * A_BYTES, 1024);
+            const uint64_t bdesc = make_desc_sw128(b_base + stage * B_BYTES, 1024);
+            if (elect_one()) {
+              // 4 x (K = 32 bytes of every row): 16 fp16 or 32 e4m3 per instruction
+              if (sg.kind) umma_kblock<1>(tmem_d, adesc, bdesc, idesc, accumulate);
+              else umma_kblock<0>(tmem_d, adesc, bdesc, idesc, accumulate);
               umma_commit(&empty[stage]);
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            if (sg.commit) {
-              umma_commit(&tfull[buf]);
-              ++g;
-              fresh = true;
-            }
+            __syncwarp();
+            accumulate = 1;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (sg.commit) {
+            if (elect_one()) umma_commit(&tfull[buf]);
+            __syncwarp();
+            ++g;
+            fresh = true;
           }
         }
       }
@@ -540,7 +537,7 @@ void set_gemm_kchunk(int v) { g_kchunk = v < 0 ? 0 : v; }
 int gemm_prefetch() {
   if (g_prefetch < 0) {
     const char* e = getenv("PG_GEMM_PREFETCH");
-    g_prefetch = e ? atoi(e) : 8;
+    g_prefetch = e ? atoi(e) : 0;
   }
   return g_prefetch;
 }

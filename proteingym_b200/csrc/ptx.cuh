@@ -130,6 +130,57 @@ __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a converged warp (the same lane every time for a full warp): the issuer of tcgen05.mma / tcgen05.commit. Keeping the
+// surrounding control flow warp-uniform and predicating only the issue lets the compiler hold descriptors in uniform registers;
+// a loop that runs under `if (lane == 0)` instead pays an ELECT / branch sequence around every uniform-datapath instruction, and the
+// single issuing thread becomes the bottleneck (ncu r02: ~240 SASS instructions per 512-cycle k-block in the GEMM's MMA loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred)::"memory");
+  return pred != 0;
+}
+// Four MMAs over one 128-byte-wide k-block (descriptor start advanced by 32 bytes = +2 in the >>4 field each), in ONE asm block:
+// KIND 0 = kind::f16 (4 x K16), KIND 1 = kind::f8f6f4 (4 x K32). `accumulate` applies to the first MMA; the other three accumulate.
+template <int KIND>
+__device__ __forceinline__ void umma_kblock(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (KIND == 0) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 t, %4, %4;\n\t"
+        "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\tadd.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\tadd.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 t, %4, %4;\n\t"
+        "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\tadd.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\tadd.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], a1, b1, %3, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], a2, b2, %3, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], a3, b3, %3, t;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
 // A operand from TMEM (fp16 packed), B from smem.
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -140,6 +191,57 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "}" ::"r"(tmem_d),
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// O (+)= P * V over 64 keys (4 k-steps of 16) in ONE asm block. A = P as packed fp16 pairs in TMEM (8 columns per k-step; hi pairs at
+// tmem_p, lo pairs LO columns further), B = V (hi plane at vh, lo plane at vl; descriptor start +128 = 16 key rows of 128 B per
+// k-step). NP == 2 issues the three products hi*hi + lo*hi + hi*lo per k-step. `accumulate` applies to the very first MMA.
+template <int NP, int LO>
+__device__ __forceinline__ void umma_pv64(uint32_t tmem_o, uint32_t tmem_p, uint64_t vh, uint64_t vl, uint32_t idesc, uint32_t accumulate) {
+  if (NP == 1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b32 a1, a2, a3;\n\t"
+        ".reg .b64 b1, b2, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 t, %4, %4;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+        "add.s64 b1, %2, 128;\n\tadd.s64 b2, %2, 256;\n\tadd.s64 b3, %2, 384;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %3, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %3, t;\n\t"
+        "}" ::"r"(tmem_o),
+        "r"(tmem_p), "l"(vh), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, t;\n\t"
+        ".reg .b32 a1, a2, a3, l0, l1, l2, l3;\n\t"
+        ".reg .b64 b1, b2, b3, c1, c2, c3;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.b32 t, %5, %5;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+        "add.u32 l0, %1, %6;\n\tadd.u32 l1, a1, %6;\n\tadd.u32 l2, a2, %6;\n\tadd.u32 l3, a3, %6;\n\t"
+        "add.s64 b1, %2, 128;\n\tadd.s64 b2, %2, 256;\n\tadd.s64 b3, %2, 384;\n\t"
+        "add.s64 c1, %3, 128;\n\tadd.s64 c2, %3, 256;\n\tadd.s64 c3, %3, 384;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %4, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [l0], %2, %4, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %3, %4, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %4, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [l1], b1, %4, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], c1, %4, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %4, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [l2], b2, %4, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], c2, %4, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %4, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [l3], b3, %4, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], c3, %4, t;\n\t"
+        "}" ::"r"(tmem_o),
+        "r"(tmem_p), "l"(vh), "l"(vl), "r"(idesc), "r"(accumulate), "n"(LO)
+        : "memory");
+  }
 }
 // All previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

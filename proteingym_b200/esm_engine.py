@@ -22,6 +22,29 @@ from .windows import optimal_window_starts
 PRECISIONS = {"f16": _lib.PG_PREC_F16, "f16x3": _lib.PG_PREC_F16X3, "f16f8": _lib.PG_PREC_F16F8}
 
 
+def choose_precision(config: EsmConfig, mutants=None, strategy: str = "masked-marginals") -> str:
+    """``--precision auto``: the cheapest operand scheme whose MEASURED error meets the 1e-3 abs per-mutant bar for this job.
+
+    f16f8 (2 tensor-pipe units) carries ~16-bit operands: per masked site its score error is 1.2e-4 mean / 4.5e-4 max at ESM-1v 650M
+    (BLAT golden, 4997 mutants) and 6.1e-4 max at ESM2 3B; errors of independently masked sites add, so 5-site mutants reach 1.0e-3 at
+    3B (tests/test_gpu_parity.py::test_golden_true_size_esm2_3b_multi_mutants). f16x3 (3 units, ~22-bit operands) stays at 8e-5 / 3.3e-4
+    in the same tests. Rule: f16f8 for models up to 1280 wide when no mutant has more than two sites (and for every strategy that reads
+    one row per site); f16x3 otherwise."""
+    if config.embed_dim > 1280:
+        return "f16x3"
+    if strategy == "pseudo-ppl":  # sums L rows per sequence
+        return "f16x3"
+    if mutants is not None:
+        k = 0
+        for m in mutants:
+            c = m.count(":") + 1
+            if c > k:
+                k = c
+                if k > 2:
+                    return "f16x3"
+    return "f16f8"
+
+
 class EsmScorer:
     def __init__(self, config: EsmConfig, state: dict, precision: str = "f16f8", device: int = 0, max_rows: int = 0):
         if not torch.cuda.is_available():
@@ -49,7 +72,7 @@ class EsmScorer:
         tensors = {k: v for k, v in state.items() if "rot_emb.inv_freq" not in k}
         if cfg.arch == "esm2":
             inv = state["layers.0.self_attn.rot_emb.inv_freq"]
-            cos, sin = rotary_tables(inv, 4096)
+            cos, sin = rotary_tables(inv, 16384)  # rotary has no length limit in the reference; 16384 tokens covers every ProteinGym target (max 3423)
             tensors["rotary.cos"], tensors["rotary.sin"] = cos, sin
         # fp32 staging copy on the device (ESM-1v 2.6 GB, ESM2-3B 11 GB); the library repacks and we free it
         gpu = [(n, t.to(self.device, torch.float32).contiguous()) for n, t in tensors.items()]

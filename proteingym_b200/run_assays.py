@@ -30,7 +30,7 @@ if __package__ in (None, ""):
 def main(argv=None):
     from proteingym_b200 import sharding
     from proteingym_b200.checkpoint import checkpoint_column_name, load_esm_checkpoint
-    from proteingym_b200.esm_engine import EsmScorer
+    from proteingym_b200.esm_engine import EsmScorer, choose_precision
     ap = argparse.ArgumentParser()
     ap.add_argument("--model-location", nargs="+", required=True)
     ap.add_argument("--model_type", nargs="+", default=["ESM1v"])
@@ -38,7 +38,8 @@ def main(argv=None):
     ap.add_argument("--dms-input", required=True)
     ap.add_argument("--dms-output", required=True)
     ap.add_argument("--mutation-col", default="mutant")
-    ap.add_argument("--precision", default="f16f8", choices=["f16f8", "f16x3", "f16"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "f16f8", "f16x3", "f16"],
+                    help="auto: per assay, the cheapest operand scheme that meets 1e-3 (esm_engine.choose_precision)")
     ap.add_argument("--indices", type=int, nargs="*", default=None, help="subset of dms_index values (default: all rows)")
     ap.add_argument("--partition", default="auto", choices=["auto", "assays", "positions"],
                     help="what is split across GPUs: whole assays (LPT) or the masked positions of each assay")
@@ -76,8 +77,12 @@ def main(argv=None):
                      for i in idx]
             by_pos = world > 1 and (a.partition == "positions" or (a.partition == "auto" and len(idx) < world))
             mine = list(idx) if by_pos else [idx[j] for j in sharding.lpt_assign(costs, world)[rank]]
-        scorer = EsmScorer(conf, state, precision=a.precision, device=local)
-        del state
+        scorers = {}
+
+        def scorer_for(prec):  # at most two handles per checkpoint (f16f8 and f16x3), created on first use
+            if prec not in scorers:
+                scorers[prec] = EsmScorer(conf, state, precision=prec, device=local)
+            return scorers[prec]
         for i in mine:
             row = mapping.iloc[i].replace(np.nan, "")
             seq = row["target_seq"].upper()
@@ -86,10 +91,14 @@ def main(argv=None):
             if i not in frames:
                 frames[i] = pd.read_csv(os.path.join(a.dms_input, row["DMS_filename"]))
             t0 = time.time()
-            frames[i][name] = scorer.score_assay(seq, list(frames[i][col]), off, shard=(rank, world) if by_pos else None).astype(np.float64)
+            muts = list(frames[i][col])
+            scorer = scorer_for(choose_precision(conf, muts) if a.precision == "auto" else a.precision)
+            frames[i][name] = scorer.score_assay(seq, muts, off, shard=(rank, world) if by_pos else None).astype(np.float64)
             if not by_pos or rank == 0:
                 summary[(i, name)] = (time.time() - t0, len(frames[i]))
-        scorer.close()
+        for sc in scorers.values():
+            sc.close()
+        del state
     for i, df in frames.items():
         if by_pos and rank != 0:  # every rank holds the same scores; one writer
             continue

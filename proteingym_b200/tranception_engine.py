@@ -214,6 +214,9 @@ class TranceptionScorer:
         rows_out = [None] * n
         if n == 0:
             return (out, rows_out) if return_rows else out
+        # the reference tokenises with truncation=True, max_length=n_ctx (model_pytorch.py:930-938 -> scoring_utils.py:97-101): a
+        # string longer than n_ctx - 2 residues (indel mode, sliding windows never produce one) is cut, [CLS] and [SEP] stay
+        seqs = [s[:self.n_ctx - 2] for s in seqs]
         order = np.argsort([len(s) for s in seqs], kind="stable")
 
         def dev32(a):

@@ -584,15 +584,21 @@ def test_esm2_3b_true_size_rows_match_oracle():
     assert serr < TOL and err < 3e-3
 
 
-@pytest.mark.parametrize("mode", PARITY_MODES)
+@pytest.mark.parametrize("mode", ["auto", "f16f8"])
 def test_golden_true_size_esm2_3b_multi_mutants(mode):
     """BASELINE config 3 architecture at TRUE SIZE (ESM2 3B: 36 x 2560, 40 heads, ffn 10240, rotary) against the UNMODIFIED reference
     CLI (oracle/gen_golden.py esm2_3b): a 256-residue protein, 300 mutants of which 215 have 2-5 sites (the errors of independently
-    masked sites add up), and the reference's own log-prob rows at 42 positions."""
+    masked sites add up), and the reference's own log-prob rows at 42 positions.
+    `auto` (what the CLIs run: esm_engine.choose_precision -> f16x3 for a model this wide) must meet the 1e-3 bar on every mutant.
+    f16f8 is measured for the record: it meets the bar on single-site mutants and misses it on some 3-5-site ones at this size, which
+    is exactly why `auto` does not select it here."""
+    from proteingym_b200.esm_engine import choose_precision
     g = load_golden("esm2_3b_multi")
     arch, seq, df = g["arch"], g["seq"], g["df"]
     want = df[g["meta"]["ckpt_names"][0].split(".")[0]].to_numpy()
-    sc = scorer(arch, g["state"](), precision=mode, max_rows=32768)
+    prec = choose_precision(checkpoint.config_from_synth(arch), list(df["mutant"])) if mode == "auto" else mode
+    assert mode != "auto" or prec == "f16x3"
+    sc = scorer(arch, g["state"](), precision=prec, max_rows=32768)
     got = sc.score_assay(seq, list(df["mutant"]))
     pos = g["meta"]["table_positions"]
     tab = sc.masked_marginal_table(seq, positions=sorted(pos)).cpu().numpy()
@@ -600,10 +606,43 @@ def test_golden_true_size_esm2_3b_multi_mutants(mode):
     err = np.abs(got - want)
     nsites = df["mutant"].str.count(":").to_numpy() + 1
     terr = np.abs(tab[pos] - g["table"]).max()
-    print(f"\nESM2-3B true size {mode}: max|dscore|={err.max():.2e} (1 site {err[nsites == 1].max():.2e}, 5 sites {err[nsites == 5].max():.2e}) "
-          f"mean={err.mean():.2e} spearman={spearman(got, want):.6f} max|dlogp|={terr:.2e}")
-    assert err.max() < TOL and spearman(got, want) >= 0.999
-    assert terr < TOL
+    print(f"\nESM2-3B true size {mode} ({prec}): max|dscore|={err.max():.2e} (1 site {err[nsites == 1].max():.2e}, 5 sites "
+          f"{err[nsites == 5].max():.2e}) mean={err.mean():.2e} spearman={spearman(got, want):.6f} max|dlogp|={terr:.2e}")
+    assert spearman(got, want) >= 0.999
+    if mode == "auto":
+        assert err.max() < TOL and terr < 5e-4
+    else:
+        assert err[nsites == 1].max() < TOL and err.max() < 3e-3 and terr < TOL
+
+
+def test_multi_site_error_growth_650m_vs_oracle():
+    """How the per-mutant error grows with the number of mutated sites at ESM-1v 650M (true size, 96-residue protein, fp32 CPU oracle):
+    the measurement behind esm_engine.choose_precision. `auto` must meet 1e-3 for every depth; f16f8 must meet it up to two sites."""
+    from proteingym_b200.esm_engine import choose_precision
+    arch = synth.ESM1V_650M
+    st = synth.make_esm_state(arch, seed=0)
+    seq = synth.random_protein(96, 7)
+    rng = np.random.RandomState(5)
+    muts = {}
+    for k in (1, 2, 3, 5):
+        lst = []
+        for _ in range(150):
+            ps = sorted(rng.choice(96, size=k, replace=False))
+            lst.append(":".join(f"{seq[p]}{p + 1}{rng.choice([a for a in synth.AA20 if a != seq[p]])}" for p in ps))
+        muts[k] = lst
+    table = O.masked_marginal_table(O.load_state(st, "esm1v"), seq, "esm1v", arch.layers, arch.heads, batch=16)
+    cfg = checkpoint.config_from_synth(arch)
+    worst = {}
+    for prec in ("f16f8", "f16x3"):
+        sc = scorer(arch, st, precision=prec, max_rows=65536)
+        for k, lst in muts.items():
+            got = sc.score_assay(seq, lst).astype(np.float64)
+            worst[(prec, k)] = float(np.abs(got - O.score_mutants(lst, seq, table)).max())
+        sc.close()
+    print("\nmax |score - fp32 oracle| by sites, ESM-1v 650M: " + ", ".join(f"{p} k={k}: {v:.2e}" for (p, k), v in worst.items()))
+    for k, lst in muts.items():
+        assert worst[(choose_precision(cfg, lst), k)] < TOL
+    assert worst[("f16f8", 1)] < TOL and worst[("f16f8", 2)] < TOL
 
 
 @pytest.mark.parametrize("L", [1, 2, 1022, 1023])
@@ -635,7 +674,6 @@ def test_position_partition_two_gpus_bit_identical():
     assert "bit_identical=True" in r.stdout
 
 
-@pytest.mark.skipif(not os.environ.get("PG_TEST_UNVERIFIED"), reason="written after round 1's GPU budget was spent: first run is due in round 2")
 @pytest.mark.parametrize("name", GOLDEN_SMALL)
 def test_model_object_seam_reproduces_reference_loop(name, tmp_path):
     """Seam B2 (proteingym_b200.pretrained): the reference's masked-marginal loop (compute_fitness.py:486-504), verbatim, over the
