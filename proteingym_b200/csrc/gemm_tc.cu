@@ -53,6 +53,14 @@ constexpr uint32_t OFF_BAR = OFF_STG + NUM_EPI_WARPS * STG_BYTES;
 constexpr uint32_t GEMM_SMEM = OFF_BAR + 256 + 1024;  // + barriers + 1 KiB alignment slack
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int MAX_SEGS = 24;
+// CTA-pair mode (cta_group::2): the pair computes a 256 x 256 tile; each CTA loads its 128 rows of A and HALF of the W tile (128 of
+// the 256 rows), so a k-block costs 32 KB of L2 -> SM traffic per CTA instead of 48 KB and the ring holds 6 stages instead of 4.
+// ncu r02: the single-CTA kernel pulls 15-17 TB/s through the L2 -> SM crossbar at 75-86 % tensor-pipe activity, i.e. it is bound
+// by that traffic, not by the tensor pipe.
+constexpr int STAGES2 = 6;
+constexpr uint32_t B2_BYTES = 128 * BK * 2;  // 16 KiB: this CTA's half of the W tile
+constexpr uint32_t OFF_B2 = STAGES2 * A_BYTES;
+static_assert(OFF_B2 + STAGES2 * B2_BYTES == OFF_STG, "both modes use the same 192 KiB of operand stages");
 
 // One run of k-blocks with fixed operand planes. kind: 0 = fp16 (columns in elements), 1 = e4m3 (columns in bytes).
 // commit: 1 = the chunk ends after this segment (publish the accumulator, switch TMEM buffer).
@@ -254,7 +262,7 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
   }
 }
 
-template <int EPI>
+template <int EPI, int CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8,
@@ -263,40 +271,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
+  constexpr int NST = CTA2 ? STAGES2 : STAGES;                 // stages of the operand ring
+  constexpr uint32_t BST = CTA2 ? B2_BYTES : B_BYTES;          // bytes of W this CTA stages per k-block
   uint8_t* smA = smem;
-  uint8_t* smB = smem + OFF_B;
+  uint8_t* smB = smem + (CTA2 ? OFF_B2 : OFF_B);
   uint8_t* smStg = smem + OFF_STG;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* empty = full + NST;
+  uint64_t* tfull = empty + NST;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int ntiles = p.tiles_m * p.tiles_n;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0;            // 0 = leader of the pair: issues the MMAs
+  const int ntiles = p.tiles_m * p.tiles_n;                    // CTA2: tiles_m counts 256-row tiles
+  const int tile0 = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tstep = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int row_base = CTA2 ? 2 * BM : BM;                       // rows of the output tile per (pair of) CTA(s)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], NUM_EPI_WARPS);
+      mbar_init(&tempty[i], CTA2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);  // pair mode: the epilogue warps of BOTH CTAs release the leader
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, TMEM_COLS);
-    tmem_relinquish();
+    if (CTA2) { tmem_alloc_2sm(tmem_ptr, TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_ptr, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -308,21 +323,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       // Optional L2 look-ahead cursor (p.prefetch k-blocks ahead of the loads, A operand only). Measured neutral-to-negative on the
       // in-model shapes (bench r02: 737 vs 762 ms/step with it off), so the default is off.
-      int pf_tile = blockIdx.x, pf_s = 0, pf_kb = 0;
+      int pf_tile = tile0, pf_s = 0, pf_kb = 0;
       auto pf_step = [&]() {
         if (pf_tile >= ntiles) return;
         const GemmSeg sg = p.seg[pf_s];
         if (elect_one())
-          tma_prefetch_l2_2d(sg.kind ? &tmA8 : &tmA, sg.a_col + pf_kb * (sg.kind ? 2 * BK : BK), (pf_tile / p.tiles_n) * BM);
+          tma_prefetch_l2_2d(sg.kind ? &tmA8 : &tmA, sg.a_col + pf_kb * (sg.kind ? 2 * BK : BK),
+                             (pf_tile / p.tiles_n) * row_base + static_cast<int>(rank) * BM);
         __syncwarp();
         if (++pf_kb == sg.nkb) {
           pf_kb = 0;
-          if (++pf_s == p.nsegs) { pf_s = 0; pf_tile += gridDim.x; }
+          if (++pf_s == p.nsegs) { pf_s = 0; pf_tile += tstep; }
         }
       };
       for (int i = 0; i < p.prefetch; ++i) pf_step();
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < ntiles; tile += tstep) {
         const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        const int a_row = m_blk * row_base + static_cast<int>(rank) * BM;          // this CTA's 128 rows of A
+        const int b_row = n_blk * BN + (CTA2 ? static_cast<int>(rank) * 128 : 0);   // pair mode: this CTA's half of the W tile
         for (int s = 0; s < p.nsegs; ++s) {
           const GemmSeg sg = p.seg[s];
           const CUtensorMap* ma = sg.kind ? &tmA8 : &tmA;
@@ -332,23 +350,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.prefetch) pf_step();
             mbar_wait(&empty[stage], phase ^ 1);
             if (elect_one()) {
-              mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
-              tma_load_2d(smA + stage * A_BYTES, ma, &full[stage], sg.a_col + kb * step, m_blk * BM);
-              tma_load_2d(smB + stage * B_BYTES, mb, &full[stage], sg.b_col + kb * step, n_blk * BN);
+              if (CTA2) {
+                // both CTAs' bytes complete on the LEADER's barrier (its MMA thread is the only consumer); the leader arms it
+                if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (A_BYTES + B2_BYTES));
+                tma_load_2d_2sm(smA + stage * A_BYTES, ma, &full[stage], sg.a_col + kb * step, a_row);
+                tma_load_2d_2sm(smB + stage * B2_BYTES, mb, &full[stage], sg.b_col + kb * step, b_row);
+              } else {
+                mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
+                tma_load_2d(smA + stage * A_BYTES, ma, &full[stage], sg.a_col + kb * step, a_row);
+                tma_load_2d(smB + stage * B_BYTES, mb, &full[stage], sg.b_col + kb * step, b_row);
+              }
             }
             __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == NST) { stage = 0; phase ^= 1; }
           }
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == 1 && rank == 0) {
       // All 32 lanes run the (warp-uniform) control flow and the barrier waits; one elected lane issues the MMAs and commits.
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);  // same bit pattern for kind::f8f6f4 with e4m3 operands
+      // Pair mode: only the leader CTA issues; the instruction reads A rows and W rows from both CTAs' shared memory (same offsets)
+      // and accumulates 128 rows in each CTA's TMEM; commits are multicast to the barriers of both CTAs.
+      constexpr uint32_t idesc = make_idesc_f16(CTA2 ? 2 * BM : BM, BN, 0, 0);  // same bit pattern for kind::f8f6f4 with e4m3 operands
       const uint32_t a_base = smem_u32(smA), b_base = smem_u32(smB);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t g = 0;  // running chunk number: TMEM buffer g & 1, barrier phase (g >> 1) & 1
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < ntiles; tile += tstep) {
         bool fresh = true;
         uint32_t accumulate = 0;
         for (int s = 0; s < p.nsegs; ++s) {
@@ -365,19 +392,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&full[stage], phase);
             tc_fence_after();
             const uint64_t adesc = make_desc_sw128(a_base + stage * A_BYTES, 1024);
-            const uint64_t bdesc = make_desc_sw128(b_base + stage * B_BYTES, 1024);
+            const uint64_t bdesc = make_desc_sw128(b_base + stage * BST, 1024);
             if (elect_one()) {
               // 4 x (K = 32 bytes of every row): 16 fp16 or 32 e4m3 per instruction
-              if (sg.kind) umma_kblock<1>(tmem_d, adesc, bdesc, idesc, accumulate);
-              else umma_kblock<0>(tmem_d, adesc, bdesc, idesc, accumulate);
-              umma_commit(&empty[stage]);
+              if (sg.kind) umma_kblock<1, CTA2 ? 2 : 1>(tmem_d, adesc, bdesc, idesc, accumulate);
+              else umma_kblock<0, CTA2 ? 2 : 1>(tmem_d, adesc, bdesc, idesc, accumulate);
+              if (CTA2) umma_commit_2sm(&empty[stage]); else umma_commit(&empty[stage]);
             }
             __syncwarp();
             accumulate = 1;
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == NST) { stage = 0; phase ^= 1; }
           }
           if (sg.commit) {
-            if (elect_one()) umma_commit(&tfull[buf]);
+            if (elect_one()) { if (CTA2) umma_commit_2sm(&tfull[buf]); else umma_commit(&tfull[buf]); }
             __syncwarp();
             ++g;
             fresh = true;
@@ -394,10 +421,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     c.tmHi = &tmHi; c.tmLo = &tmLo; c.tmRes = &tmRes;
     c.stg = smStg + (warp - FIRST_EPI_WARP) * STG_BYTES;
     c.lane = lane;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < ntiles; tile += tstep) {
       const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
       c.gcol = n_blk * BN + half_id * 128;
-      c.grow0 = m_blk * BM + q * 32;
+      c.grow0 = m_blk * row_base + static_cast<int>(rank) * BM + q * 32;
       c.row = static_cast<long long>(c.grow0) + lane;
       c.row_ok = c.row < p.M;
       float acc[128];
@@ -439,7 +466,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);
+        if (lane == 0) {
+          if (CTA2 && rank != 0) mbar_arrive_cluster(&tempty[buf], 0);  // the leader's MMA thread waits on its own barrier
+          else mbar_arrive(&tempty[buf]);
+        }
       }
       finalize_group<EPI, 0>(acc, p, c);
       finalize_group<EPI, 1>(acc, p, c);
@@ -449,7 +479,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CTA2) cluster_sync_all();  // neither CTA's shared / tensor memory may go away while the pair still uses it
+  if (warp == 2) {
+    if (CTA2) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -525,7 +558,15 @@ int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
 
 // Longest run of K one hi*hi chunk accumulates before the epilogue takes it over (see the header). Default 1280; the environment
 // variable PG_GEMM_KCHUNK or pg_set_tuning("gemm_kchunk", v) override it; 0 = no chunking (round-1 behaviour, for the probe).
-static int g_kchunk = -1, g_prefetch = -1;
+static int g_kchunk = -1, g_prefetch = -1, g_cta2 = -1;
+int gemm_cta2() {
+  if (g_cta2 < 0) {
+    const char* e = getenv("PG_GEMM_CTA2");
+    g_cta2 = e ? atoi(e) : 0;
+  }
+  return g_cta2;
+}
+void set_gemm_cta2(int v) { g_cta2 = v ? 1 : 0; }
 int gemm_kchunk() {
   if (g_kchunk < 0) {
     const char* e = getenv("PG_GEMM_KCHUNK");
@@ -559,24 +600,26 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   PG_CUDA_OK(cudaGetDevice(&dev));
   static bool attr_set[64] = {};
   if (dev < 64 && !attr_set[dev]) {
-    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+#define PG_SET_SMEM(E)                                                                                              \
+  PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<E, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)); \
+  PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM))
+    PG_SET_SMEM(0); PG_SET_SMEM(1); PG_SET_SMEM(2); PG_SET_SMEM(3); PG_SET_SMEM(4);
+#undef PG_SET_SMEM
     attr_set[dev] = true;
   }
   const uint64_t K = static_cast<uint64_t>(g.K);
   const uint64_t width = K * (g.nseg == 3 ? 2 : 1);
+  const int cta2 = gemm_cta2();
+  const uint32_t wbox = cta2 ? 128 : BN;  // rows of W one CTA stages per k-block (pair mode: its half of the 256-row tile)
   CUtensorMap tmA, tmB, tmA8{}, tmB8{};
   int rc = make_tmap_2d(&tmA, g.a, g.M, width, g.lda, BM, BK, 2, 128);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmB, g.w, g.N, width, g.ldw, BN, BK, 2, 128);
+  rc = make_tmap_2d(&tmB, g.w, g.N, width, g.ldw, wbox, BK, 2, 128);
   if (rc) return rc;
   if (g.nseg == 2) {  // e4m3 planes follow the fp16 hi plane of each row: bytes [2K, 4K) = K-concatenated [lo8 | hi8] / [hi8 | lo8]
     rc = make_tmap_2d(&tmA8, static_cast<const uint8_t*>(g.a) + 2 * K, g.M, 2 * K, static_cast<uint64_t>(g.lda) * 2, BM, 2 * BK, 1, 128);
     if (rc) return rc;
-    rc = make_tmap_2d(&tmB8, static_cast<const uint8_t*>(g.w) + 2 * K, g.N, 2 * K, static_cast<uint64_t>(g.ldw) * 2, BN, 2 * BK, 1, 128);
+    rc = make_tmap_2d(&tmB8, static_cast<const uint8_t*>(g.w) + 2 * K, g.N, 2 * K, static_cast<uint64_t>(g.ldw) * 2, wbox, 2 * BK, 1, 128);
     if (rc) return rc;
   }
   CUtensorMap tmHi{}, tmLo{}, tmRes{};
@@ -628,18 +671,43 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   p.out_fmt = (g.epi == 2) ? 0 : g.out_fmt;
   p.out_scale = g.out_scale;
   p.rot_cos = g.rot_cos; p.rot_sin = g.rot_sin; p.rot_T = g.rot_T; p.rot_dim = g.rot_dim;
-  p.tiles_m = (g.M + BM - 1) / BM;
+  p.tiles_m = cta2 ? (g.M + 2 * BM - 1) / (2 * BM) : (g.M + BM - 1) / BM;
   p.tiles_n = (g.N + BN - 1) / BN;
   p.prefetch = gemm_prefetch();
   const int ntiles = p.tiles_m * p.tiles_n;
-  const int grid = ntiles < num_sms() ? ntiles : num_sms();
-  switch (g.epi) {
-    case 0: gemm_tc_kernel<0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-    case 1: gemm_tc_kernel<1><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-    case 2: gemm_tc_kernel<2><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-    case 3: gemm_tc_kernel<3><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-    default: gemm_tc_kernel<4><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+  if (!cta2) {
+    const int grid = ntiles < num_sms() ? ntiles : num_sms();
+    switch (g.epi) {
+      case 0: gemm_tc_kernel<0, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      case 1: gemm_tc_kernel<1, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      case 2: gemm_tc_kernel<2, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      case 3: gemm_tc_kernel<3, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      default: gemm_tc_kernel<4, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    }
+    PG_CUDA_OK(cudaGetLastError());
+    return PG_OK;
   }
+  // pair mode: clusters of two CTAs (same TPC), one cluster per pair of SMs
+  const int pairs = ntiles < num_sms() / 2 ? ntiles : num_sms() / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GEMM_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+  switch (g.epi) {
+    case 0: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<0, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    case 1: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    case 2: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    case 3: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<3, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    default: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<4, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+  }
+  PG_CUDA_OK(e);
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;
 }

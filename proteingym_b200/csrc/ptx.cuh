@@ -146,40 +146,76 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 // Four MMAs over one 128-byte-wide k-block (descriptor start advanced by 32 bytes = +2 in the >>4 field each), in ONE asm block:
-// KIND 0 = kind::f16 (4 x K16), KIND 1 = kind::f8f6f4 (4 x K32). `accumulate` applies to the first MMA; the other three accumulate.
-template <int KIND>
+// KIND 0 = kind::f16 (4 x K16), KIND 1 = kind::f8f6f4 (4 x K32); CG = cta_group (2: the instruction spans the CTA pair, M = 256,
+// issued by the leader CTA only). `accumulate` applies to the first MMA; the other three accumulate.
+#define PG_UMMA_KBLOCK(CGS, KINDS)                                                                                                   \
+  asm volatile(                                                                                                                      \
+      "{\n\t"                                                                                                                        \
+      ".reg .pred p, t;\n\t"                                                                                                         \
+      ".reg .b64 a1, b1, a2, b2, a3, b3;\n\t"                                                                                        \
+      "setp.ne.b32 p, %4, 0;\n\t"                                                                                                    \
+      "setp.eq.b32 t, %4, %4;\n\t"                                                                                                   \
+      "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\tadd.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\tadd.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t" \
+      "tcgen05.mma.cta_group::" CGS ".kind::" KINDS " [%0], %1, %2, %3, p;\n\t"                                                       \
+      "tcgen05.mma.cta_group::" CGS ".kind::" KINDS " [%0], a1, b1, %3, t;\n\t"                                                       \
+      "tcgen05.mma.cta_group::" CGS ".kind::" KINDS " [%0], a2, b2, %3, t;\n\t"                                                       \
+      "tcgen05.mma.cta_group::" CGS ".kind::" KINDS " [%0], a3, b3, %3, t;\n\t"                                                       \
+      "}" ::"r"(tmem_d),                                                                                                             \
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)                                                                            \
+      : "memory")
+template <int KIND, int CG = 1>
 __device__ __forceinline__ void umma_kblock(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if (KIND == 0) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, t;\n\t"
-        ".reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "setp.eq.b32 t, %4, %4;\n\t"
-        "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\tadd.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\tadd.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+  if (CG == 1) {
+    if (KIND == 0) PG_UMMA_KBLOCK("1", "f16"); else PG_UMMA_KBLOCK("1", "f8f6f4");
   } else {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, t;\n\t"
-        ".reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "setp.eq.b32 t, %4, %4;\n\t"
-        "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\tadd.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\tadd.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], a1, b1, %3, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], a2, b2, %3, t;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], a3, b3, %3, t;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if (KIND == 0) PG_UMMA_KBLOCK("2", "f16"); else PG_UMMA_KBLOCK("2", "f8f6f4");
   }
+}
+#undef PG_UMMA_KBLOCK
+
+// ---------------------------------------------------------------- CTA pairs (cta_group::2): forms taken from CUTLASS' sm100 headers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-pair bit of a shared address: names the LEADER CTA's copy of a variable
+// 2D tiled load issued by either CTA of a pair into ITS OWN shared memory; the transaction bytes complete on the leader CTA's barrier.
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// All previously issued cta_group::2 MMAs of this thread arrive on `bar` in BOTH CTAs of the pair when complete.
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+// Arrive on the barrier at the same shared-memory offset in CTA `rank` of this cluster.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {  // one whole warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // A operand from TMEM (fp16 packed), B from smem.
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

@@ -52,7 +52,7 @@ def mask_position(row: torch.Tensor, mask_idx: int) -> int:
 
 
 class B200EsmModel:
-    def __init__(self, config, state, name, precision="f16f8", device=0):
+    def __init__(self, config, state, name, precision="f16x3", device=0):
         self.config, self._state, self.name = config, state, name
         self.precision, self._device = precision, device
         self.scorer = None
@@ -84,6 +84,6 @@ class B200EsmModel:
         return {"logits": out}
 
 
-def load_model_and_alphabet(model_location: str, precision: str = "f16f8", device: int = 0):
+def load_model_and_alphabet(model_location: str, precision: str = "f16x3", device: int = 0):
     config, state, name = load_esm_checkpoint(model_location)
     return B200EsmModel(config, state, name, precision, device), ALPHABET

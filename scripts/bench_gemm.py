@@ -35,8 +35,9 @@ for name, N, K, epi in SHAPES:
             args.out_h, args.ldo, args.out_lo_off = out.data_ptr(), N * np_, (N if np_ == 2 else 0)
             # QKV feeds the attention kernel (fp16 hi/lo), fc1 feeds fc2 (operand format of the mode)
             args.out_fmt, args.out_scale = ((2 if nseg == 2 else 0) if name == "fc1" else 0), 2.0
-        for kc in KCH:
+        for kc, cta2 in [(k, c) for k in KCH for c in (0, 1)]:
             lib.pg_set_tuning(b"gemm_kchunk", kc)
+            lib.pg_set_tuning(b"gemm_cta2", cta2)
             for _ in range(3):
                 _lib.check(lib.pg_gemm(C.byref(args), None))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -46,8 +47,9 @@ for name, N, K, epi in SHAPES:
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
             alg = 2.0 * M * N * K / ms / 1e9
-            print(json.dumps({"gemm": name, "N": N, "K": K, "epi": epi, "nseg": nseg, "kchunk": kc, "ms": round(ms, 4),
+            print(json.dumps({"gemm": name, "N": N, "K": K, "epi": epi, "nseg": nseg, "kchunk": kc, "cta2": cta2, "ms": round(ms, 4),
                               "algorithmic_tflops": round(alg, 1), "issued_tflops": round(alg * {1: 1, 3: 3, 2: 2}[nseg], 1),
                               "issued_frac_of_burst_peak": round(alg * {1: 1, 3: 3, 2: 2}[nseg] / PEAK, 3)}), flush=True)
+        lib.pg_set_tuning(b"gemm_cta2", 0)
         del a, w
     del x, w32

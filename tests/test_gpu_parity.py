@@ -66,8 +66,10 @@ def spearman(a, b):
 @pytest.mark.parametrize("M,N,K,nseg,epi", [(128, 256, 64, 1, 0), (1, 8, 64, 1, 0), (257, 520, 192, 1, 1), (129, 100, 64, 1, 2),
                                             (500, 384, 128, 1, 3), (300, 320, 128, 3, 0), (300, 320, 128, 3, 1),
                                             (1000, 1280, 1280, 3, 2), (300, 384, 128, 3, 3), (4096, 3840, 1280, 1, 0)])
-def test_gemm_matches_fp64(M, N, K, nseg, epi):
+@pytest.mark.parametrize("cta2", [0, 1])
+def test_gemm_matches_fp64(M, N, K, nseg, epi, cta2):
     lib = _lib.load()
+    lib.pg_set_tuning(b"gemm_cta2", cta2)  # 1: the CTA-pair (cta_group::2) form of the kernel
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda", generator=g)
     W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
@@ -102,8 +104,11 @@ def test_gemm_matches_fp64(M, N, K, nseg, epi):
             x1, x2 = ref[:, h0:h0 + 32], ref[:, h0 + 32:h0 + 64]
             r[:, h0:h0 + 32], r[:, h0 + 32:h0 + 64] = x1 * c - x2 * s, x2 * c + x1 * s
         ref = r
-    _lib.check(lib.pg_gemm(C.byref(args), None))
-    torch.cuda.synchronize()
+    try:
+        _lib.check(lib.pg_gemm(C.byref(args), None))
+        torch.cuda.synchronize()
+    finally:
+        lib.pg_set_tuning(b"gemm_cta2", 0)
     got = resid.double() if epi == 2 else out[:, :N].double() + (out[:, N:].double() if nseg == 3 else 0)
     err = (got - ref).abs().max().item()
     # fp32 accumulate of exactly-representable products; the fp16 output rounding dominates for single-plane outputs
@@ -115,7 +120,8 @@ def test_gemm_matches_fp64(M, N, K, nseg, epi):
 @pytest.mark.parametrize("M,N,K,epi,out_fmt", [(128, 256, 64, 0, 1), (300, 320, 128, 1, 2), (257, 576, 192, 2, 0), (1000, 1280, 1280, 2, 0),
                                                (500, 384, 128, 3, 1), (640, 5120, 1280, 1, 2), (300, 1280, 5120, 2, 0),
                                                (130, 192, 10240, 0, 2)])
-def test_gemm_f16f8_matches_fp64(M, N, K, epi, out_fmt):
+@pytest.mark.parametrize("cta2", [0, 1])
+def test_gemm_f16f8_matches_fp64(M, N, K, epi, out_fmt, cta2):
     """nseg 2: fp16 hi*hi + e4m3 cross terms. The kernel's products are exact in fp32, so against an fp64 evaluation of the SAME
     quantised planes only accumulation error remains; pg_pack_weight's row scales are checked on the way."""
     lib = _lib.load()
@@ -173,8 +179,12 @@ def test_gemm_f16f8_matches_fp64(M, N, K, epi, out_fmt):
                 r[:, h0:h0 + 32], r[:, h0 + 32:h0 + 64] = x1 * c - x2 * sn, x2 * c + x1 * sn
             return r
         ref, full = rot(ref), rot(full)
-    _lib.check(lib.pg_gemm(C.byref(args), None))
-    torch.cuda.synchronize()
+    lib.pg_set_tuning(b"gemm_cta2", cta2)
+    try:
+        _lib.check(lib.pg_gemm(C.byref(args), None))
+        torch.cuda.synchronize()
+    finally:
+        lib.pg_set_tuning(b"gemm_cta2", 0)
     amax = ref.abs().max().item()
     bound = 4e-7 * (3 * K) ** 0.5 * max(4.0, amax)
     if epi == 2:

@@ -119,6 +119,21 @@ def test_prefix_reuse_rejects_bad_calls():
     sc.close()
 
 
+def test_row_sharding_two_gpus_matches_single_gpu():
+    """SURVEY.md §8e for Tranception: the sequence rows of one assay split over 2 GPUs + one NCCL all-gather per direction give the
+    single-GPU scores. Needs 2 devices (skipped on the 1-GPU box; runs under `gpurun --gpus 2`)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29673", os.path.join(root, "scripts", "check_tranception_sharding.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ok=True" in r.stdout
+
+
 def test_retrieval_fusion_matches_oracle():
     arch = synth.TranceptionArch(1, 256, 4, 256)
     st = synth.make_tranception_state(arch, 4)
