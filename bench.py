@@ -531,8 +531,8 @@ def main():
         except Exception:
             pass
         res["roofline"] = {
-            "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::f16 + kind::f8f6f4, M128xN256, TMA 4-stage ring, chunked RN "
-                                         "accumulation, TMA-store epilogue)",
+            "bound": "tensor", "kernel": "gemm_tc_kernel (CTA pairs: tcgen05.mma cta_group::2 kind::f16 + kind::f8f6f4, 256x256 tile per pair, "
+                                         "TMA 6-stage ring, chunked RN accumulation, TMA-store epilogue)",
             "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": (achieved / sustained) if achieved else None,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how}); burst {burst}",
             "algorithmic_flops_per_launch": f_lin * a.steps / max(1, gemm_launches), "launches": gemm_launches,

@@ -230,6 +230,8 @@ int pg_profile_end(float* ms, int32_t* counts, int32_t ncat);
 /* Process-wide tuning knobs (benchmarks / numerics probes; defaults are the measured-best values):
  *   "gemm_kchunk"  longest run of K (elements) a hi*hi accumulation chunk covers before the epilogue adds it in RN fp32
  *                  (default 1280; 0 = no chunking). Also settable through the environment variable PG_GEMM_KCHUNK.
+ *   "gemm_cta2"    1 (default): the GEMM runs as CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, W tile split across the pair);
+ *                  0: one CTA per 128 x 256 tile (round-1 structure). PG_GEMM_CTA2.
  *   "gemm_prefetch" k-blocks of L2 look-ahead the GEMM's TMA producer issues for the streamed A operand (default 0 = off: measured
  *                  neutral-to-negative in the model; PG_GEMM_PREFETCH). */
 int pg_set_tuning(const char* key, int32_t value);

@@ -102,19 +102,26 @@ __global__ void pack_weight_t_kernel(const float* __restrict__ w, int N, int K, 
   out[static_cast<long long>(n) * K * np + k] = hi;
   if (np == 2) out[static_cast<long long>(n) * K * np + K + k] = lo;
 }
-// Weight row n in the fp16 + e4m3 format of gemm_tc.cu (nseg 2): [hi fp16 (K) | hi8 (K bytes) | lo8 (K bytes)], row pitch 4K bytes,
-// hi8 = e4m3(hi * t), lo8 = e4m3(lo * 2^11 * t) with t = the power of two that puts the row's largest |hi| in (112, 224];
-// w_inv[n] = 1 / t. One warp per row; element (n, k) of the source is w[n * sn + k * sk] (sk = 1: nn.Linear; sn = 1: Conv1D).
+// Weights in the fp16 + e4m3 format of gemm_tc.cu (nseg 2): row n = [hi fp16 (K) | hi8 (K bytes) | lo8 (K bytes)], pitch 4K bytes,
+// hi8 = e4m3(hi * t), lo8 = e4m3(lo * 2^11 * t) with ONE power of two t per matrix: the one that puts the largest |hi| of the matrix in
+// (112, 224]. e4m3 is a floating-point format (2^-4 relative precision over 15 binades), so rows much smaller than the largest one
+// keep their precision; a per-row scale would only cost the epilogue a load per output column. w_inv[n] = 1 / t for every n.
+// Element (n, k) of the source is w[n * sn + k * sk] (sk = 1: nn.Linear; sn = 1: Conv1D). Two kernels: matrix |hi| maximum, then pack.
+__global__ void weight_absmax_kernel(const float* __restrict__ w, int N, int K, long long sn, long long sk, float scale,
+                                     unsigned int* __restrict__ amax_bits) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float a = 0.f;
+  if (i < static_cast<long long>(N) * K) a = fabsf(__half2float(f2h_sat(w[(i / K) * sn + (i % K) * sk] * scale)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+  if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(amax_bits, __float_as_uint(a));  // non-negative floats order like their bit patterns
+}
 __global__ void pack_weight_f8_kernel(const float* __restrict__ w, int N, int K, long long sn, long long sk, float scale,
-                                      __half* __restrict__ out, float* __restrict__ w_inv) {
+                                      const unsigned int* __restrict__ amax_bits, __half* __restrict__ out, float* __restrict__ w_inv) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
-  const float* wr = w + static_cast<long long>(n) * sn;
-  float amax = 0.f;
-  for (int k = lane; k < K; k += 32) amax = fmaxf(amax, fabsf(__half2float(f2h_sat(wr[k * sk] * scale))));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  const float amax = __uint_as_float(*amax_bits);
   float t = 1.f;
   if (amax > 0.f) {
     int e;
@@ -122,6 +129,7 @@ __global__ void pack_weight_f8_kernel(const float* __restrict__ w, int N, int K,
     t = ldexpf(1.f, 8 - e);           // amax * t in [128, 256)
     if (amax * t > 224.f) t *= 0.5f;  // -> (112, 224]: one binade of headroom below the e4m3 maximum of 448
   }
+  const float* wr = w + static_cast<long long>(n) * sn;
   __half* orow = out + static_cast<long long>(n) * K * 2;
   uint8_t* f8 = reinterpret_cast<uint8_t*>(orow + K);
   for (int k = lane; k < K; k += 32) {
@@ -134,6 +142,14 @@ __global__ void pack_weight_f8_kernel(const float* __restrict__ w, int N, int K,
     f8[K + k] = static_cast<uint8_t>(cvt_e4m3x2((v - hf) * t * 2048.f, 0.f) & 0xff);
   }
   if (lane == 0) w_inv[n] = 1.f / t;
+}
+// One matrix: absmax pass + pack pass on stream s; `scratch` is one device word per call (kept alive by the caller).
+void launch_pack_weight_f8(const float* w, int N, int K, long long sn, long long sk, float scale, unsigned int* scratch, __half* out,
+                           float* w_inv, cudaStream_t s) {
+  const long long tot = static_cast<long long>(N) * K;
+  cudaMemsetAsync(scratch, 0, sizeof(unsigned int), s);
+  weight_absmax_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(w, N, K, sn, sk, scale, scratch);
+  pack_weight_f8_kernel<<<(N + 7) / 8, 256, 0, s>>>(w, N, K, sn, sk, scale, scratch, out, w_inv);
 }
 __global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, float scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,6 +200,8 @@ struct pg_handle_s {
   float *tok_logp = nullptr, *slopes = nullptr;
   // exact wild-type-prefix reuse (pg_ar_prefix_begin / pg_ar_loglik_prefix): per layer, the wild type's raw q/k/v rows (conv
   // look-back) and conv'd q/k/v rows (keys / values of the shared prefix), [layers][prefix_T][3d*np] fp16 each
+  unsigned int* pack_scratch = nullptr;  // one word per packed matrix (absmax of the matrix), [layers * 6]
+  int pack_used = 0;
   __half *raw_cache = nullptr, *kv_cache = nullptr;
   int prefix_T = 0;        // rows recorded by the last pg_ar_prefix_begin (0 = none)
   int prefix_cap = 0;      // rows the caches can hold
@@ -232,7 +250,7 @@ int run_lin(pg_handle h, int cat, const Lin& L, cudaStream_t s, int rot_T = 0) {
   GemmLaunch g{};
   g.a = L.a; g.lda = L.lda; g.w = L.w; g.ldw = static_cast<int64_t>(L.K) * np; g.bias = L.bias;
   g.M = L.M; g.N = L.N; g.K = L.K; g.nseg = h->nseg; g.epi = L.epi;
-  g.a_scale = L.a_scale; g.w_inv = L.w_inv;
+  g.a_scale = L.a_scale; g.w_inv = L.w_inv; g.w_uniform = 1;  // pg_load_weights: one e4m3 scale per (fused) weight matrix
   if (L.epi == 2) {
     g.resid = L.resid; g.ldr = L.N;
   } else {
@@ -476,6 +494,7 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
     A(&h->tok_logp, static_cast<size_t>(h->max_rows));
     A(&h->slopes, D.heads);
   }
+  if (h->nseg == 2) A(&h->pack_scratch, static_cast<size_t>(D.layers) * 6);
   A(&h->embed, static_cast<size_t>(D.vocab) * d);
   if (D.arch == PG_ARCH_ESM1B) A(&h->pos, static_cast<size_t>(D.max_positions + 2) * d);
   A(&h->lnbg, d); A(&h->lnbb, d); A(&h->lnag, d); A(&h->lnab, d);
@@ -530,13 +549,13 @@ int pg_load_weights(pg_handle h, const pg_tensor* tensors, int32_t n) {
   auto pack = [&](__half* dst, float* inv, const float* src, int N, int K, float scale = 1.f) {
     if (!src) return;
     const long long tot = static_cast<long long>(N) * K;
-    if (f8) pack_weight_f8_kernel<<<(N + 7) / 8, 256>>>(src, N, K, K, 1, scale, dst, inv);
+    if (f8) launch_pack_weight_f8(src, N, K, K, 1, scale, h->pack_scratch + (h->pack_used++ % (D.layers * 6)), dst, inv, 0);
     else pack_weight_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256>>>(src, N, K, scale, dst, np);
   };
   auto pack_t = [&](__half* dst, float* inv, const float* src, int N, int K) {
     if (!src) return;
     const long long tot = static_cast<long long>(N) * K;
-    if (f8) pack_weight_f8_kernel<<<(N + 7) / 8, 256>>>(src, N, K, 1, N, 1.f, dst, inv);
+    if (f8) launch_pack_weight_f8(src, N, K, 1, N, 1.f, h->pack_scratch + (h->pack_used++ % (D.layers * 6)), dst, inv, 0);
     else pack_weight_t_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256>>>(src, N, K, dst, np);
   };
   if (D.arch == PG_ARCH_TRANCEPTION) {
@@ -573,9 +592,26 @@ int pg_load_weights(pg_handle h, const pg_tensor* tensors, int32_t n) {
     Layer& L = h->layers[l];
     const std::string p = "layers." + std::to_string(l) + ".";
     const size_t dd = static_cast<size_t>(d) * d * np;
-    pack(L.wqkv, L.iqkv, get(p + "self_attn.q_proj.weight", d, d), d, d, qscale);
-    pack(L.wqkv + dd, f8 ? L.iqkv + d : nullptr, get(p + "self_attn.k_proj.weight", d, d), d, d);
-    pack(L.wqkv + 2 * dd, f8 ? L.iqkv + 2 * d : nullptr, get(p + "self_attn.v_proj.weight", d, d), d, d);
+    if (f8) {  // q, k, v form ONE GEMM operand: one common e4m3 scale (matrix maximum over the three, q already scaled)
+      const float* wq = get(p + "self_attn.q_proj.weight", d, d);
+      const float* wk = get(p + "self_attn.k_proj.weight", d, d);
+      const float* wv = get(p + "self_attn.v_proj.weight", d, d);
+      if (wq && wk && wv) {
+        unsigned int* word = h->pack_scratch + (h->pack_used++ % (D.layers * 6));
+        const unsigned nb = static_cast<unsigned>((static_cast<long long>(d) * d + 255) / 256);
+        cudaMemsetAsync(word, 0, sizeof(unsigned int), 0);
+        weight_absmax_kernel<<<nb, 256>>>(wq, d, d, d, 1, qscale, word);
+        weight_absmax_kernel<<<nb, 256>>>(wk, d, d, d, 1, 1.f, word);
+        weight_absmax_kernel<<<nb, 256>>>(wv, d, d, d, 1, 1.f, word);
+        pack_weight_f8_kernel<<<(d + 7) / 8, 256>>>(wq, d, d, d, 1, qscale, word, L.wqkv, L.iqkv);
+        pack_weight_f8_kernel<<<(d + 7) / 8, 256>>>(wk, d, d, d, 1, 1.f, word, L.wqkv + dd, L.iqkv + d);
+        pack_weight_f8_kernel<<<(d + 7) / 8, 256>>>(wv, d, d, d, 1, 1.f, word, L.wqkv + 2 * dd, L.iqkv + 2 * d);
+      }
+    } else {
+      pack(L.wqkv, nullptr, get(p + "self_attn.q_proj.weight", d, d), d, d, qscale);
+      pack(L.wqkv + dd, nullptr, get(p + "self_attn.k_proj.weight", d, d), d, d);
+      pack(L.wqkv + 2 * dd, nullptr, get(p + "self_attn.v_proj.weight", d, d), d, d);
+    }
     copy(L.bqkv, get(p + "self_attn.q_proj.bias", d, 1), d, qscale);
     copy(L.bqkv + d, get(p + "self_attn.k_proj.bias", d, 1), d);
     copy(L.bqkv + 2 * d, get(p + "self_attn.v_proj.bias", d, 1), d);
@@ -845,7 +881,14 @@ int pg_pack_weight(const float* w, int32_t N, int32_t K, int32_t fmt, void* out,
   const long long tot = static_cast<long long>(N) * K;
   if (fmt == 2) {
     if (!w_inv) return set_error(PG_ERR_ARG, "pg_pack_weight: fmt 2 needs w_inv[N]");
-    pack_weight_f8_kernel<<<(N + 7) / 8, 256, 0, s>>>(w, N, K, K, 1, 1.f, static_cast<__half*>(out), w_inv);
+    // the matrix maximum is accumulated in w_inv[0]'s storage (as bits) before the pack kernel overwrites it with 1 / t... a separate
+    // word is cleaner: the last row's slot is written last by its own warp only, so use a small static scratch per device instead
+    static unsigned int* scratch[64] = {};
+    int dev = 0;
+    PG_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 64) return set_error(PG_ERR_UNSUPPORTED, "pg_pack_weight: device ordinal >= 64");
+    if (!scratch[dev]) PG_CUDA_OK(cudaMalloc(&scratch[dev], 256));
+    launch_pack_weight_f8(w, N, K, K, 1, 1.f, scratch[dev], static_cast<__half*>(out), w_inv, s);
   } else if (fmt == 0 || fmt == 1) {
     pack_weight_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(w, N, K, 1.f, static_cast<__half*>(out), fmt + 1);
   } else {

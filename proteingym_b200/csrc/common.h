@@ -49,6 +49,7 @@ struct GemmLaunch {
   const float* rot_cos; const float* rot_sin; int rot_T; int rot_dim;
   float a_scale = 0.f;            // nseg 2: s used by the producer of a's e4m3 planes
   const float* w_inv = nullptr;   // nseg 2: [N] 1 / t_n of the weight rows
+  int w_uniform = 0;              // nseg 2: all w_inv[n] are equal (one scale per matrix, as pg_load_weights / pg_pack_weight produce)
   int out_fmt = 0;                // epi != 2: 0, 1 or 2 (see above); planes at out_lo_off
   float out_scale = 0.f;          // out_fmt 2: s of the GEMM that will consume `out`
 };

@@ -330,13 +330,20 @@ class TranceptionScorer:
                 groups.setdefault((w, windows[i], start), []).append(i)
             else:
                 plain.append(i)
+        by_wt = {}
+        for (w, win, start), members in groups.items():
+            by_wt.setdefault((w, win), []).append((start, members))
+        # a window pays for its extra wild-type pass (T rows) only when its mutants skip clearly more rows than that; otherwise
+        # (e.g. proteins longer than the context, where every mutant has its own window) its members take the plain path
+        for key in list(by_wt):
+            T = len(key[0]) + 2
+            if sum(start * len(members) for start, members in by_wt[key]) < 2 * T:
+                plain += [i for _, members in by_wt.pop(key) for i in members]
+        plain.sort()
         rows_full = sum(len(x) + 2 for x in strings)
         rows_run = sum(len(strings[i]) + 2 for i in plain)
         if plain:
             out[plain] = self.sequence_logprobs([strings[i] for i in plain], windows=[windows[i] for i in plain], flip=flip, **prior_kw)
-        by_wt = {}
-        for (w, win, start), members in groups.items():
-            by_wt.setdefault((w, win), []).append((start, members))
         for (w, win), lst in by_wt.items():
             rows_run += len(w) + 2
             wt_tok, wt_rows = self._prefix_begin(w, win, flip, prior_kw)

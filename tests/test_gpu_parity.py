@@ -128,7 +128,7 @@ def test_gemm_f16f8_matches_fp64(M, N, K, epi, out_fmt, cta2):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda", generator=g)
     W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
-    W[::7] *= 37.0  # rows of very different magnitude: the per-row weight scale has to follow
+    W[::7] *= 37.0  # rows of very different magnitude: e4m3 is floating point, one scale per matrix has to be enough
     bias = torch.randn(N, device="cuda", generator=g)
     sA, sO = 4.0, 2.0
     a_op = pack_a_f8(A, sA)
@@ -139,9 +139,9 @@ def test_gemm_f16f8_matches_fp64(M, N, K, epi, out_fmt, cta2):
     t = 1.0 / w_inv.double()
     whi = w_op[:, :2 * K].contiguous().view(torch.float16)
     assert torch.equal(whi, W.to(torch.float16))
-    amax = whi.float().abs().amax(dim=1).double()
+    amax = whi.float().abs().max().double()  # ONE power-of-two scale per matrix: its largest |hi| lands in (112, 224]
     mant, _ = torch.frexp(t)
-    assert torch.all(mant == 0.5) and torch.all(amax * t <= 224.0) and torch.all(amax * t > 112.0)  # powers of two, (112, 224]
+    assert torch.all(mant == 0.5) and torch.all(t == t[0]) and amax * t[0] <= 224.0 and amax * t[0] > 112.0
     assert torch.equal(w_op[:, 2 * K:3 * K], q8(whi.float() * t[:, None].float()))
     assert torch.equal(w_op[:, 3 * K:], q8((W - whi.float()) * (2048.0 * t[:, None].float())))
     ahi, alo8, ahi8 = unpack_f8(a_op, K, sA)
