@@ -267,7 +267,7 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
         return res, [float(x.item()) for x in per_rank], (t_host, time.time())
 
     def share(entries, costs, k, cap):
-        picks, info = workloads.pick_subset(entries, costs, k, cap)
+        picks, info = workloads.pick_subset(entries, costs, k, cap, replicas=world)
         assign = sharding.lpt_assign([costs[i] for i in picks], world)
         return picks, [picks[j] for j in assign[rank]], info
 
@@ -283,7 +283,7 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
     arch = synth.ESM2_3B
     ents = shapes["substitutions"]
     costs = [workloads.esm_cost(e, arch) for e in ents]
-    picks, mine, info = share(ents, costs, 3 * world, 3.0e15)
+    picks, mine, info = share(ents, costs, 3, 3.0e15)
     from proteingym_b200.esm_engine import choose_precision
     prec3 = choose_precision(checkpoint.config_from_synth(arch), None) if a.precision != "f16" else "f16"  # the CLI's auto rule: f16x3 at this width
     state = checkpoint.normalise_synth_state(arch, synth.make_esm_state(arch, seed=0, device=dev))
@@ -296,7 +296,7 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
     sc.close()
     record("config3: ESM2 3B (36x2560, 40 heads, ffn 10240, rotary) masked-marginals, synthetic assays with the lengths / mutant counts / "
            "multi-mutant shares of reference_files/DMS_substitutions.csv, LPT over the ranks",
-           f"{len(picks)} of {len(ents)} assays, evenly spaced over the cost-sorted list of the {info.get('eligible')} with cost <= "
+           f"{len(picks)} of {len(ents)} assays ({info.get('classes')} size classes evenly spaced over the cost-sorted list x {world} neighbours per class), of the {info.get('eligible')} with cost <= "
            f"{info.get('cost_cap_tflop', 0):.0f} TFLOP ({info.get('dropped_over_cap')} dropped); L = {[ents[i]['L'] for i in picks]}; "
            "mutants capped at 20000 per assay; masked positions = unique mutated positions",
            picks, costs, sum(min(ents[i]["n_mutants"], 20000, 19 * ents[i]["L"]) for i in picks), per_rank, tw, precision=prec3)
@@ -311,7 +311,7 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
     ents = shapes["indels"]
     nm = [min(e["n_mutants"], 2000) for e in ents]
     costs = [workloads.tranception_cost(e, tarch, n) for e, n in zip(ents, nm)]
-    picks, mine, info = share(ents, costs, 3 * world, 1.0e15)
+    picks, mine, info = share(ents, costs, 3, 1.0e15)
     tsc = TranceptionScorer(cfg, tstate, precision=a.precision, device=local_rank)
     frames = []
     for i in mine:
@@ -323,7 +323,7 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
     _, per_rank, tw = timed(lambda: [tsc.score_mutants(df, seq, indel_mode=True) for seq, df in frames])
     record("config4: Tranception-L (36x1280, 20 heads, n_ctx 1024) autoregressive scoring, both directions + WT, synthetic indel assays "
            "with the lengths / variant counts of reference_files/DMS_indels.csv, LPT over the ranks",
-           f"{len(picks)} of {len(ents)} assays (evenly spaced over the cost-sorted list, {info.get('dropped_over_cap')} over the cap dropped); "
+           f"{len(picks)} of {len(ents)} assays ({info.get('classes')} size classes evenly spaced over the cost-sorted list x {world} neighbours per class, {info.get('dropped_over_cap')} over the cap dropped); "
            f"L = {[ents[i]['L'] for i in picks]}; variants capped at 2000 per assay",
            picks, costs, sum(nm[i] for i in picks), per_rank, tw)
     tsc.close()
@@ -332,7 +332,7 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
     ents = [e for e in shapes["substitutions"] if e["L"] <= 1022]
     nm = [min(e["n_mutants"], 500, 19 * e["L"]) for e in ents]
     costs = [workloads.tranception_cost(e, tarch, n) for e, n in zip(ents, nm)]
-    picks, mine, info = share(ents, costs, 2 * world, 1.0e15)
+    picks, mine, info = share(ents, costs, 2, 1.0e15)
     esc = TranceptEVEScorer(cfg, tstate, full_target_seq="M", precision=a.precision, device=local_rank)
     jobs = []
     for i in mine:
@@ -358,7 +358,7 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
     _, per_rank, tw = timed(lambda: run5(jobs))
     record("config5: TranceptEVE (Tranception-L + MSA prior + EVE prior fused in the LM-head kernel), synthetic substitution assays shaped "
            "like DMS_substitutions with synthetic [L,25] log-priors (SURVEY.md §8d), LPT over the ranks",
-           f"{len(picks)} of the {len(ents)} assays with L <= 1022, evenly spaced over the cost-sorted list; L = "
+           f"{len(picks)} of the {len(ents)} assays with L <= 1022 ({info.get('classes')} size classes evenly spaced over the cost-sorted list x {world} neighbours per class); L = "
            f"{[ents[i]['L'] for i in picks]}; mutants capped at 500 per assay",
            picks, costs, sum(nm[i] for i in picks), per_rank, tw,
            extra={"prefix_reuse_token_rows": {"plain": esc.reuse_rows[0], "run": esc.reuse_rows[1]} if esc.reuse_rows else None})
@@ -368,8 +368,12 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
 
 
 def main():
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL's version banner, the progress lines the
+    # scoring engines print like the reference does) goes to stderr from here on
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(json_fd, "w")
     a = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -406,7 +410,7 @@ def main():
                                            "extrapolated": True,
                                            "note": "one CPU process on rank 0 at every --gpus N (the reference's CPU path has no multi-GPU form)"},
                           "e2e": {"value": v, "unit": "mutants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}))
+                          "gpu_launches": 0}), file=json_out, flush=True)
         return
 
     # ------------------------------------------------------------------------------------------------------ our arm
@@ -516,6 +520,33 @@ def main():
             res["e2e"] = {"value": world * a.steps * n_mut / float(e2e_s.item()), "unit": "mutants/s",
                           "h2d_bytes_per_step": int(preps[a.warmup][0].numel() * 4), "d2h_bytes_per_step": int(n_mut * 4),
                           "bit_identical_to_resident_leg": bool(same)}
+        # ---- leg 4 (N > 1): strong scaling — ONE assay per step, its masked positions partitioned over the ranks, the [P, vocab]
+        #      table completed by one NCCL all-gather per step (compute_fitness --partition positions) ----
+        if with_e2e and dist is not None:
+            log(f"measure {precision}: strong-scaling leg")
+            seq0, muts0 = make_assay(0, L, n_mut)
+            h0, z0 = scorer.prepare_assay(seq0, muts0)
+            d0 = h0.to(scorer.device)
+            for s in range(max(1, a.warmup)):
+                sc = scorer.run_assay(h0, z0, dev=d0, shard=(rank, world))
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for s in range(a.steps):
+                sc = scorer.run_assay(h0, z0, dev=d0, shard=(rank, world))
+            s1.record()
+            barrier()
+            sms = torch.tensor([s0.elapsed_time(s1)], device="cuda")
+            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+            ref = sc.clone()
+            dist.broadcast(ref, src=0)
+            same = torch.tensor([int(torch.equal(ref, sc))], device="cuda")
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            res["strong_scaling"] = {"workload": "ONE config-2 assay per step, masked positions partitioned over the ranks "
+                                                 "(--partition positions), one all-gather of the table per step",
+                                     "value": a.steps * n_mut / (float(sms.item()) / 1e3), "unit": "mutants/s", "scaling": "strong",
+                                     "ms_per_step": float(sms.item()) / a.steps, "n_gpus": world,
+                                     "scores_identical_on_every_rank": bool(same.item())}
         # ---- roofline of the dominant kernel (tcgen05 GEMM) from the event timings of leg 2 ----
         cats = {n: {"ms": float(cat_ms[i]), "launches": int(cat_n[i])} for i, n in enumerate(_lib.PROFILE_CATEGORIES) if cat_n[i]}
         P = preps[a.warmup][1]["P"]
@@ -586,6 +617,8 @@ def main():
         {"precision_mode": m, "dtype": DT[m], "value": r["value"], "unit": "mutants/s", "ms_per_step": r["ms_per_step"], "clocks": r["clocks"],
          "roofline": {k: r["roofline"][k] for k in ("achieved", "frac", "issued_tflops", "issued_frac", "whole_step",
                                                     "kernel_ms_in_timed_region", "secondary")}} for m, r in others]
+    if "strong_scaling" in main_res:
+        out["strong_scaling"] = main_res["strong_scaling"]
     if extra is not None:
         out["other_workloads"] = extra
 
@@ -595,7 +628,7 @@ def main():
         v, info = cpu_mutants_per_s(arch, cpu_state, a.cpu_seconds, threads, L, n_mut)
         out["cpu_baseline"] = {"value": v, "unit": "mutants/s", "cores": info["threads"], "host_cpus": threads, "kind": info["kind"],
                                "sample": cpu_sample_text(info), "extrapolated": True}
-    print(json.dumps(out))
+    print(json.dumps(out), file=json_out, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

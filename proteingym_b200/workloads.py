@@ -35,15 +35,23 @@ def tranception_cost(entry: dict, arch, n_mutants: int) -> float:
     return 2.0 * (n_mutants + 1) * T * per_tok
 
 
-def pick_subset(entries, costs, k: int, cost_cap: float):
-    """k entries spread evenly over the cost-sorted list of those with cost <= cost_cap. Returns (indices, info)."""
+def pick_subset(entries, costs, k: int, cost_cap: float, replicas: int = 1):
+    """k size classes spread evenly over the cost-sorted list of the entries with cost <= cost_cap, ``replicas`` neighbouring entries
+    of that list per class (weak scaling: N ranks score N distinct assays of each class, so an LPT assignment of the subset is as
+    balanced as one of the full benchmark; replicas = 1 is the plain evenly-spaced pick). Returns (indices, info)."""
     order = [i for i in sorted(range(len(entries)), key=lambda i: (costs[i], i)) if costs[i] <= cost_cap]
     dropped = len(entries) - len(order)
     k = min(k, len(order))
     if k == 0:
         return [], {"eligible": 0, "dropped_over_cap": dropped}
-    picks = sorted({order[int(round(j * (len(order) - 1) / max(1, k - 1)))] for j in range(k)}) if k > 1 else [order[len(order) // 2]]
-    info = {"eligible": len(order), "dropped_over_cap": dropped, "cost_cap_tflop": cost_cap / 1e12,
+    n = len(order)
+    centres = [int(round(j * (n - 1) / max(1, k - 1))) for j in range(k)] if k > 1 else [n // 2]
+    picks = set()
+    for c in centres:
+        start = min(max(c - replicas // 2, 0), max(n - replicas, 0))
+        picks.update(order[start:start + replicas])
+    picks = sorted(picks)
+    info = {"eligible": n, "dropped_over_cap": dropped, "cost_cap_tflop": cost_cap / 1e12, "classes": k, "replicas": replicas,
             "subset_cost_tflop": sum(costs[i] for i in picks) / 1e12, "all_cost_tflop": sum(costs) / 1e12}
     return picks, info
 
