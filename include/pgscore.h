@@ -25,8 +25,11 @@ enum pg_status { PG_OK = 0, PG_ERR_ARG = 1, PG_ERR_CUDA = 2, PG_ERR_STATE = 3, P
 enum pg_arch {
   PG_ARCH_ESM1B = 0, /* ESM-1b / ESM-1v: learned positions (esm/model/esm1.py:83-102) */
   PG_ARCH_ESM2 = 1,  /* ESM2: rotary (esm/model/esm2.py:40-74) */
-  PG_ARCH_TRANCEPTION = 2 /* Tranception decoder: grouped ALiBi, depthwise-conv q/k/v, relu^2 MLP
-                             (tranception/model_pytorch.py:90-632); max_positions = n_ctx, vocab = 25 */
+  PG_ARCH_TRANCEPTION = 2, /* Tranception decoder: grouped ALiBi, depthwise-conv q/k/v, relu^2 MLP
+                              (tranception/model_pytorch.py:90-632); max_positions = n_ctx, vocab = 25 */
+  PG_ARCH_MSA = 3          /* MSA Transformer: tied row attention + column attention + FFN per layer, learned column positions and
+                              (when the state holds "msa_position_embedding") row positions (esm/model/msa_transformer.py:100-222,
+                              esm/axial_attention.py) */
 };
 
 /* Tensor-core operand precision. The reference is strict fp32. Every operand is an fp16 pair hi + lo.
@@ -84,6 +87,15 @@ const char* pg_last_error(pg_handle h); /* h may be NULL: returns the last creat
 int pg_masked_marginals(pg_handle h, const int32_t* tokens, int32_t n_tokens, const int32_t* positions,
                         const int32_t* win_start, const int32_t* out_row, int32_t P, int32_t T, float* out_logprobs,
                         pg_stream stream);
+
+/* Replaces the MSA Transformer masked-marginals loop (compute_fitness.py:383-399; model call msa_transformer.py:150-222): `tokens` is
+ * the sampled alignment as [R, C_full] token ids (BOS column included, row 0 = the target, no padding); for every p the token at
+ * (row 0, column positions[p]) is replaced by <mask>, the whole alignment — or its window of Cw columns starting at win_start[p] when
+ * C_full > 1024 (win_start null: 0) — is forwarded, and out_logprobs[p, :] = log_softmax(logits[row 0, column positions[p]]).
+ * PG_ARCH_MSA handles only. All pointers are device memory. Several positions are processed per pass (max_rows / (R * Cw), at least 1
+ * alignment must fit). */
+int pg_msa_masked_marginals(pg_handle h, const int32_t* tokens, int32_t R, int32_t C_full, const int32_t* positions,
+                            const int32_t* win_start, int32_t P, int32_t Cw, float* out_logprobs, pg_stream stream);
 
 /* Full-table variant used by wt-marginals (compute_fitness.py:475): one unmasked (or arbitrarily masked) forward of
  * `T` tokens starting at `win_start`, emitting log_softmax for every token: out [T, vocab]. mask_pos = -1 for none. */

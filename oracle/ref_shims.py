@@ -1,7 +1,9 @@
 """ORACLE SUPPORT — TEST INFRASTRUCTURE ONLY (build container only: needs /root/reference).
 
 Makes the UNMODIFIED reference ESM scorer importable/runnable on CPU with torch 2.11:
-  1. stub ``Bio`` modules (Biopython is absent; imported at compute_fitness.py:9 and utils/msa_utils.py:9-11),
+  1. stub ``Bio`` modules (Biopython is absent; imported at compute_fitness.py:9 and utils/msa_utils.py:9-11); ``SeqIO.parse`` gets a
+     minimal FASTA reader (records with ``.description`` / ``.seq``), which is all the MSA Transformer path asks of it
+     (compute_fitness.py:31-37),
   2. ``torch.Tensor.cuda`` -> identity, because masked-marginals calls ``.cuda()`` unconditionally
      (compute_fitness.py:502) even with ``--nogpu``,
   3. ``torch.serialization.add_safe_globals([argparse.Namespace])`` (torch>=2.6 weights_only default vs
@@ -24,6 +26,28 @@ def available() -> bool:
     return os.path.isfile(os.path.join(ESM_DIR, "compute_fitness.py"))
 
 
+class _Record:
+    def __init__(self, description, seq):
+        self.description, self.id, self.seq = description, description.split()[0] if description else "", seq
+
+
+def _fasta_records(filename, fmt="fasta"):
+    """Stand-in for Bio.SeqIO.parse(filename, "fasta"): yields records in file order."""
+    assert fmt == "fasta"
+    name, parts = None, []
+    with open(filename) as fh:
+        for line in fh:
+            line = line.rstrip("\n")
+            if line.startswith(">"):
+                if name is not None:
+                    yield _Record(name, "".join(parts))
+                name, parts = line[1:], []
+            elif name is not None:
+                parts.append(line.strip())
+    if name is not None:
+        yield _Record(name, "".join(parts))
+
+
 def install():
     """Idempotent. Returns the reference ``compute_fitness`` module."""
     import torch
@@ -34,6 +58,7 @@ def install():
             m = types.ModuleType(name)
             sys.modules[name] = m
     sys.modules["Bio"].SeqIO = sys.modules["Bio.SeqIO"]
+    sys.modules["Bio.SeqIO"].parse = _fasta_records
     sys.modules["Bio.SeqRecord"].SeqRecord = object
     sys.modules["Bio.Seq"].Seq = object
     torch.serialization.add_safe_globals([argparse.Namespace])

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpgscore.so")
 
-PG_ARCH_ESM1B, PG_ARCH_ESM2, PG_ARCH_TRANCEPTION = 0, 1, 2
+PG_ARCH_ESM1B, PG_ARCH_ESM2, PG_ARCH_TRANCEPTION, PG_ARCH_MSA = 0, 1, 2, 3
 PG_PREC_F16, PG_PREC_F16X3, PG_PREC_F16F8 = 0, 1, 2
 
 
@@ -53,6 +53,8 @@ SIGNATURES = {
     "pg_last_error": (C.c_char_p, [C.c_void_p]),
     "pg_masked_marginals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_void_p, C.c_void_p]),
+    "pg_msa_masked_marginals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                          C.c_void_p, C.c_void_p]),
     "pg_forward_logprobs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p]),
     "pg_score_mutants": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -20,7 +20,7 @@ MASK_IDX = 32
 
 @dataclass
 class EsmConfig:
-    arch: str            # "esm1b" (ESM-1b / ESM-1v, learned positions) | "esm2" (rotary)
+    arch: str            # "esm1b" (ESM-1b / ESM-1v, learned positions) | "esm2" (rotary) | "msa" (MSA Transformer)
     layers: int
     embed_dim: int
     heads: int
@@ -78,6 +78,60 @@ def load_esm_checkpoint(model_location: str):
              if not k.startswith("contact_head") and k != "lm_head.weight"}
     state["embed_tokens.weight"] = tied.detach().to(torch.float32).contiguous()
     return conf, state, checkpoint_column_name(model_location)
+
+
+def _msa_model_key(name: str) -> str:
+    """File key -> model key of an msa_transformer checkpoint (pretrained.py:107-115): the loader swaps "row" and "column" in every
+    name (the first release stored the two attention blocks under each other's names), then strips the encoder prefixes."""
+    if "row" in name:
+        name = name.replace("row", "column")
+    else:
+        name = name.replace("column", "row")
+    return _strip_v1(name)
+
+
+def load_msa_checkpoint(model_location: str):
+    """-> (EsmConfig with arch "msa", state: dict[str, fp32 CPU tensor], score column name) for a fair-esm ``msa_transformer`` file.
+    ``msa_position_embedding`` is returned as [1024, embed_dim] (the first release's [1, 1024, 1, 1] table broadcasts over the width,
+    msa_transformer.py:166-168); absent when the checkpoint was trained without it."""
+    path = Path(model_location)
+    if not str(model_location).endswith(".pt"):
+        raise ValueError("only local .pt checkpoints are supported (no network): " + str(model_location))
+    with torch.serialization.safe_globals([argparse.Namespace]):
+        data = torch.load(str(path), map_location="cpu", weights_only=True)
+    args = data["args"]
+    if args.arch != "msa_transformer":
+        raise ValueError(f"not an msa_transformer checkpoint: {args.arch!r}")
+    raw = {_msa_model_key(k): v for k, v in data["model"].items()}
+    get = lambda n, dflt=None: getattr(args, n, getattr(args, "encoder_" + n, dflt))
+    conf = EsmConfig("msa", int(get("layers")), int(get("embed_dim")), int(get("attention_heads")), int(get("ffn_embed_dim")),
+                     False, True, int(get("max_positions", 1024)))
+    tied = raw["lm_head.weight"] if "lm_head.weight" in raw else raw["embed_tokens.weight"]
+    state = {k: v.detach().to(torch.float32).contiguous() for k, v in raw.items()
+             if not k.startswith("contact_head") and k != "lm_head.weight"}
+    state["embed_tokens.weight"] = tied.detach().to(torch.float32).contiguous()
+    if get("embed_positions_msa", False) and "msa_position_embedding" in state:
+        state["msa_position_embedding"] = normalise_row_positions(state["msa_position_embedding"], conf.embed_dim)
+    else:
+        state.pop("msa_position_embedding", None)
+    return conf, state, checkpoint_column_name(model_location)
+
+
+def normalise_row_positions(t: torch.Tensor, d: int) -> torch.Tensor:
+    t = t.to(torch.float32).reshape(1024, -1)
+    return t.expand(1024, d).contiguous()
+
+
+def config_from_msa_synth(arch) -> EsmConfig:
+    return EsmConfig("msa", arch.layers, arch.embed_dim, arch.heads, arch.ffn_dim, False, True, arch.max_positions, arch.vocab)
+
+
+def normalise_msa_synth_state(arch, st: dict) -> dict:
+    """Apply to an in-memory ``synth.make_msa_state`` dict what ``load_msa_checkpoint`` does to a file."""
+    st = {k: v.to(torch.float32).contiguous() for k, v in st.items() if k != "lm_head.weight"}
+    if "msa_position_embedding" in st:
+        st["msa_position_embedding"] = normalise_row_positions(st["msa_position_embedding"], arch.embed_dim)
+    return st
 
 
 def config_from_synth(arch) -> EsmConfig:

@@ -1,12 +1,13 @@
-"""Drop-in for ``proteingym/baselines/esm/compute_fitness.py`` (ESM-1b / ESM-1v / ESM2 branch).
+"""Drop-in for ``proteingym/baselines/esm/compute_fitness.py``: the ESM-1b / ESM-1v / ESM2 branch and the MSA Transformer branch.
 
 Same flags, same DMS/mapping resolution, same output CSV (all input columns + one float column per checkpoint named by the
-file stem + ``Ensemble_ESM1v`` when ``"ESM1v" in --model_type``), so ``scripts/scoring_DMS_zero_shot/scoring_ESM1v_substitutions.sh``
-and ``scoring_ESM2_substitutions.sh`` work with only the script path changed. Reference line numbers refer to
+file stem + ``Ensemble_ESM1v`` when ``"ESM1v" in --model_type``; for the MSA Transformer one ``<checkpoint>_seed<s>`` column per seed +
+``<checkpoint>_ensemble``), so ``scripts/scoring_DMS_zero_shot/scoring_ESM1v_substitutions.sh``, ``scoring_ESM2_substitutions.sh`` and
+``scoring_MSA_transformer_substitutions.sh`` work with only the script path changed. Reference line numbers refer to
 proteingym/baselines/esm/compute_fitness.py.
 
-Not reproduced (out of scope): the MSA Transformer branch (:360-425) and hhfilter/MSA sampling — selecting
-``--model_type MSA_transformer`` raises NotImplementedError. Additive flags: ``--precision``, ``--device``.
+Not reproduced: ``--filter-msa`` (the reference shells out to the external hhfilter binary, :78-89) and pseudo-ppl with the MSA
+Transformer (:406-418); both fail loudly. Additive flags: ``--precision``, ``--device``.
 """
 from __future__ import annotations
 
@@ -25,7 +26,7 @@ if __package__ in (None, ""):
 # (flags, kwargs) — the reference parser's option names, types, defaults, nargs and choices (checked one by one against a dump of
 # the reference's create_parser() in tests/golden/esm_cli_flags.json); help texts are ours.
 _FLAGS = [
-    (("--model_type",), dict(type=str, default="MSA_transformer", nargs="+", help="ESM1v | ESM1b | ESM2 (MSA_transformer is not handled here)")),
+    (("--model_type",), dict(type=str, default="MSA_transformer", nargs="+", help="MSA_transformer | ESM1v | ESM1b | ESM2")),
     (("--model-location",), dict(type=str, nargs="+", help="one or more local fair-esm .pt checkpoints; one output column each")),
     (("--sequence",), dict(type=str, help="wild-type sequence (filled from the mapping file when --dms_index is given)")),
     (("--dms-input",), dict(type=pathlib.Path, help="DMS CSV, or the folder holding the DMS CSVs when --dms_index is given")),
@@ -69,8 +70,11 @@ def create_parser():
 
 
 def resolve_assay(args):
-    """DMS / mapping resolution of the reference's ``main`` (:286-343). Returns (df, mutant_col, offset_idx)."""
+    """DMS / mapping resolution of the reference's ``main`` (:286-343). Returns (df, mutant_col, offset_idx); for the MSA Transformer
+    it also sets args.msa_path / args.MSA_start / args.MSA_end / args.msa_weight_file and trims args.sequence to the aligned range."""
     mutant_col = args.mutation_col
+    msa = "MSA_transformer" in args.model_type
+    args.msa_weight_file = None
     if args.dms_index is not None:
         mapping = pd.read_csv(args.dms_mapping)
         DMS_id = mapping["DMS_id"][args.dms_index]
@@ -86,11 +90,29 @@ def resolve_assay(args):
         mutant_col = row["DMS_mutant_column"] if "DMS_mutant_column" in mapping.columns else mutant_col
         args.dms_output = str(args.dms_output) + os.sep + DMS_id + ".csv"
         offset = row["start_idx"] if "start_idx" in mapping.columns and row["start_idx"] != "" else 1
+        if msa:  # :308-326
+            end = offset + len(args.sequence)
+            if row["MSA_filename"] == "":
+                raise ValueError("No MSA found for DMS: " + str(DMS_id))
+            args.msa_path = str(args.msa_path) + os.sep + row["MSA_filename"]
+            args.MSA_start = int(row["MSA_start"]) if "MSA_start" in mapping.columns else 1
+            args.MSA_end = int(row["MSA_end"]) if "MSA_end" in mapping.columns else len(args.sequence)
+            if "weight_file_name" in mapping.columns and args.msa_weights_folder is not None:
+                args.msa_weight_file = args.msa_weights_folder + os.sep + row["weight_file_name"]
+            if offset != args.MSA_start or end != args.MSA_end:
+                args.sequence = args.sequence[args.MSA_start - 1:args.MSA_end]
     else:
         DMS_id = str(args.dms_input).split(os.sep)[-1].split(".csv")[0]
         args.dms_output = str(args.dms_output) + os.sep + DMS_id + ".csv"
         offset = args.offset_idx
         args.sequence = args.target_seq.upper()
+        if msa:  # :333-340
+            if args.MSA_start is None or args.MSA_end is None:
+                if args.msa_path:
+                    print("MSA start and end not provided -- Assuming the MSA is covering the full WT sequence")
+                args.MSA_start, args.MSA_end = 1, len(args.target_seq)
+            if args.msa_weights_folder is not None:
+                args.msa_weight_file = args.msa_weights_folder + os.sep + args.weight_file_name
     df = pd.read_csv(args.dms_input)
     if len(df) == 0:
         raise ValueError("No rows found in the dataframe")
@@ -123,18 +145,75 @@ def score_model(scorer, args, df, mutant_col, offset_idx) -> np.ndarray:
     raise ValueError(args.scoring_strategy)
 
 
+def main_msa_transformer(args, df, mutant_col):
+    """The MSA Transformer branch of the reference's model loop (:360-425) and its ensemble column (:538-542)."""
+    from proteingym_b200 import msa_engine
+    from proteingym_b200.checkpoint import load_msa_checkpoint
+    from proteingym_b200.esm_engine import choose_precision
+    assert args.scoring_strategy in ["masked-marginals", "pseudo-ppl"], "Zero-shot scoring strategy not supported with MSA Transformer"
+    if args.scoring_strategy == "pseudo-ppl":
+        raise NotImplementedError("pseudo-ppl with the MSA Transformer (compute_fitness.py:406-418) is not part of the B200 path")
+    seeds = [args.seeds] if isinstance(args.seeds, int) else list(args.seeds)
+    offset_idx = args.MSA_start
+    name = None
+    for model_location in args.model_location:
+        config, state, name = load_msa_checkpoint(model_location)
+        processed = None
+        if args.msa_sampling_strategy == "sequence-reweighting":
+            processed = msa_engine.process_msa(str(args.msa_path), args.msa_weight_file, args.filter_msa, device=args.device)
+        elif args.filter_msa:
+            msa_engine.process_msa(str(args.msa_path), args.msa_weight_file, True)
+        scorer = None
+        precision = choose_precision(config, df[mutant_col], args.scoring_strategy) if args.precision == "auto" else args.precision
+        for seed in seeds:
+            col = f"{name}_seed{seed}"
+            if os.path.exists(args.dms_output):  # :365-372
+                prior = pd.read_csv(args.dms_output)
+                if col in prior.columns and not args.overwrite_prior_scores:
+                    print(f"Skipping seed {seed} as it is already in the dataframe")
+                    df = prior
+                    continue
+            rows = msa_engine.sample_msa(filename=str(args.msa_path), nseq=args.msa_samples, sampling_strategy=args.msa_sampling_strategy,
+                                         random_seed=seed, weight_filename=args.msa_weight_file, processed_msa=processed,
+                                         device=args.device)
+            R, C = len(rows), len(rows[0][1]) + 1
+            print(f"Batch sizes: torch.Size([1, {R}, {C}])")
+            need = msa_engine.default_max_rows(config, R, min(C, 1024), 1 if precision == "f16" else 2)
+            if scorer is None or scorer.max_rows < R * min(C, 1024):
+                if scorer is not None:
+                    scorer.close()
+                scorer = msa_engine.MsaScorer(config, state, precision=precision, device=args.device, max_rows=need)
+                print("Scoring with {} and model {} (operand precision {})".format(args.scoring_strategy, name, precision))
+            df[col] = scorer.score_assay(rows, args.sequence, list(df[mutant_col]), offset_idx).astype(np.float64)
+            if os.path.exists(args.dms_output) and not args.overwrite_prior_scores:  # :419-423
+                prior = pd.read_csv(args.dms_output)
+                assert col not in prior.columns, f"Column {col} already exists in {args.dms_output}"
+                prior = prior.merge(df[[col, "mutant"]], on="mutant")
+                prior.to_csv(args.dms_output, index=False)
+                df = prior
+            else:
+                df.to_csv(args.dms_output, index=False)
+        if scorer is not None:
+            scorer.close()
+    df[f"{name}_ensemble"] = 0.0
+    for seed in seeds:
+        df[f"{name}_ensemble"] += df[f"{name}_seed{seed}"]
+    df[f"{name}_ensemble"] /= len(seeds)
+    df.to_csv(args.dms_output, index=False)
+
+
 def main(args):
     from proteingym_b200.checkpoint import load_esm_checkpoint
     from proteingym_b200.esm_engine import EsmScorer, choose_precision
     if not os.path.exists(args.dms_output):
         os.mkdir(args.dms_output)
     print("Arguments:", args)
-    if "MSA_transformer" in args.model_type:
-        raise NotImplementedError("MSA Transformer scoring is outside the B200 hot path (use the reference script)")
     if args.nogpu:
         raise RuntimeError("--nogpu: this scorer is the B200 path and has no CPU fallback (use the reference script)")
     df, mutant_col, offset_idx = resolve_assay(args)
     print("Starting model scoring")
+    if "MSA_transformer" in args.model_type:
+        return main_msa_transformer(args, df, mutant_col)
     for model_location in args.model_location:
         config, state, name = load_esm_checkpoint(model_location)
         if config.arch != "esm2" and len(args.sequence) + 2 > 1024 and args.scoring_strategy == "wt-marginals" \

@@ -20,7 +20,7 @@ int set_error(int code, const std::string& msg) {
 }
 int launch_attention_tc(const AttnLaunch& a, cudaStream_t s) {
   static const bool old = getenv("PG_ATTN_TC3") != nullptr;
-  return old ? launch_attention_tc3(a, s) : launch_attention_tc4(a, s);
+  return (old && !a.perm_C) ? launch_attention_tc3(a, s) : launch_attention_tc4(a, s);
 }
 
 int num_sms() {  // of the current device (cached per ordinal: one process may hold handles on several GPUs)
@@ -205,6 +205,11 @@ struct pg_handle_s {
   __half *raw_cache = nullptr, *kv_cache = nullptr;
   int prefix_T = 0;        // rows recorded by the last pg_ar_prefix_begin (0 = none)
   int prefix_cap = 0;      // rows the caches can hold
+  // MSA Transformer: column-attention blocks (ln1*, wqkv, wo of a Layer), row-position table, tied-attention workspace
+  std::vector<pg::Layer> col_layers;
+  float* row_pos = nullptr;         // [1024, d] or null
+  void* tied_ws = nullptr;          // one allocation, regrown on demand (not in `allocs`)
+  size_t tied_bytes = 0;
   // compact buffers for the pruned last layer (one row per sequence)
   float* xc = nullptr;
   __half *cabuf = nullptr, *cfbuf = nullptr;
@@ -399,6 +404,121 @@ int forward_tranception(pg_handle h, const int32_t* ids, int B, int T, cudaStrea
   return PG_OK;
 }
 
+// MSA Transformer stack (msa_transformer.py:150-222) over Bc masked copies of an [R, Cw] alignment window; token rows are (b, r, c)
+// with c fastest. Per layer (AxialTransformerLayer, modules.py:205-235): tied row attention, column attention, FFN, each a pre-LN
+// residual block. The tied attention's two products run as grouped GEMMs on regrouped operands (msa_transformer.cu), always with fp16
+// hi/lo pairs when the handle has them (x3: they are < 10 % of the FLOPs); the column attention is the tcgen05 attention kernel over
+// the B*Cw columns as sequences of R rows, fed by a LayerNorm that writes its rows in (b, c, r) order.
+int forward_msa(pg_handle h, const int32_t* tokens, int R, int Cfull, const int32_t* positions, const int32_t* win_start, int p_offset,
+                int Bc, int Cw, cudaStream_t s) {
+  const pg_model_desc& D = h->desc;
+  const int d = D.embed_dim, f = D.ffn_dim, np = h->np, H = D.heads;
+  const int afmt = h->nseg == 2 ? 2 : (np == 2 ? 1 : 0);
+  const int qfmt = np == 2 ? 1 : 0;
+  const int64_t ldd = static_cast<int64_t>(d) * np, ldf = static_cast<int64_t>(f) * np, ldq = static_cast<int64_t>(3 * d) * np;
+  const int rows = Bc * R * Cw;
+  // tied-attention workspace: Q' / K' [G*Cp, Nt*np] (Q' doubles as the context buffer), V' [G*Nt, Kp*np], S fp32 [G*Cp, Kp], P [G*Cp, Kp*np]
+  const int G = Bc * H, Cp = (Cw + 255) / 256 * 256, Kp = (Cw + 63) / 64 * 64, Nt = R * 64;
+  const int64_t ldt = static_cast<int64_t>(Nt) * np, ldv = static_cast<int64_t>(Kp) * np, lds = Kp, ldp = static_cast<int64_t>(Kp) * np;
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t b_q = al(static_cast<size_t>(G) * Cp * ldt * 2), b_v = al(static_cast<size_t>(G) * Nt * ldv * 2);
+  const size_t b_s = al(static_cast<size_t>(G) * Cp * lds * 4), b_p = al(static_cast<size_t>(G) * Cp * ldp * 2);
+  const size_t need = 2 * b_q + b_v + b_s + b_p;
+  if (need > h->tied_bytes) {
+    if (h->tied_ws) cudaFree(h->tied_ws);
+    h->tied_ws = nullptr; h->tied_bytes = 0;
+    PG_CUDA_OK(cudaMalloc(&h->tied_ws, need));
+    h->tied_bytes = need;
+    PG_CUDA_OK(cudaMemsetAsync(h->tied_ws, 0, need, s));
+  }
+  uint8_t* ws = static_cast<uint8_t*>(h->tied_ws);
+  __half* tq = reinterpret_cast<__half*>(ws);
+  __half* tk = reinterpret_cast<__half*>(ws + b_q);
+  __half* tv = reinterpret_cast<__half*>(ws + 2 * b_q);
+  float* S = reinterpret_cast<float*>(ws + 2 * b_q + b_v);
+  __half* P = reinterpret_cast<__half*>(ws + 2 * b_q + b_v + b_s);
+  int rc;
+  MsaEmbedLaunch e{};
+  e.tokens = tokens; e.R = R; e.Cfull = Cfull; e.positions = positions; e.win_start = win_start; e.p_offset = p_offset;
+  e.B = Bc; e.Cw = Cw; e.d = d; e.embed = h->embed; e.pos_table = h->pos; e.row_pos = h->row_pos;
+  e.gamma = h->lnbg; e.beta = h->lnbb; e.mask_idx = 32; e.x = h->x;
+  { ProfScope ps(CAT_EMBED, s); rc = launch_msa_embed(e, s); }
+  if (rc) return rc;
+  auto ln = [&](const float* g, const float* b, int pR, int pC) {
+    ProfScope ps(CAT_LN, s);
+    return launch_layernorm_f16(h->x, d, g, b, rows, d, h->abuf, ldd, np == 2 ? d : 0, s, afmt, S_LN, pR, pC);
+  };
+  const float row_scale = 1.0f / sqrtf(static_cast<float>(R));  // align_scaling (axial_attention.py:78-80); head_dim^-1/2 is in the weights
+  for (int l = 0; l < D.layers; ++l) {
+    const Layer& L = h->layers[l];
+    const Layer& CL = h->col_layers[l];
+    // ---- tied row attention
+    rc = ln(L.ln1g, L.ln1b, 0, 0);
+    if (rc) return rc;
+    Lin q{h->abuf, ldd, S_LN, L.wqkv, L.iqkv, L.bqkv, rows, 3 * d, d, 0};
+    q.out = h->qkv; q.out_fmt = qfmt;
+    rc = run_lin(h, CAT_GEMM_QKV, q, s);
+    if (rc) return rc;
+    { ProfScope ps(CAT_OTHER, s, 2);
+      rc = launch_tied_gather_qk(h->qkv, ldq, np == 2 ? 3 * d : 0, Bc, R, Cw, H, Cp, tq, tk, ldt, s);
+      if (!rc) rc = launch_tied_transpose_v(h->qkv, ldq, np == 2 ? 3 * d : 0, Bc, R, Cw, H, Kp, tv, ldv, s); }
+    if (rc) return rc;
+    PG_CUDA_OK(cudaMemsetAsync(S, 0, b_s, s));
+    { GemmLaunch g{};
+      g.a = tq; g.lda = ldt; g.w = tk; g.ldw = ldt; g.M = G * Cp; g.N = Cw; g.K = Nt; g.nseg = np == 2 ? 3 : 1; g.epi = 2;
+      g.resid = S; g.ldr = lds; g.grp_rows_a = Cp; g.grp_rows_b = Cp;
+      ProfScope ps(CAT_ATTN, s);
+      rc = launch_gemm(g, s); }
+    if (rc) return rc;
+    { ProfScope ps(CAT_OTHER, s);
+      rc = launch_tied_softmax(S, lds, G, Cw, Cp, Kp, row_scale, P, ldp, np, s); }
+    if (rc) return rc;
+    { GemmLaunch g{};
+      g.a = P; g.lda = ldp; g.w = tv; g.ldw = ldv; g.M = G * Cp; g.N = Nt; g.K = Kp; g.nseg = np == 2 ? 3 : 1; g.epi = 0;
+      g.out = tq; g.ldo = ldt; g.out_fmt = afmt; g.out_lo_off = afmt ? Nt : 0; g.out_scale = S_ATT;
+      g.grp_rows_a = Cp; g.grp_rows_b = Nt;
+      ProfScope ps(CAT_ATTN, s);
+      rc = launch_gemm(g, s); }
+    if (rc) return rc;
+    { ProfScope ps(CAT_OTHER, s, afmt == 2 ? 3 : (afmt == 1 ? 2 : 1));
+      rc = launch_tied_scatter_out(tq, ldt, h->abuf, ldd, afmt, Bc, R, Cw, H, Cp, s); }
+    if (rc) return rc;
+    Lin o{h->abuf, ldd, S_ATT, L.wo, L.io, L.bo, rows, d, d, 2};
+    o.resid = h->x;
+    rc = run_lin(h, CAT_GEMM_OUT, o, s);
+    if (rc) return rc;
+    // ---- column attention: rows regrouped to (b, c, r) by the LayerNorm, back to (b, r, c) by the attention kernel
+    rc = ln(CL.ln1g, CL.ln1b, R, Cw);
+    if (rc) return rc;
+    Lin q2{h->abuf, ldd, S_LN, CL.wqkv, CL.iqkv, CL.bqkv, rows, 3 * d, d, 0};
+    q2.out = h->qkv; q2.out_fmt = qfmt;
+    rc = run_lin(h, CAT_GEMM_QKV, q2, s);
+    if (rc) return rc;
+    AttnLaunch a{};
+    a.qkv = h->qkv; a.ld = ldq; a.lo_off = np == 2 ? 3 * d : 0;
+    a.out = h->abuf; a.ldo = ldd; a.out_lo_off = np == 2 ? d : 0; a.out_fmt = afmt; a.out_scale = S_ATT;
+    a.B = Bc * Cw; a.T = R; a.heads = H; a.nseg = np == 2 ? 3 : 1; a.causal = 0; a.alibi_slopes = nullptr; a.perm_C = Cw;
+    { ProfScope ps(CAT_ATTN, s); rc = launch_attention_tc(a, s); }
+    if (rc) return rc;
+    Lin o2{h->abuf, ldd, S_ATT, CL.wo, CL.io, CL.bo, rows, d, d, 2};
+    o2.resid = h->x;
+    rc = run_lin(h, CAT_GEMM_OUT, o2, s);
+    if (rc) return rc;
+    // ---- feed-forward
+    rc = ln(L.ln2g, L.ln2b, 0, 0);
+    if (rc) return rc;
+    Lin f1{h->abuf, ldd, S_LN, L.w1, L.i1, L.b1, rows, f, d, 1};
+    f1.out = h->fbuf; f1.out_fmt = afmt; f1.out_scale = S_GELU;
+    rc = run_lin(h, CAT_GEMM_FC1, f1, s);
+    if (rc) return rc;
+    Lin f2{h->fbuf, ldf, S_GELU, L.w2, L.i2, L.b2, rows, d, f, 2};
+    f2.resid = h->x;
+    rc = run_lin(h, CAT_GEMM_FC2, f2, s);
+    if (rc) return rc;
+  }
+  return PG_OK;
+}
+
 HeadLaunch head_args(pg_handle h, int T) {
   HeadLaunch hl{};
   hl.x = h->x; hl.d = h->desc.embed_dim; hl.T = T;
@@ -415,7 +535,7 @@ using namespace pg;
 
 extern "C" {
 
-int pg_abi_version(void) { return 3; }
+int pg_abi_version(void) { return 4; }
 
 long long pg_launch_count(void) {
   std::lock_guard<std::mutex> lk(prof_mu());
@@ -460,7 +580,8 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
     return set_error(PG_ERR_ARG, "pg_create: non-positive model dimension");
   if (D.embed_dim != D.heads * 64) return set_error(PG_ERR_UNSUPPORTED, "pg_create: head_dim must be 64");
   if (D.embed_dim % 64 || D.ffn_dim % 64) return set_error(PG_ERR_UNSUPPORTED, "pg_create: embed_dim and ffn_dim must be multiples of 64");
-  if (D.arch != PG_ARCH_ESM1B && D.arch != PG_ARCH_ESM2 && D.arch != PG_ARCH_TRANCEPTION) return set_error(PG_ERR_UNSUPPORTED, "pg_create: unknown arch");
+  if (D.arch != PG_ARCH_ESM1B && D.arch != PG_ARCH_ESM2 && D.arch != PG_ARCH_TRANCEPTION && D.arch != PG_ARCH_MSA)
+    return set_error(PG_ERR_UNSUPPORTED, "pg_create: unknown arch");
   if (D.arch == PG_ARCH_TRANCEPTION && D.heads % 4) return set_error(PG_ERR_UNSUPPORTED, "pg_create: Tranception needs heads % 4 == 0 (model_pytorch.py:129-131)");
   if (D.precision != PG_PREC_F16 && D.precision != PG_PREC_F16X3 && D.precision != PG_PREC_F16F8)
     return set_error(PG_ERR_ARG, "pg_create: unknown precision");
@@ -489,6 +610,15 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
     if (h->nseg == 2) { A(&L.iqkv, 3 * d); A(&L.io, d); A(&L.i1, f); A(&L.i2, d); }
     if (D.arch == PG_ARCH_TRANCEPTION) A(&L.conv_taps, 3 * 4 * 64 * 8);
   }
+  if (D.arch == PG_ARCH_MSA) {
+    h->col_layers.resize(D.layers);
+    for (auto& L : h->col_layers) {
+      A(&L.wqkv, static_cast<size_t>(3) * d * d * np); A(&L.wo, static_cast<size_t>(d) * d * np);
+      A(&L.bqkv, 3 * d); A(&L.bo, d); A(&L.ln1g, d); A(&L.ln1b, d);
+      if (h->nseg == 2) { A(&L.iqkv, 3 * d); A(&L.io, d); }
+    }
+    A(&h->row_pos, static_cast<size_t>(1024) * d);
+  }
   if (D.arch == PG_ARCH_TRANCEPTION) {
     A(&h->qkv2, static_cast<size_t>(h->max_rows) * 3 * d * np);
     A(&h->tok_logp, static_cast<size_t>(h->max_rows));
@@ -496,7 +626,7 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
   }
   if (h->nseg == 2) A(&h->pack_scratch, static_cast<size_t>(D.layers) * 6);
   A(&h->embed, static_cast<size_t>(D.vocab) * d);
-  if (D.arch == PG_ARCH_ESM1B) A(&h->pos, static_cast<size_t>(D.max_positions + 2) * d);
+  if (D.arch == PG_ARCH_ESM1B || D.arch == PG_ARCH_MSA) A(&h->pos, static_cast<size_t>(D.max_positions + 2) * d);
   A(&h->lnbg, d); A(&h->lnbb, d); A(&h->lnag, d); A(&h->lnab, d);
   A(&h->hdw, static_cast<size_t>(d) * d); A(&h->hdb, d); A(&h->hlng, d); A(&h->hlnb, d); A(&h->hbias, D.vocab);
   A(&h->x, static_cast<size_t>(h->max_rows) * d);
@@ -522,6 +652,7 @@ int pg_destroy(pg_handle h) {
   if (!h) return PG_OK;
   cudaSetDevice(h->desc.device);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->tied_ws) cudaFree(h->tied_ws);
   delete h;
   return PG_OK;
 }
@@ -588,14 +719,13 @@ int pg_load_weights(pg_handle h, const pg_tensor* tensors, int32_t n) {
     return PG_OK;
   }
   const float qscale = 0.125f;  // head_dim^-1/2 with head_dim == 64 (multihead_attention.py:103,261); exact power of two
-  for (int l = 0; l < D.layers; ++l) {
-    Layer& L = h->layers[l];
-    const std::string p = "layers." + std::to_string(l) + ".";
+  // one attention block: q/k/v/out projections at `pa` ("...self_attn." / "...row_self_attention.layer."), its LayerNorm at `pl`
+  auto load_attn = [&](Layer& L, const std::string& pa, const std::string& pl) {
     const size_t dd = static_cast<size_t>(d) * d * np;
     if (f8) {  // q, k, v form ONE GEMM operand: one common e4m3 scale (matrix maximum over the three, q already scaled)
-      const float* wq = get(p + "self_attn.q_proj.weight", d, d);
-      const float* wk = get(p + "self_attn.k_proj.weight", d, d);
-      const float* wv = get(p + "self_attn.v_proj.weight", d, d);
+      const float* wq = get(pa + "q_proj.weight", d, d);
+      const float* wk = get(pa + "k_proj.weight", d, d);
+      const float* wv = get(pa + "v_proj.weight", d, d);
       if (wq && wk && wv) {
         unsigned int* word = h->pack_scratch + (h->pack_used++ % (D.layers * 6));
         const unsigned nb = static_cast<unsigned>((static_cast<long long>(d) * d + 255) / 256);
@@ -608,28 +738,50 @@ int pg_load_weights(pg_handle h, const pg_tensor* tensors, int32_t n) {
         pack_weight_f8_kernel<<<(d + 7) / 8, 256>>>(wv, d, d, d, 1, 1.f, word, L.wqkv + 2 * dd, L.iqkv + 2 * d);
       }
     } else {
-      pack(L.wqkv, nullptr, get(p + "self_attn.q_proj.weight", d, d), d, d, qscale);
-      pack(L.wqkv + dd, nullptr, get(p + "self_attn.k_proj.weight", d, d), d, d);
-      pack(L.wqkv + 2 * dd, nullptr, get(p + "self_attn.v_proj.weight", d, d), d, d);
+      pack(L.wqkv, nullptr, get(pa + "q_proj.weight", d, d), d, d, qscale);
+      pack(L.wqkv + dd, nullptr, get(pa + "k_proj.weight", d, d), d, d);
+      pack(L.wqkv + 2 * dd, nullptr, get(pa + "v_proj.weight", d, d), d, d);
     }
-    copy(L.bqkv, get(p + "self_attn.q_proj.bias", d, 1), d, qscale);
-    copy(L.bqkv + d, get(p + "self_attn.k_proj.bias", d, 1), d);
-    copy(L.bqkv + 2 * d, get(p + "self_attn.v_proj.bias", d, 1), d);
-    pack(L.wo, L.io, get(p + "self_attn.out_proj.weight", d, d), d, d);
-    copy(L.bo, get(p + "self_attn.out_proj.bias", d, 1), d);
-    pack(L.w1, L.i1, get(p + "fc1.weight", f, d), f, d);
-    copy(L.b1, get(p + "fc1.bias", f, 1), f);
-    pack(L.w2, L.i2, get(p + "fc2.weight", d, f), d, f);
-    copy(L.b2, get(p + "fc2.bias", d, 1), d);
-    copy(L.ln1g, get(p + "self_attn_layer_norm.weight", d, 1), d);
-    copy(L.ln1b, get(p + "self_attn_layer_norm.bias", d, 1), d);
-    copy(L.ln2g, get(p + "final_layer_norm.weight", d, 1), d);
-    copy(L.ln2b, get(p + "final_layer_norm.bias", d, 1), d);
+    copy(L.bqkv, get(pa + "q_proj.bias", d, 1), d, qscale);
+    copy(L.bqkv + d, get(pa + "k_proj.bias", d, 1), d);
+    copy(L.bqkv + 2 * d, get(pa + "v_proj.bias", d, 1), d);
+    pack(L.wo, L.io, get(pa + "out_proj.weight", d, d), d, d);
+    copy(L.bo, get(pa + "out_proj.bias", d, 1), d);
+    copy(L.ln1g, get(pl + "weight", d, 1), d);
+    copy(L.ln1b, get(pl + "bias", d, 1), d);
+  };
+  auto load_ffn = [&](Layer& L, const std::string& pf, const std::string& pl) {
+    pack(L.w1, L.i1, get(pf + "fc1.weight", f, d), f, d);
+    copy(L.b1, get(pf + "fc1.bias", f, 1), f);
+    pack(L.w2, L.i2, get(pf + "fc2.weight", d, f), d, f);
+    copy(L.b2, get(pf + "fc2.bias", d, 1), d);
+    copy(L.ln2g, get(pl + "weight", d, 1), d);
+    copy(L.ln2b, get(pl + "bias", d, 1), d);
+  };
+  for (int l = 0; l < D.layers; ++l) {
+    const std::string p = "layers." + std::to_string(l) + ".";
+    if (D.arch == PG_ARCH_MSA) {  // AxialTransformerLayer (modules.py:194-196): three NormalizedResidualBlocks {layer, layer_norm}
+      load_attn(h->layers[l], p + "row_self_attention.layer.", p + "row_self_attention.layer_norm.");
+      load_attn(h->col_layers[l], p + "column_self_attention.layer.", p + "column_self_attention.layer_norm.");
+      load_ffn(h->layers[l], p + "feed_forward_layer.layer.", p + "feed_forward_layer.layer_norm.");
+    } else {
+      load_attn(h->layers[l], p + "self_attn.", p + "self_attn_layer_norm.");
+      load_ffn(h->layers[l], p, p + "final_layer_norm.");
+    }
+  }
+  if (D.arch == PG_ARCH_MSA) {
+    auto it = by_name.find("msa_position_embedding");  // host-expanded to [1024, d] (the first release stores a 1-wide table)
+    if (it != by_name.end()) {
+      if (it->second->shape[0] != 1024 || it->second->shape[1] != d) missing += "msa_position_embedding(shape) ";
+      else copy(h->row_pos, static_cast<const float*>(it->second->data), static_cast<size_t>(1024) * d);
+    } else {
+      h->row_pos = nullptr;  // embed_positions_msa off (msa_transformer.py:106-114)
+    }
   }
   copy(h->embed, get("embed_tokens.weight", D.vocab, d), static_cast<size_t>(D.vocab) * d);
-  if (D.arch == PG_ARCH_ESM1B)
+  if (D.arch == PG_ARCH_ESM1B || D.arch == PG_ARCH_MSA)
     copy(h->pos, get("embed_positions.weight", D.max_positions + 2, d), static_cast<size_t>(D.max_positions + 2) * d);
-  if (D.emb_ln_before) {
+  if (D.emb_ln_before || D.arch == PG_ARCH_MSA) {
     copy(h->lnbg, get("emb_layer_norm_before.weight", d, 1), d);
     copy(h->lnbb, get("emb_layer_norm_before.bias", d, 1), d);
   }
@@ -666,6 +818,7 @@ int pg_masked_marginals(pg_handle h, const int32_t* tokens, int32_t n_tokens, co
   if (!h) return set_error(PG_ERR_ARG, "pg_masked_marginals: null handle");
   if (!h->loaded) return fail(h, PG_ERR_STATE, "pg_masked_marginals: weights not loaded");
   if (h->desc.arch == PG_ARCH_TRANCEPTION) return fail(h, PG_ERR_STATE, "pg_masked_marginals: handle is a Tranception model (use pg_ar_loglik)");
+  if (h->desc.arch == PG_ARCH_MSA) return fail(h, PG_ERR_STATE, "pg_masked_marginals: handle is an MSA Transformer (use pg_msa_masked_marginals)");
   if (!tokens || !positions || !out_logprobs) return fail(h, PG_ERR_ARG, "pg_masked_marginals: null buffer");
   if (P < 0 || T <= 0 || T > n_tokens) return fail(h, PG_ERR_ARG, "pg_masked_marginals: bad P/T");
   if (h->desc.arch == PG_ARCH_ESM1B && T > h->desc.max_positions)
@@ -691,11 +844,45 @@ int pg_masked_marginals(pg_handle h, const int32_t* tokens, int32_t n_tokens, co
   return PG_OK;
 }
 
+int pg_msa_masked_marginals(pg_handle h, const int32_t* tokens, int32_t R, int32_t C_full, const int32_t* positions,
+                            const int32_t* win_start, int32_t P, int32_t Cw, float* out_logprobs, pg_stream stream) {
+  if (!h) return set_error(PG_ERR_ARG, "pg_msa_masked_marginals: null handle");
+  if (!h->loaded) return fail(h, PG_ERR_STATE, "pg_msa_masked_marginals: weights not loaded");
+  if (h->desc.arch != PG_ARCH_MSA) return fail(h, PG_ERR_STATE, "pg_msa_masked_marginals: handle is not an MSA Transformer");
+  if (!tokens || !positions || !out_logprobs) return fail(h, PG_ERR_ARG, "pg_msa_masked_marginals: null buffer");
+  if (P < 0 || R <= 0 || Cw <= 0 || Cw > C_full) return fail(h, PG_ERR_ARG, "pg_msa_masked_marginals: bad P/R/Cw");
+  if (Cw > h->desc.max_positions) return fail(h, PG_ERR_ARG, "pg_msa_masked_marginals: window longer than the learned position table");
+  if (R > 1024 && h->row_pos) return fail(h, PG_ERR_ARG, "pg_msa_masked_marginals: the row-position table covers 1024 alignment rows (msa_transformer.py:163-168)");
+  if (Cw < C_full && !win_start) return fail(h, PG_ERR_ARG, "pg_msa_masked_marginals: windows need win_start");
+  const long long per_msa = static_cast<long long>(R) * Cw;
+  if (per_msa > h->max_rows) return fail(h, PG_ERR_ARG, "pg_msa_masked_marginals: one alignment exceeds the workspace (raise max_rows)");
+  PG_CUDA_OK(cudaSetDevice(h->desc.device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  long long per = h->max_rows / per_msa;
+  if (per > h->head_cap) per = h->head_cap;
+  for (int p0 = 0; p0 < P; p0 += static_cast<int>(per)) {
+    const int Bc = (P - p0) < per ? (P - p0) : static_cast<int>(per);
+    int rc = forward_msa(h, tokens, R, C_full, positions, win_start, p0, Bc, Cw, s);
+    if (rc) return fail(h, rc, tls_error());
+    row_select_kernel<<<(Bc + 255) / 256, 256, 0, s>>>(positions, win_start, nullptr, p0, Bc, h->row_sel);
+    rc = launch_gather_rows(h->x, h->row_sel, Bc, static_cast<int>(per_msa), h->desc.embed_dim, h->xc, s);
+    if (rc) return fail(h, rc, tls_error());
+    ProfScope ps(CAT_HEAD, s, 5);
+    HeadLaunch hl = head_args(h, 1);
+    hl.x = h->xc; hl.P = Bc; hl.all_rows = 1;
+    hl.out = out_logprobs + static_cast<long long>(p0) * h->desc.vocab;
+    rc = launch_head(hl, s);
+    if (rc) return fail(h, rc, tls_error());
+  }
+  return PG_OK;
+}
+
 int pg_forward_logprobs(pg_handle h, const int32_t* tokens, int32_t n_tokens, int32_t win_start, int32_t T, int32_t mask_pos,
                         float* out_logprobs, pg_stream stream) {
   if (!h) return set_error(PG_ERR_ARG, "pg_forward_logprobs: null handle");
   if (!h->loaded) return fail(h, PG_ERR_STATE, "pg_forward_logprobs: weights not loaded");
   if (h->desc.arch == PG_ARCH_TRANCEPTION) return fail(h, PG_ERR_STATE, "pg_forward_logprobs: handle is a Tranception model (use pg_ar_loglik)");
+  if (h->desc.arch == PG_ARCH_MSA) return fail(h, PG_ERR_STATE, "pg_forward_logprobs: handle is an MSA Transformer (use pg_msa_masked_marginals)");
   if (!tokens || !out_logprobs || T <= 0 || win_start < 0 || win_start + T > n_tokens) return fail(h, PG_ERR_ARG, "pg_forward_logprobs: bad arguments");
   if (h->desc.arch == PG_ARCH_ESM1B && T > h->desc.max_positions) return fail(h, PG_ERR_ARG, "pg_forward_logprobs: sequence longer than the learned position table");
   if (h->desc.arch == PG_ARCH_ESM2 && T > h->rot_rows) return fail(h, PG_ERR_ARG, "pg_forward_logprobs: sequence longer than rotary tables");

@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(AttnLaunch a) {
 
 int launch_attention(const AttnLaunch& a, cudaStream_t s) {
   if (a.B <= 0 || a.T <= 0) return PG_OK;
+  if (a.perm_C) return set_error(PG_ERR_UNSUPPORTED, "attention: the column-attention row order is only in the tcgen05 kernel (attention_tc4.cu)");
   if (a.ld % 8 || a.lo_off % 8 || a.ldo % 2 || a.out_lo_off % 2) return set_error(PG_ERR_ARG, "attention: misaligned pitches");
   if (a.nseg != 1 && a.nseg != 3) return set_error(PG_ERR_ARG, "attention: nseg must be 1 or 3");
   if (a.heads > 65535 || a.B > 65535) return set_error(PG_ERR_ARG, "attention: grid too large");

@@ -423,6 +423,7 @@ __global__ void __launch_bounds__(384, 1) attn_tc3_kernel(const __grid_constant_
 
 int launch_attention_tc3(const AttnLaunch& a, cudaStream_t s) {
   if (a.B <= 0 || a.T <= 0) return PG_OK;
+  if (a.perm_C) return set_error(PG_ERR_UNSUPPORTED, "attention: the column-attention row order is only in the tcgen05 kernel (attention_tc4.cu)");
   if (a.nseg != 1 && a.nseg != 3) return set_error(PG_ERR_ARG, "attention: nseg must be 1 or 3");
   if (a.ld % 8 || a.lo_off % 8 || a.ldo % 8 || a.out_lo_off % 8 || (reinterpret_cast<uintptr_t>(a.out) & 15))
     return set_error(PG_ERR_ARG, "attention_tc3: pitches must be multiples of 8 elements and out 16-byte aligned");

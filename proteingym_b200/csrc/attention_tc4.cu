@@ -56,6 +56,7 @@ struct Attn4Params {
   int causal;
   const float* alibi_slopes;
   int out_fmt; float out_scale;  // common.h operand formats: 1 = fp16 lo plane, 2 = e4m3 [lo8 | hi8] planes for the out_proj GEMM
+  int perm_C;                    // > 0: sequence b is column (b / perm_C, b % perm_C) of an alignment; output rows go to (., r, c) order
 };
 
 __device__ __forceinline__ float ex2a3(float x) {
@@ -375,7 +376,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
       tc_fence_after();
       const bool wr = live && qidx < p.T;
       const float rl = 1.f / l;
-      const long long orow_idx = static_cast<long long>(b) * p.Tq + (qidx - p.s_tiles * QT);
+      long long orow_idx = static_cast<long long>(b) * p.Tq + (qidx - p.s_tiles * QT);
+      if (p.perm_C > 0) orow_idx = (static_cast<long long>(b / p.perm_C) * p.Tq + qidx) * p.perm_C + b % p.perm_C;
       __half* orow = p.out + orow_idx * p.ldo + h * 64;
       uint8_t* f8 = reinterpret_cast<uint8_t*>(p.out + orow_idx * p.ldo + p.out_lo_off) + h * 64;
       const float sh = p.out_scale, sl = p.out_scale * 2048.f;
@@ -460,6 +462,8 @@ int launch_attention_tc4(const AttnLaunch& a, cudaStream_t s) {
   p.causal = a.causal; p.alibi_slopes = a.alibi_slopes;
   p.out_fmt = a.out_fmt < 0 ? (a.out_lo_off > 0 ? 1 : 0) : a.out_fmt;
   p.out_scale = a.out_scale;
+  p.perm_C = a.perm_C;
+  if (a.perm_C < 0 || (a.perm_C > 0 && (a.prefix || a.B % a.perm_C))) return set_error(PG_ERR_ARG, "attention_tc4: bad column-attention arguments");
   if (p.out_fmt > 2 || (p.out_fmt >= 1 && a.out_lo_off <= 0) || (p.out_fmt == 2 && !(a.out_scale > 0.f)))
     return set_error(PG_ERR_ARG, "attention_tc4: bad output format");
   const int np = a.nseg == 3 ? 2 : 1;

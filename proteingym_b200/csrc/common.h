@@ -52,6 +52,9 @@ struct GemmLaunch {
   int w_uniform = 0;              // nseg 2: all w_inv[n] are equal (one scale per matrix, as pg_load_weights / pg_pack_weight produce)
   int out_fmt = 0;                // epi != 2: 0, 1 or 2 (see above); planes at out_lo_off
   float out_scale = 0.f;          // out_fmt 2: s of the GEMM that will consume `out`
+  // Grouped (block-diagonal) form, nseg 1 / 3 only: rows [g*grp_rows_a, (g+1)*grp_rows_a) of A (M = groups * grp_rows_a, a multiple of
+  // 256 per group) are multiplied with rows [g*grp_rows_b, g*grp_rows_b + N) of w; outputs keep A's row index. 0 = plain GEMM.
+  int grp_rows_a = 0, grp_rows_b = 0;
 };
 int launch_gemm(const GemmLaunch& g, cudaStream_t s);
 void set_gemm_kchunk(int v);    // tuning: see gemm_tc.cu
@@ -60,7 +63,7 @@ void set_gemm_cta2(int v);      // 1: CTA-pair (cta_group::2) GEMM kernel
 
 // fmt / scale as above (fmt 0 when lo_off == 0).
 int launch_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int rows, int d, __half* out,
-                         int64_t ldo, int64_t lo_off, cudaStream_t s, int fmt = -1, float scale = 0.f);
+                         int64_t ldo, int64_t lo_off, cudaStream_t s, int fmt = -1, float scale = 0.f, int perm_R = 0, int perm_C = 0);
 
 struct AttnLaunch {
   const __half* qkv; int64_t ld; int64_t lo_off;
@@ -74,6 +77,9 @@ struct AttnLaunch {
   // whose first prefix_len rows (a multiple of 128) are shared; their K and V live in `prefix` (one sequence, same pitch / planes).
   const __half* prefix = nullptr;
   int prefix_len = 0;
+  // Column attention of an alignment (tcgen05 kernel only): the B sequences are the columns (b, c) of [R = T, C = perm_C] alignments;
+  // output row (sequence (b, c), position r) is written to row (b, r, c) of `out`.
+  int perm_C = 0;
 };
 int launch_attention(const AttnLaunch& a, cudaStream_t s);
 
@@ -140,4 +146,27 @@ struct ArFusion {
 };
 int launch_ar_head(const float* x, int d, int B, int T, int vocab, const int32_t* ids, const int32_t* lens, const float* lnf_g,
                    const float* lnf_b, const float* wte, const ArFusion& fusion, float* tok_logp, float* out_sum, cudaStream_t s);
+}  // namespace pg
+
+namespace pg {
+// MSA Transformer (msa_transformer.cu): embedding of B masked copies of an [R, Cfull] alignment window, and the regroupings /
+// softmax of the tied row attention.
+struct MsaEmbedLaunch {
+  const int32_t* tokens; int R, Cfull;   // [R, Cfull] alignment tokens (BOS column included)
+  const int32_t* positions;              // [P] masked column of row 0
+  const int32_t* win_start;              // [P] first column of the window, or null (0)
+  int p_offset, B, Cw, d;                // this chunk: positions [p_offset, p_offset + B), windows of Cw columns
+  const float* embed; const float* pos_table; const float* row_pos;  // [vocab, d], [max_pos + 2, d], [1024, d] or null
+  const float* gamma; const float* beta; // emb_layer_norm_before
+  int mask_idx;
+  float* x;                              // [B * R * Cw, d]
+};
+int launch_msa_embed(const MsaEmbedLaunch& e, cudaStream_t s);
+int launch_tied_gather_qk(const __half* qkv, int64_t ldq, int64_t lo_off, int B, int R, int C, int H, int Cp, __half* tq, __half* tk,
+                          int64_t ldt, cudaStream_t s);
+int launch_tied_transpose_v(const __half* qkv, int64_t ldq, int64_t lo_off, int B, int R, int C, int H, int Kp, __half* tv, int64_t ldv,
+                            cudaStream_t s);
+int launch_tied_softmax(const float* S, int64_t lds, int G, int C, int Cp, int Kp, float scale, __half* P, int64_t ldp, int np, cudaStream_t s);
+int launch_tied_scatter_out(const __half* ot, int64_t ldo_t, __half* out, int64_t ldo, int fmt, int B, int R, int C, int H, int Cp,
+                            cudaStream_t s);
 }  // namespace pg

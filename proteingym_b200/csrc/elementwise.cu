@@ -40,7 +40,7 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 template <int MAXV>  // float4 vectors per lane; d <= MAXV*128
 __global__ void layernorm_f16_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, int rows, int d, __half* __restrict__ out,
-                                     long long ldo, long long lo_off, int fmt, float scale) {
+                                     long long ldo, long long lo_off, int fmt, float scale, int perm_R, int perm_C) {
   const int warps_per_block = blockDim.x >> 5;
   const long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -68,7 +68,14 @@ __global__ void layernorm_f16_kernel(const float* __restrict__ x, long long ldx,
     }
   }
   const float rstd = rsqrtf(warp_sum(ss) / d + 1e-5f);
-  __half* orow = out + row * ldo;
+  // perm_C > 0: input rows are (b, r, c) with c fastest; the output row is (b, c, r) — the column-attention layout of an alignment
+  long long orow_idx = row;
+  if (perm_C > 0) {
+    const long long rc = static_cast<long long>(perm_R) * perm_C;
+    const long long b = row / rc, rem = row % rc;
+    orow_idx = (b * perm_C + rem % perm_C) * perm_R + rem / perm_C;
+  }
+  __half* orow = out + orow_idx * ldo;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + i * 32;
@@ -361,17 +368,18 @@ int launch_gather_rows(const float* x, const int32_t* row_sel, int B, int T, int
 }
 
 int launch_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int rows, int d, __half* out,
-                         int64_t ldo, int64_t lo_off, cudaStream_t s, int fmt, float scale) {
+                         int64_t ldo, int64_t lo_off, cudaStream_t s, int fmt, float scale, int perm_R, int perm_C) {
   if (rows <= 0) return PG_OK;
+  if (perm_C > 0 && (perm_R <= 0 || rows % (perm_R * perm_C))) return set_error(PG_ERR_ARG, "layernorm: rows must be whole [R, C] alignments");
   if (d % 4 || ldx % 4 || ldo % 4 || lo_off % 4) return set_error(PG_ERR_ARG, "layernorm: d and pitches must be multiples of 4");
   if (fmt < 0) fmt = lo_off > 0 ? 1 : 0;
   if (fmt > 2 || (fmt >= 1 && lo_off <= 0) || (fmt == 2 && !(scale > 0.f))) return set_error(PG_ERR_ARG, "layernorm: bad output format");
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
-  if (d <= 128 * 4) layernorm_f16_kernel<4><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale);
-  else if (d <= 128 * 10) layernorm_f16_kernel<10><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale);
-  else if (d <= 128 * 20) layernorm_f16_kernel<20><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale);
-  else if (d <= 128 * 40) layernorm_f16_kernel<40><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale);
+  if (d <= 128 * 4) layernorm_f16_kernel<4><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale, perm_R, perm_C);
+  else if (d <= 128 * 10) layernorm_f16_kernel<10><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale, perm_R, perm_C);
+  else if (d <= 128 * 20) layernorm_f16_kernel<20><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale, perm_R, perm_C);
+  else if (d <= 128 * 40) layernorm_f16_kernel<40><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale, perm_R, perm_C);
   else return set_error(PG_ERR_UNSUPPORTED, "layernorm: d > 5120");
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;

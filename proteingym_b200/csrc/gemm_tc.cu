@@ -83,6 +83,7 @@ struct GemmKParams {
   const float* rot_cos; const float* rot_sin; int rot_T; int rot_dim;
   int tiles_m, tiles_n;
   int prefetch;           // k-blocks of L2 look-ahead for the A operand (0 = off)
+  int grp_rows_a, grp_rows_b;  // grouped (block-diagonal) mode: A rows [g*grp_rows_a, (g+1)*grp_rows_a) pair with W rows g*grp_rows_b + n
 };
 
 // Exact-erf GELU (esm/modules.py:17-24): 0.5*x*(1+erf(x/sqrt2)) = 0.5*x + 0.5*|x|*erf(|x|/sqrt2).
@@ -341,7 +342,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = tile0; tile < ntiles; tile += tstep) {
         const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
         const int a_row = m_blk * row_base + static_cast<int>(rank) * BM;          // this CTA's 128 rows of A
-        const int b_row = n_blk * BN + (CTA2 ? static_cast<int>(rank) * 128 : 0);   // pair mode: this CTA's half of the W tile
+        int b_row = n_blk * BN + (CTA2 ? static_cast<int>(rank) * 128 : 0);         // pair mode: this CTA's half of the W tile
+        if (p.grp_rows_a) b_row += (m_blk * row_base / p.grp_rows_a) * p.grp_rows_b;  // grouped: this group's block of W rows
         for (int s = 0; s < p.nsegs; ++s) {
           const GemmSeg sg = p.seg[s];
           const CUtensorMap* ma = sg.kind ? &tmA8 : &tmA;
@@ -624,7 +626,11 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   CUtensorMap tmA, tmB, tmA8{}, tmB8{};
   int rc = make_tmap_2d(&tmA, g.a, g.M, width, g.lda, BM, BK, 2, 128);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmB, g.w, g.N, width, g.ldw, wbox, BK, 2, 128);
+  const bool grouped = g.grp_rows_a > 0;
+  if (grouped && (g.nseg == 2 || g.grp_rows_a % (2 * BM) || g.grp_rows_b < g.N || g.M % g.grp_rows_a || g.bias || g.epi == 3))
+    return set_error(PG_ERR_ARG, "gemm: grouped mode needs fp16 operands, A groups of a multiple of 256 rows, W groups of >= N rows, no bias");
+  const uint64_t w_rows = grouped ? static_cast<uint64_t>(g.M / g.grp_rows_a) * g.grp_rows_b : static_cast<uint64_t>(g.N);
+  rc = make_tmap_2d(&tmB, g.w, w_rows, width, g.ldw, wbox, BK, 2, 128);
   if (rc) return rc;
   if (g.nseg == 2) {  // e4m3 planes follow the fp16 hi plane of each row: bytes [2K, 4K) = K-concatenated [lo8 | hi8] / [hi8 | lo8]
     rc = make_tmap_2d(&tmA8, static_cast<const uint8_t*>(g.a) + 2 * K, g.M, 2 * K, static_cast<uint64_t>(g.lda) * 2, BM, 2 * BK, 1, 128);
@@ -684,7 +690,8 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   p.rot_cos = g.rot_cos; p.rot_sin = g.rot_sin; p.rot_T = g.rot_T; p.rot_dim = g.rot_dim;
   p.tiles_m = cta2 ? (g.M + 2 * BM - 1) / (2 * BM) : (g.M + BM - 1) / BM;
   p.tiles_n = (g.N + BN - 1) / BN;
-  p.prefetch = gemm_prefetch();
+  p.prefetch = grouped ? 0 : gemm_prefetch();
+  p.grp_rows_a = g.grp_rows_a; p.grp_rows_b = g.grp_rows_b;
   const int ntiles = p.tiles_m * p.tiles_n;
   if (!cta2) {
     const int grid = ntiles < num_sms() ? ntiles : num_sms();

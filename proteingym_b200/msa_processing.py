@@ -46,7 +46,7 @@ def _lower(a: np.ndarray) -> np.ndarray:
 class MSAProcessing:
     def __init__(self, MSA_location="", theta=0.2, use_weights=True, weights_location=None, preprocess_MSA=True,
                  threshold_sequence_frac_gaps=0.5, threshold_focus_cols_frac_gaps=0.3,
-                 remove_sequences_with_indeterminate_AA_in_focus_cols=True, device=0):
+                 remove_sequences_with_indeterminate_AA_in_focus_cols=True, device=0, on_missing_weights="exit"):
         self.MSA_location = MSA_location
         self.weights_location = weights_location
         self.theta = theta
@@ -57,6 +57,9 @@ class MSAProcessing:
         self.threshold_focus_cols_frac_gaps = threshold_focus_cols_frac_gaps
         self.remove_sequences_with_indeterminate_AA_in_focus_cols = remove_sequences_with_indeterminate_AA_in_focus_cols
         self.device = device
+        # a weights path that does not exist: "exit" = the Tranception / TranceptEVE copies stop (msa_utils.py:363-365); "compute" = the
+        # copy the ESM scripts use computes the weights and saves them there (proteingym/utils/msa_utils.py:218-241)
+        self.on_missing_weights = on_missing_weights
         self.gen_alignment()
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -129,7 +132,7 @@ class MSAProcessing:
         self.seq_name_to_sequence = {n: list(fmat[i].tobytes().decode("latin-1")) for i, n in enumerate(names)}
 
         if self.use_weights:
-            if (self.weights_location is not None) and (not os.path.isfile(self.weights_location)):
+            if (self.weights_location is not None) and (not os.path.isfile(self.weights_location)) and self.on_missing_weights == "exit":
                 print("Provided weights location is invalid")
                 sys.exit(0)                                        # the reference's behaviour (msa_utils.py:363-365)
             from . import sharding

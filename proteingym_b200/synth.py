@@ -354,3 +354,107 @@ def write_a2m(path: str, msa: dict, width: int = 60):
             fh.write(n + "\n")
             for k in range(0, len(s), width):
                 fh.write(s[k:k + width] + "\n")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# MSA Transformer (reference: proteingym/baselines/esm/esm/model/msa_transformer.py, esm/axial_attention.py, esm/modules.py:145-235)
+@dataclass
+class MsaArch:
+    layers: int
+    embed_dim: int
+    heads: int
+    ffn_dim: int
+    embed_positions_msa: bool = True
+    msa_pos_dim: int = 0       # last dimension of msa_position_embedding: 0 = embed_dim (MSA-1b), 1 = the first release's broadcast form
+    max_positions: int = 1024
+    vocab: int = 33
+
+
+MSA_1B = MsaArch(12, 768, 12, 3072)
+
+
+def make_msa_state(arch: MsaArch, seed: int = 0, qk_gain: float = 2.0, device=None) -> dict:
+    """State dict with the key names of the reference ``MSATransformer`` module (msa_transformer.py:100-148; AxialTransformerLayer
+    = three NormalizedResidualBlocks, modules.py:194-203,374-388). Same distributions as ``make_esm_state``."""
+    g = torch.Generator(device=device if device is not None else "cpu").manual_seed(seed)
+    d, f, V = arch.embed_dim, arch.ffn_dim, arch.vocab
+    rn = lambda *shape: torch.randn(shape, generator=g, device=g.device)
+    st = {}
+    emb = 0.1 * rn(V, d)
+    emb[1].zero_()
+    st["embed_tokens.weight"] = emb
+    if arch.embed_positions_msa:
+        st["msa_position_embedding"] = 0.1 * rn(1, 1024, 1, arch.msa_pos_dim or d)
+    pos = 0.1 * rn(arch.max_positions + 2, d)
+    pos[1].zero_()
+    st["embed_positions.weight"] = pos
+    st["emb_layer_norm_before.weight"] = 1 + 0.1 * rn(d)
+    st["emb_layer_norm_before.bias"] = 0.05 * rn(d)
+    xb = math.sqrt(3.0 / (2 * d))
+    for i in range(arch.layers):
+        for blk in ("row_self_attention", "column_self_attention"):
+            p = f"layers.{i}.{blk}."
+            for nm, gain in (("k", qk_gain), ("v", 1.0), ("q", qk_gain)):
+                st[p + f"layer.{nm}_proj.weight"] = _uniform(g, (d, d), xb) * gain
+                st[p + f"layer.{nm}_proj.bias"] = _uniform(g, (d,), 1 / math.sqrt(d)) * gain
+            st[p + "layer.out_proj.weight"] = _uniform(g, (d, d), math.sqrt(6.0 / (2 * d)))
+            st[p + "layer.out_proj.bias"] = _uniform(g, (d,), 1 / math.sqrt(d))
+            st[p + "layer_norm.weight"] = 1 + 0.1 * rn(d)
+            st[p + "layer_norm.bias"] = 0.05 * rn(d)
+        p = f"layers.{i}.feed_forward_layer."
+        st[p + "layer.fc1.weight"] = _uniform(g, (f, d), 1 / math.sqrt(d))
+        st[p + "layer.fc1.bias"] = _uniform(g, (f,), 1 / math.sqrt(d))
+        st[p + "layer.fc2.weight"] = _uniform(g, (d, f), 1 / math.sqrt(f))
+        st[p + "layer.fc2.bias"] = _uniform(g, (d,), 1 / math.sqrt(f))
+        st[p + "layer_norm.weight"] = 1 + 0.1 * rn(d)
+        st[p + "layer_norm.bias"] = 0.05 * rn(d)
+    st["emb_layer_norm_after.weight"] = 1 + 0.1 * rn(d)
+    st["emb_layer_norm_after.bias"] = 0.05 * rn(d)
+    st["lm_head.dense.weight"] = _uniform(g, (d, d), 1 / math.sqrt(d))
+    st["lm_head.dense.bias"] = _uniform(g, (d,), 1 / math.sqrt(d))
+    st["lm_head.layer_norm.weight"] = 1 + 0.1 * rn(d)
+    st["lm_head.layer_norm.bias"] = 0.05 * rn(d)
+    st["lm_head.bias"] = 0.1 * rn(V)
+    st["lm_head.weight"] = st["embed_tokens.weight"]
+    return st
+
+
+def msa_file_key(model_key: str) -> str:
+    """Model key -> key in a released msa_transformer checkpoint file: the loader swaps "row" and "column" in every name
+    (pretrained.py:113,115) and strips the ``encoder.`` / ``encoder.sentence_encoder.`` prefixes (:109-112)."""
+    k = model_key.replace("row", "\0").replace("column", "row").replace("\0", "column")
+    return ("encoder.lm_head." + k[len("lm_head."):]) if k.startswith("lm_head.") else "encoder.sentence_encoder." + k
+
+
+def write_msa_checkpoint(path: str, arch: MsaArch, seed: int = 0, state: dict | None = None) -> dict:
+    """fair-esm v1 file (``{"args": Namespace(arch="msa_transformer", ...), "model": state}``) that the reference loader accepts."""
+    st = state if state is not None else make_msa_state(arch, seed)
+    assert not os.path.basename(path).startswith("esm2")
+    args = argparse.Namespace(arch="msa_transformer", layers=arch.layers, embed_dim=arch.embed_dim, ffn_embed_dim=arch.ffn_dim,
+                              attention_heads=arch.heads, max_positions=arch.max_positions, dropout=0.1, attention_dropout=0.1,
+                              activation_dropout=0.1, max_tokens=2 ** 14, max_tokens_per_msa=2 ** 14, embed_positions_msa=arch.embed_positions_msa,
+                              final_bias=True)
+    torch.save({"args": args, "model": {msa_file_key(k): v for k, v in st.items()}}, path)
+    return st
+
+
+def random_alignment(target_seq: str, n_rows: int, seed: int, sub_rate=(0.05, 0.6), gap_rate: float = 0.08, insert_cols=()):
+    """[(name, aligned row)] for the MSA Transformer path: the target first (name ``>target/1-L``), rows of the same length made of
+    upper-case residues and '-' (and '.' in ``insert_cols`` of the non-target rows, which the reference keeps as tokens after
+    upper-casing, compute_fitness.py:69-70)."""
+    rng = np.random.RandomState(seed)
+    rows = [(">target/1-%d" % len(target_seq), target_seq)]
+    ins = set(insert_cols)
+    for i in range(n_rows - 1):
+        r = rng.uniform(*sub_rate)
+        s = list(target_seq)
+        for j in range(len(s)):
+            u = rng.rand()
+            if j in ins:
+                s[j] = "."
+            elif u < gap_rate:
+                s[j] = "-"
+            elif u < gap_rate + r:
+                s[j] = AA20[rng.randint(0, 20)]
+        rows.append((">seq%d/1-%d" % (i, len(target_seq)), "".join(s)))
+    return rows
