@@ -80,7 +80,7 @@ SIGNATURES = {
 }
 
 PROFILE_CATEGORIES = ["embed", "layernorm", "gemm_qkv", "attention", "gemm_out", "gemm_fc1", "gemm_fc2", "head", "score",
-                      "other"]
+                      "other", "tied_gemm", "regroup"]
 
 _lib = None
 

@@ -409,8 +409,11 @@ int forward_tranception(pg_handle h, const int32_t* ids, int B, int T, cudaStrea
 // residual block. The tied attention's two products run as grouped GEMMs on regrouped operands (msa_transformer.cu), always with fp16
 // hi/lo pairs when the handle has them (x3: they are < 10 % of the FLOPs); the column attention is the tcgen05 attention kernel over
 // the B*Cw columns as sequences of R rows, fed by a LayerNorm that writes its rows in (b, c, r) order.
+// `sel` (device, [Bc]): the window column of each alignment whose (row 0) output the caller reads. The last layer then runs exactly
+// what that output depends on — the full q/k/v projection of its row attention, one row of each tied attention map, and the rest on
+// the Bc*R rows of column sel[b] (column attention) and on Bc rows (FFN); the result is left in h->xc [Bc, d].
 int forward_msa(pg_handle h, const int32_t* tokens, int R, int Cfull, const int32_t* positions, const int32_t* win_start, int p_offset,
-                int Bc, int Cw, cudaStream_t s) {
+                int Bc, int Cw, cudaStream_t s, const int32_t* sel) {
   const pg_model_desc& D = h->desc;
   const int d = D.embed_dim, f = D.ffn_dim, np = h->np, H = D.heads;
   const int afmt = h->nseg == 2 ? 2 : (np == 2 ? 1 : 0);
@@ -418,7 +421,7 @@ int forward_msa(pg_handle h, const int32_t* tokens, int R, int Cfull, const int3
   const int64_t ldd = static_cast<int64_t>(d) * np, ldf = static_cast<int64_t>(f) * np, ldq = static_cast<int64_t>(3 * d) * np;
   const int rows = Bc * R * Cw;
   // tied-attention workspace: Q' / K' [G*Cp, Nt*np] (Q' doubles as the context buffer), V' [G*Nt, Kp*np], S fp32 [G*Cp, Kp], P [G*Cp, Kp*np]
-  const int G = Bc * H, Cp = (Cw + 255) / 256 * 256, Kp = (Cw + 63) / 64 * 64, Nt = R * 64;
+  const int G = Bc * H, Cp = (Cw + 127) / 128 * 128, Kp = (Cw + 63) / 64 * 64, Nt = R * 64;
   const int64_t ldt = static_cast<int64_t>(Nt) * np, ldv = static_cast<int64_t>(Kp) * np, lds = Kp, ldp = static_cast<int64_t>(Kp) * np;
   auto al = [](size_t b) { return (b + 255) / 256 * 256; };
   const size_t b_q = al(static_cast<size_t>(G) * Cp * ldt * 2), b_v = al(static_cast<size_t>(G) * Nt * ldv * 2);
@@ -459,7 +462,55 @@ int forward_msa(pg_handle h, const int32_t* tokens, int R, int Cfull, const int3
     q.out = h->qkv; q.out_fmt = qfmt;
     rc = run_lin(h, CAT_GEMM_QKV, q, s);
     if (rc) return rc;
-    { ProfScope ps(CAT_OTHER, s, 2);
+    if (l == D.layers - 1) {
+      // ---- pruned last layer (exact)
+      const int BR = Bc * R;
+      uint8_t* fb = reinterpret_cast<uint8_t*>(h->fbuf);  // the MLP hidden buffer is idle here: compact residual / operand / q-k-v rows
+      float* xr = reinterpret_cast<float*>(fb);
+      __half* cab = reinterpret_cast<__half*>(fb + al(static_cast<size_t>(BR) * d * 4));
+      __half* cqkv = reinterpret_cast<__half*>(fb + al(static_cast<size_t>(BR) * d * 4) + al(static_cast<size_t>(BR) * ldd * 2));
+      { ProfScope ps(CAT_TIED, s, 3);
+        rc = launch_tied_col_attention(h->qkv, ldq, np == 2 ? 3 * d : 0, sel, Bc, R, Cw, H, row_scale, S, cab, ldd, np == 2 ? d : 0, afmt,
+                                       S_ATT, s); }
+      if (rc) return rc;
+      { ProfScope ps(CAT_REGROUP, s);
+        rc = launch_msa_gather_col(h->x, sel, Bc, R, Cw, d, xr, s); }
+      if (rc) return rc;
+      Lin o{cab, ldd, S_ATT, L.wo, L.io, L.bo, BR, d, d, 2};
+      o.resid = xr;
+      rc = run_lin(h, CAT_GEMM_OUT, o, s);
+      if (rc) return rc;
+      { ProfScope ps(CAT_LN, s);
+        rc = launch_layernorm_f16(xr, d, CL.ln1g, CL.ln1b, BR, d, cab, ldd, np == 2 ? d : 0, s, afmt, S_LN); }
+      if (rc) return rc;
+      Lin q2{cab, ldd, S_LN, CL.wqkv, CL.iqkv, CL.bqkv, BR, 3 * d, d, 0};
+      q2.out = cqkv; q2.out_fmt = qfmt;
+      rc = run_lin(h, CAT_GEMM_QKV, q2, s);
+      if (rc) return rc;
+      AttnLaunch a{};
+      a.qkv = cqkv; a.ld = ldq; a.lo_off = np == 2 ? 3 * d : 0;
+      a.out = cab; a.ldo = ldd; a.out_lo_off = np == 2 ? d : 0; a.out_fmt = afmt; a.out_scale = S_ATT;
+      a.B = Bc; a.T = R; a.heads = H; a.nseg = np == 2 ? 3 : 1; a.causal = 0; a.alibi_slopes = nullptr;
+      { ProfScope ps(CAT_ATTN, s); rc = launch_attention_tc(a, s); }
+      if (rc) return rc;
+      Lin o2{cab, ldd, S_ATT, CL.wo, CL.io, CL.bo, BR, d, d, 2};
+      o2.resid = xr;
+      rc = run_lin(h, CAT_GEMM_OUT, o2, s);
+      if (rc) return rc;
+      rc = launch_gather_rows(xr, h->row_sel + h->head_cap, Bc, R, d, h->xc, s);  // row 0 of every alignment
+      if (rc) return rc;
+      { ProfScope ps(CAT_LN, s);
+        rc = launch_layernorm_f16(h->xc, d, L.ln2g, L.ln2b, Bc, d, h->cabuf, ldd, np == 2 ? d : 0, s, afmt, S_LN); }
+      if (rc) return rc;
+      Lin f1{h->cabuf, ldd, S_LN, L.w1, L.i1, L.b1, Bc, f, d, 1};
+      f1.out = h->cfbuf; f1.out_fmt = afmt; f1.out_scale = S_GELU;
+      rc = run_lin(h, CAT_GEMM_FC1, f1, s);
+      if (rc) return rc;
+      Lin f2{h->cfbuf, ldf, S_GELU, L.w2, L.i2, L.b2, Bc, d, f, 2};
+      f2.resid = h->xc;
+      return run_lin(h, CAT_GEMM_FC2, f2, s);
+    }
+    { ProfScope ps(CAT_REGROUP, s, 2);
       rc = launch_tied_gather_qk(h->qkv, ldq, np == 2 ? 3 * d : 0, Bc, R, Cw, H, Cp, tq, tk, ldt, s);
       if (!rc) rc = launch_tied_transpose_v(h->qkv, ldq, np == 2 ? 3 * d : 0, Bc, R, Cw, H, Kp, tv, ldv, s); }
     if (rc) return rc;
@@ -467,20 +518,20 @@ int forward_msa(pg_handle h, const int32_t* tokens, int R, int Cfull, const int3
     { GemmLaunch g{};
       g.a = tq; g.lda = ldt; g.w = tk; g.ldw = ldt; g.M = G * Cp; g.N = Cw; g.K = Nt; g.nseg = np == 2 ? 3 : 1; g.epi = 2;
       g.resid = S; g.ldr = lds; g.grp_rows_a = Cp; g.grp_rows_b = Cp;
-      ProfScope ps(CAT_ATTN, s);
+      ProfScope ps(CAT_TIED, s);
       rc = launch_gemm(g, s); }
     if (rc) return rc;
-    { ProfScope ps(CAT_OTHER, s);
+    { ProfScope ps(CAT_REGROUP, s);
       rc = launch_tied_softmax(S, lds, G, Cw, Cp, Kp, row_scale, P, ldp, np, s); }
     if (rc) return rc;
     { GemmLaunch g{};
       g.a = P; g.lda = ldp; g.w = tv; g.ldw = ldv; g.M = G * Cp; g.N = Nt; g.K = Kp; g.nseg = np == 2 ? 3 : 1; g.epi = 0;
       g.out = tq; g.ldo = ldt; g.out_fmt = afmt; g.out_lo_off = afmt ? Nt : 0; g.out_scale = S_ATT;
       g.grp_rows_a = Cp; g.grp_rows_b = Nt;
-      ProfScope ps(CAT_ATTN, s);
+      ProfScope ps(CAT_TIED, s);
       rc = launch_gemm(g, s); }
     if (rc) return rc;
-    { ProfScope ps(CAT_OTHER, s, afmt == 2 ? 3 : (afmt == 1 ? 2 : 1));
+    { ProfScope ps(CAT_REGROUP, s);
       rc = launch_tied_scatter_out(tq, ldt, h->abuf, ldd, afmt, Bc, R, Cw, H, Cp, s); }
     if (rc) return rc;
     Lin o{h->abuf, ldd, S_ATT, L.wo, L.io, L.bo, rows, d, d, 2};
@@ -635,7 +686,7 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
   A(&h->fbuf, static_cast<size_t>(h->max_rows) * f * np);
   A(&h->hs_a, static_cast<size_t>(h->head_cap) * d);
   A(&h->hs_b, static_cast<size_t>(h->head_cap) * d);
-  A(&h->row_sel, h->head_cap);
+  A(&h->row_sel, 2 * static_cast<size_t>(h->head_cap));  // second half: zeros (row 0 of every compacted sequence)
   A(&h->xc, static_cast<size_t>(h->head_cap) * d);
   A(&h->cabuf, static_cast<size_t>(h->head_cap) * d * np);
   A(&h->cfbuf, static_cast<size_t>(h->head_cap) * f * np);
@@ -644,6 +695,7 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
     pg_destroy(h);
     return set_error(rc, m);
   }
+  cudaMemset(h->row_sel, 0, 2 * static_cast<size_t>(h->head_cap) * sizeof(int32_t));
   *out = h;
   return PG_OK;
 }
@@ -862,10 +914,8 @@ int pg_msa_masked_marginals(pg_handle h, const int32_t* tokens, int32_t R, int32
   if (per > h->head_cap) per = h->head_cap;
   for (int p0 = 0; p0 < P; p0 += static_cast<int>(per)) {
     const int Bc = (P - p0) < per ? (P - p0) : static_cast<int>(per);
-    int rc = forward_msa(h, tokens, R, C_full, positions, win_start, p0, Bc, Cw, s);
-    if (rc) return fail(h, rc, tls_error());
     row_select_kernel<<<(Bc + 255) / 256, 256, 0, s>>>(positions, win_start, nullptr, p0, Bc, h->row_sel);
-    rc = launch_gather_rows(h->x, h->row_sel, Bc, static_cast<int>(per_msa), h->desc.embed_dim, h->xc, s);
+    int rc = forward_msa(h, tokens, R, C_full, positions, win_start, p0, Bc, Cw, s, h->row_sel);
     if (rc) return fail(h, rc, tls_error());
     ProfScope ps(CAT_HEAD, s, 5);
     HeadLaunch hl = head_args(h, 1);

@@ -25,7 +25,7 @@ int set_error(int code, const std::string& msg);
 int num_sms();
 
 // Launch accounting + optional per-category CUDA-event timing (bench.py's roofline leg). Categories:
-enum ProfCat { CAT_EMBED = 0, CAT_LN, CAT_GEMM_QKV, CAT_ATTN, CAT_GEMM_OUT, CAT_GEMM_FC1, CAT_GEMM_FC2, CAT_HEAD, CAT_SCORE, CAT_OTHER, CAT_COUNT };
+enum ProfCat { CAT_EMBED = 0, CAT_LN, CAT_GEMM_QKV, CAT_ATTN, CAT_GEMM_OUT, CAT_GEMM_FC1, CAT_GEMM_FC2, CAT_HEAD, CAT_SCORE, CAT_OTHER, CAT_TIED, CAT_REGROUP, CAT_COUNT };
 struct ProfScope {  // records an event pair around the launches issued in its lifetime when profiling is on
   ProfScope(int cat, cudaStream_t s, int launches = 1);
   ~ProfScope();
@@ -53,7 +53,7 @@ struct GemmLaunch {
   int out_fmt = 0;                // epi != 2: 0, 1 or 2 (see above); planes at out_lo_off
   float out_scale = 0.f;          // out_fmt 2: s of the GEMM that will consume `out`
   // Grouped (block-diagonal) form, nseg 1 / 3 only: rows [g*grp_rows_a, (g+1)*grp_rows_a) of A (M = groups * grp_rows_a, a multiple of
-  // 256 per group) are multiplied with rows [g*grp_rows_b, g*grp_rows_b + N) of w; outputs keep A's row index. 0 = plain GEMM.
+  // 128 per group; 256 lets the CTA-pair kernel run) are multiplied with rows [g*grp_rows_b, g*grp_rows_b + N) of w; outputs keep A's row index. 0 = plain GEMM.
   int grp_rows_a = 0, grp_rows_b = 0;
 };
 int launch_gemm(const GemmLaunch& g, cudaStream_t s);
@@ -169,4 +169,9 @@ int launch_tied_transpose_v(const __half* qkv, int64_t ldq, int64_t lo_off, int 
 int launch_tied_softmax(const float* S, int64_t lds, int G, int C, int Cp, int Kp, float scale, __half* P, int64_t ldp, int np, cudaStream_t s);
 int launch_tied_scatter_out(const __half* ot, int64_t ldo_t, __half* out, int64_t ldo, int fmt, int B, int R, int C, int H, int Cp,
                             cudaStream_t s);
+// Last layer: tied row attention for the single query column sel[b] of every alignment -> context rows (b, r) in operand format
+// (S1: [B, H, C] fp32 scratch); and the residual rows of that column.
+int launch_tied_col_attention(const __half* qkv, int64_t ldq, int64_t lo_off, const int32_t* sel, int B, int R, int C, int H, float scale,
+                              float* S1, __half* out, int64_t ldo, int64_t out_lo_off, int out_fmt, float out_scale, cudaStream_t s);
+int launch_msa_gather_col(const float* x, const int32_t* sel, int B, int R, int C, int d, float* xr, cudaStream_t s);
 }  // namespace pg

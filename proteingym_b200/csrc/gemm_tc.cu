@@ -621,14 +621,15 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   }
   const uint64_t K = static_cast<uint64_t>(g.K);
   const uint64_t width = K * (g.nseg == 3 ? 2 : 1);
-  const int cta2 = gemm_cta2();
+  const bool grouped = g.grp_rows_a > 0;
+  // CTA pairs work on 256-row tiles; a grouped problem whose groups are only a multiple of 128 rows runs the single-CTA form
+  const int cta2 = gemm_cta2() && !(grouped && g.grp_rows_a % (2 * BM));
   const uint32_t wbox = cta2 ? 128 : BN;  // rows of W one CTA stages per k-block (pair mode: its half of the 256-row tile)
   CUtensorMap tmA, tmB, tmA8{}, tmB8{};
   int rc = make_tmap_2d(&tmA, g.a, g.M, width, g.lda, BM, BK, 2, 128);
   if (rc) return rc;
-  const bool grouped = g.grp_rows_a > 0;
-  if (grouped && (g.nseg == 2 || g.grp_rows_a % (2 * BM) || g.grp_rows_b < g.N || g.M % g.grp_rows_a || g.bias || g.epi == 3))
-    return set_error(PG_ERR_ARG, "gemm: grouped mode needs fp16 operands, A groups of a multiple of 256 rows, W groups of >= N rows, no bias");
+  if (grouped && (g.nseg == 2 || g.grp_rows_a % BM || g.grp_rows_b < g.N || g.M % g.grp_rows_a || g.bias || g.epi == 3))
+    return set_error(PG_ERR_ARG, "gemm: grouped mode needs fp16 operands, A groups of a multiple of 128 rows, W groups of >= N rows, no bias");
   const uint64_t w_rows = grouped ? static_cast<uint64_t>(g.M / g.grp_rows_a) * g.grp_rows_b : static_cast<uint64_t>(g.N);
   rc = make_tmap_2d(&tmB, g.w, w_rows, width, g.ldw, wbox, BK, 2, 128);
   if (rc) return rc;

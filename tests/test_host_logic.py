@@ -99,7 +99,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pg_abi_version() == 3
+    assert lib.pg_abi_version() == 4
 
 
 def test_product_path_never_imports_the_oracle():
@@ -147,7 +147,9 @@ def test_cli_resolve_assay_errors_match_reference(tmp_path):
     synth.write_mapping_csv(str(tmp_path / "map.csv"), [("A1", "a1.csv", "mkv"), ("A1", "a1b.csv", "MKV"), ("B2", "b2.csv", "MKVL")])
     import pandas as pd
     pd.DataFrame({"mutant": []}).to_csv(tmp_path / "b2.csv", index=False)
-    base = ["--dms_mapping", str(tmp_path / "map.csv"), "--dms-input", str(tmp_path), "--dms-output", str(tmp_path / "out")]
+    base = ["--dms_mapping", str(tmp_path / "map.csv"), "--dms-input", str(tmp_path), "--dms-output", str(tmp_path / "out"), "--model_type", "ESM1v"]
+    with pytest.raises(KeyError, match="MSA_filename"):  # the parser's default model type is the MSA Transformer, which needs the MSA columns (:311)
+        resolve_assay(create_parser().parse_args(base[:-2] + ["--dms_index", "2"]))
     with pytest.raises(ValueError, match="Multiple mappings found"):
         resolve_assay(create_parser().parse_args(base + ["--dms_index", "0"]))
     with pytest.raises(ValueError, match="No rows found"):

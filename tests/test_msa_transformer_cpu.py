@@ -107,3 +107,16 @@ def test_window_arithmetic_matches_reference_slices():
     for i in (0, 1, 511, 512, 513, 588, 589, 590, 1000, 1100):
         s, e = MO.optimal_window(i, C + 1, 1024)
         assert starts[i] == s and min(starts[i] + 1024, C) == min(e, C)
+
+
+def test_oracle_true_size_msa1b_rows_match_reference():
+    """12 x 768 (MSA-1b) on 48 x 130 tokens: two rows of the reference's table (a forward is ~6 s of CPU)."""
+    if not have("msa1b"):
+        pytest.skip("true-size fixture not generated")
+    c = load_case("msa1b")
+    arch, meta = c["arch"], c["meta"]
+    st = synth.make_msa_state(arch, meta["seed"], qk_gain=c["qk_gain"])
+    toks = MO.tokenize_alignment(c["rows"])
+    pos = meta["table_positions"][5:7]
+    tab = MO.masked_marginal_table(st, toks, arch.layers, arch.heads, positions=pos).numpy()
+    assert np.abs(tab - c["table"][5:7]).max() < 1e-4
