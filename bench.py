@@ -366,30 +366,35 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
     torch.cuda.empty_cache()
 
     # ---- MSA Transformer: masked positions of one alignment, the launcher's 400 sampled rows ----
-    log("MSA Transformer")
-    from proteingym_b200 import msa_engine
-    march = synth.MSA_1B
-    mcfg = checkpoint.config_from_msa_synth(march)
-    mstate = checkpoint.normalise_msa_synth_state(march, synth.make_msa_state(march, 0, device=dev))
-    R, Lm, npos = 400, 512, 8
-    toks = msa_engine.tokenize_alignment(synth.random_alignment(synth.random_protein(Lm, seed=100 + rank), R, seed=200 + rank))
-    msc = msa_engine.MsaScorer(mcfg, mstate, precision=a.precision, device=local_rank,
-                               max_rows=msa_engine.default_max_rows(mcfg, R, Lm + 1, 1 if a.precision == "f16" else 2, want=4))
-    del mstate
-    pos = np.linspace(1, Lm, npos).astype(np.int32)
-    msc.masked_marginal_rows(toks, pos[:4])  # warm-up
-    _, per_rank, tw = timed(lambda: msc.masked_marginal_rows(toks, pos))
-    msc.close()
-    d_, f_, C_ = march.embed_dim, march.ffn_dim, Lm + 1
-    flop = march.layers * (2.0 * R * C_ * (8 * d_ * d_ + 2 * d_ * f_) + 4.0 * C_ * C_ * R * d_ + 4.0 * R * R * C_ * d_)
-    secs = max(per_rank) / 1e3
-    out.append({"config": "MSA Transformer (MSA-1b: 12 x 768, 12 heads, ffn 3072; tied row attention + column attention) masked-marginals of one "
-                          f"synthetic alignment per rank: {R} sampled rows x {Lm} residues (+BOS), {npos} masked positions, 4 per pass",
-                "sample": f"{npos} of the {Lm + 1} columns per rank; one alignment forward per masked position (compute_fitness.py:383-399)",
-                "precision_mode": a.precision, "n_gpus": world, "value": world * npos / secs, "unit": "masked positions/s",
-                "mutants_per_s_all_singles": 19 * world * npos / secs, "seconds": secs, "per_rank_ms": per_rank,
-                "algorithmic_tflop_per_position": flop / 1e12, "algorithmic_tflops": world * npos * flop / 1e12 / secs,
-                "frac_of_peak": npos * flop / 1e12 / secs / sustained, "clocks": sampler.window(*tw) if sampler else None})
+    try:
+        log("MSA Transformer")
+        from proteingym_b200 import msa_engine
+        march = synth.MSA_1B
+        mcfg = checkpoint.config_from_msa_synth(march)
+        mstate = checkpoint.normalise_msa_synth_state(march, synth.make_msa_state(march, 0, device=dev))
+        R, Lm, npos = 400, 512, 8
+        toks = msa_engine.tokenize_alignment(synth.random_alignment(synth.random_protein(Lm, seed=100 + rank), R, seed=200 + rank))
+        msc = msa_engine.MsaScorer(mcfg, mstate, precision=a.precision, device=local_rank,
+                                   max_rows=msa_engine.default_max_rows(mcfg, R, Lm + 1, 1 if a.precision == "f16" else 2, want=4))
+        del mstate
+        pos = np.linspace(1, Lm, npos).astype(np.int32)
+        msc.masked_marginal_rows(toks, pos[:4])  # warm-up
+        _, per_rank, tw = timed(lambda: msc.masked_marginal_rows(toks, pos))
+        msc.close()
+        d_, f_, C_ = march.embed_dim, march.ffn_dim, Lm + 1
+        flop = march.layers * (2.0 * R * C_ * (8 * d_ * d_ + 2 * d_ * f_) + 4.0 * C_ * C_ * R * d_ + 4.0 * R * R * C_ * d_)
+        secs = max(per_rank) / 1e3
+        out.append({"config": "MSA Transformer (MSA-1b: 12 x 768, 12 heads, ffn 3072; tied row attention + column attention) masked-marginals of one "
+                              f"synthetic alignment per rank: {R} sampled rows x {Lm} residues (+BOS), {npos} masked positions, 4 per pass",
+                    "sample": f"{npos} of the {Lm + 1} columns per rank; one alignment forward per masked position (compute_fitness.py:383-399)",
+                    "precision_mode": a.precision, "n_gpus": world, "value": world * npos / secs, "unit": "masked positions/s",
+                    "mutants_per_s_all_singles": 19 * world * npos / secs, "seconds": secs, "per_rank_ms": per_rank,
+                    "algorithmic_tflop_per_position": flop / 1e12, "algorithmic_tflops": world * npos * flop / 1e12 / secs,
+                    "frac_of_peak": npos * flop / 1e12 / secs / sustained, "clocks": sampler.window(*tw) if sampler else None})
+    except Exception as e:  # noqa: BLE001  (keep the entries of configs 3-5)
+        if dist is not None:
+            raise
+        out.append({"config": "MSA Transformer", "error": f"{type(e).__name__}: {e}"})
     torch.cuda.empty_cache()
     return out
 

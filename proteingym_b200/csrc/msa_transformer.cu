@@ -197,18 +197,20 @@ __global__ void tied_col_scores_kernel(const __half* __restrict__ qkv, long long
                                        int R, int C, int H, float scale, float* __restrict__ S1) {
   const int j = blockIdx.x, b = blockIdx.y;
   const int h = threadIdx.x >> 4, l = threadIdx.x & 15;
+  const bool live = h < H;  // the block is padded to whole warps (the shuffles below need them)
+  const int hh = live ? h : 0;
   const int d = H * 64;
-  const __half* q = qkv + (static_cast<long long>(b) * R * C + sel[b]) * ldq + h * 64 + l * 4;
-  const __half* k = qkv + (static_cast<long long>(b) * R * C + j) * ldq + d + h * 64 + l * 4;
+  const __half* q = qkv + (static_cast<long long>(b) * R * C + sel[b]) * ldq + hh * 64 + l * 4;
+  const __half* k = qkv + (static_cast<long long>(b) * R * C + j) * ldq + d + hh * 64 + l * 4;
   const long long step = static_cast<long long>(C) * ldq;
   float acc = 0.f;
-  for (int r = 0; r < R; ++r) {
+  for (int r = 0; r < (live ? R : 0); ++r) {
     const float4 a = load4_hilo(q + r * step, lo_off), c = load4_hilo(k + r * step, lo_off);
     acc = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, acc))));
   }
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, 16);
-  if (l == 0) S1[(static_cast<long long>(b) * H + h) * C + j] = acc * scale;
+  if (live && l == 0) S1[(static_cast<long long>(b) * H + h) * C + j] = acc * scale;
 }
 // one warp per (b, h): in-place softmax over the C keys
 __global__ void tied_col_softmax_kernel(float* __restrict__ S1, int G, int C) {
@@ -231,6 +233,7 @@ __global__ void tied_col_context_kernel(const __half* __restrict__ qkv, long lon
                                         float out_scale) {
   const int r = blockIdx.x, b = blockIdx.y;
   const int h = threadIdx.x >> 4, l = threadIdx.x & 15;
+  if (h >= H) return;
   const int d = H * 64;
   const __half* v = qkv + (static_cast<long long>(b) * R + r) * C * ldq + 2 * d + h * 64 + l * 4;
   const float* p = P1 + (static_cast<long long>(b) * H + h) * C;
@@ -328,9 +331,9 @@ int launch_tied_scatter_out(const __half* ot, int64_t ldo_t, __half* out, int64_
 int launch_tied_col_attention(const __half* qkv, int64_t ldq, int64_t lo_off, const int32_t* sel, int B, int R, int C, int H, float scale,
                               float* S1, __half* out, int64_t ldo, int64_t out_lo_off, int out_fmt, float out_scale, cudaStream_t s) {
   if (H * 16 > 1024 || B > 65535 || R > 2147483647 / 2) return set_error(PG_ERR_UNSUPPORTED, "tied attention: more than 64 heads or 65535 alignments per pass");
-  tied_col_scores_kernel<<<dim3(C, B), H * 16, 0, s>>>(qkv, ldq, lo_off, sel, R, C, H, scale, S1);
+  tied_col_scores_kernel<<<dim3(C, B), (H * 16 + 31) / 32 * 32, 0, s>>>(qkv, ldq, lo_off, sel, R, C, H, scale, S1);
   tied_col_softmax_kernel<<<(B * H + 7) / 8, 256, 0, s>>>(S1, B * H, C);
-  tied_col_context_kernel<<<dim3(R, B), H * 16, 0, s>>>(qkv, ldq, lo_off, S1, R, C, H, out, ldo, out_lo_off, out_fmt, out_scale);
+  tied_col_context_kernel<<<dim3(R, B), (H * 16 + 31) / 32 * 32, 0, s>>>(qkv, ldq, lo_off, S1, R, C, H, out, ldo, out_lo_off, out_fmt, out_scale);
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;
 }
