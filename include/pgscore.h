@@ -192,6 +192,10 @@ typedef struct {
   const float* rot_cos; const float* rot_sin; int32_t rot_T; int32_t rot_dim;
   float a_scale; const float* w_inv; /* nseg 2 */
   int32_t out_fmt; float out_scale;
+  /* grouped (block-diagonal) form, nseg 1 / 3, no bias: rows [g*grp_rows_a, (g+1)*grp_rows_a) of a (M = groups * grp_rows_a, a multiple
+   * of 128 per group) meet rows [g*grp_rows_b, g*grp_rows_b + N) of w; outputs keep a's row index. The tied row attention of the MSA
+   * Transformer runs its two products this way (esm/axial_attention.py:140,176). 0 = plain GEMM. */
+  int32_t grp_rows_a, grp_rows_b;
 } pg_gemm_args;
 int pg_gemm(const pg_gemm_args* args, pg_stream stream);
 

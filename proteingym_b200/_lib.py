@@ -27,7 +27,8 @@ class PgGemmArgs(C.Structure):
                 ("out_h", C.c_void_p), ("ldo", C.c_int64), ("out_lo_off", C.c_int64),
                 ("resid", C.c_void_p), ("ldr", C.c_int64),
                 ("rot_cos", C.c_void_p), ("rot_sin", C.c_void_p), ("rot_T", C.c_int32), ("rot_dim", C.c_int32),
-                ("a_scale", C.c_float), ("w_inv", C.c_void_p), ("out_fmt", C.c_int32), ("out_scale", C.c_float)]
+                ("a_scale", C.c_float), ("w_inv", C.c_void_p), ("out_fmt", C.c_int32), ("out_scale", C.c_float),
+                ("grp_rows_a", C.c_int32), ("grp_rows_b", C.c_int32)]
 
 
 class PgAttnArgs(C.Structure):

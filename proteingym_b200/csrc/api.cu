@@ -1101,6 +1101,7 @@ int pg_gemm(const pg_gemm_args* a, pg_stream stream) {
   g.rot_cos = a->rot_cos; g.rot_sin = a->rot_sin; g.rot_T = a->rot_T; g.rot_dim = a->rot_dim;
   g.a_scale = a->a_scale; g.w_inv = a->w_inv; g.out_scale = a->out_scale;
   g.out_fmt = a->out_fmt ? a->out_fmt : (a->out_lo_off > 0 ? 1 : 0);
+  g.grp_rows_a = a->grp_rows_a; g.grp_rows_b = a->grp_rows_b;
   ProfScope ps(CAT_OTHER, static_cast<cudaStream_t>(stream));
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }

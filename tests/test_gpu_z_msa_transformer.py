@@ -153,3 +153,49 @@ def test_cli_matches_reference_csv(tmp_path):
     # second run: every seed column exists -> skipped, file unchanged (compute_fitness.py:365-372)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "Skipping seed" in r.stdout
+
+
+@pytest.mark.parametrize("G,rows_a,N,rows_b,K,nseg,epi", [(3, 128, 100, 100, 128, 3, 2), (4, 256, 300, 384, 192, 3, 0), (2, 384, 513, 640, 1024, 1, 2),
+                                                          (5, 128, 64, 64, 64, 3, 0), (2, 640, 513, 640, 2560, 3, 2), (3, 256, 3200, 3200, 192, 3, 0)])
+@pytest.mark.parametrize("cta2", [0, 1])
+def test_grouped_gemm_matches_fp64(G, rows_a, N, rows_b, K, nseg, epi, cta2):
+    """The block-diagonal form of the tcgen05 GEMM the tied row attention uses (scores: epi 2 into fp32; context: epi 0 into fp16
+    hi/lo planes): group g multiplies rows [g*rows_a, (g+1)*rows_a) of a with rows [g*rows_b, g*rows_b + N) of w."""
+    import ctypes as C
+    lib = _lib.load()
+    lib.pg_set_tuning(b"gemm_cta2", cta2)
+    g = torch.Generator(device="cuda").manual_seed(G + rows_a + N + K)
+    A = torch.randn(G * rows_a, K, device="cuda", generator=g)
+    W = torch.randn(G * rows_b, K, device="cuda", generator=g) / K ** 0.5
+
+    def hilo(t):
+        hi = t.to(torch.float16)
+        return torch.cat([hi, (t - hi.float()).to(torch.float16)], dim=1).contiguous()
+    a16, w16 = (hilo(A), hilo(W)) if nseg == 3 else (A.half().contiguous(), W.half().contiguous())
+    Ad = a16[:, :K].double() + (a16[:, K:].double() if nseg == 3 else 0)
+    Wd = w16[:, :K].double() + (w16[:, K:].double() if nseg == 3 else 0)
+    ref = torch.stack([Ad[i * rows_a:(i + 1) * rows_a] @ Wd[i * rows_b:i * rows_b + N].T for i in range(G)]).reshape(G * rows_a, N)
+    if nseg == 3:  # the kernel drops lo*lo
+        ref = ref - torch.stack([a16[i * rows_a:(i + 1) * rows_a, K:].double() @ w16[i * rows_b:i * rows_b + N, K:].double().T
+                                 for i in range(G)]).reshape(G * rows_a, N)
+    args = _lib.PgGemmArgs()
+    args.a, args.lda, args.w, args.ldw = a16.data_ptr(), a16.shape[1], w16.data_ptr(), w16.shape[1]
+    args.M, args.N, args.K, args.nseg, args.epi = G * rows_a, N, K, nseg, epi
+    args.grp_rows_a, args.grp_rows_b = rows_a, rows_b
+    npl = 2 if nseg == 3 else 1
+    ldr = (N + 3) // 4 * 4
+    if epi == 2:
+        resid = torch.zeros(G * rows_a, ldr, device="cuda")
+        args.resid, args.ldr = resid.data_ptr(), ldr
+    else:
+        out = torch.zeros(G * rows_a, N * npl, device="cuda", dtype=torch.float16)
+        args.out_h, args.ldo, args.out_lo_off = out.data_ptr(), N * npl, (N if nseg == 3 else 0)
+    try:
+        _lib.check(lib.pg_gemm(C.byref(args), None))
+        torch.cuda.synchronize()
+    finally:
+        lib.pg_set_tuning(b"gemm_cta2", 1)
+    got = resid[:, :N].double() if epi == 2 else out[:, :N].double() + (out[:, N:].double() if nseg == 3 else 0)
+    err, amax = (got - ref).abs().max().item(), ref.abs().max().item()
+    bound = 4e-7 * (K * nseg) ** 0.5 * max(4.0, amax) if (epi == 2 or nseg == 3) else 2.5e-3 * max(1.0, amax / 4)
+    assert err < bound, (err, bound)
