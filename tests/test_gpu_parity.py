@@ -65,7 +65,7 @@ def spearman(a, b):
 # ------------------------------------------------------------------------------------------------ kernel level
 @pytest.mark.parametrize("M,N,K,nseg,epi", [(128, 256, 64, 1, 0), (1, 8, 64, 1, 0), (257, 520, 192, 1, 1), (129, 100, 64, 1, 2),
                                             (500, 384, 128, 1, 3), (300, 320, 128, 3, 0), (300, 320, 128, 3, 1),
-                                            (1000, 1280, 1280, 3, 2), (300, 384, 128, 3, 3), (4096, 3840, 1280, 1, 0)])
+                                            (1000, 1280, 1280, 3, 2), (300, 384, 128, 3, 3), (4096, 3840, 1280, 1, 0), (300, 320, 128, 3, 4)])
 @pytest.mark.parametrize("cta2", [0, 1])
 def test_gemm_matches_fp64(M, N, K, nseg, epi, cta2):
     lib = _lib.load()
@@ -92,6 +92,8 @@ def test_gemm_matches_fp64(M, N, K, nseg, epi, cta2):
         args.out_h, args.ldo, args.out_lo_off = out.data_ptr(), N * npl, (N if nseg == 3 else 0)
         if epi == 1:
             ref = ref * 0.5 * (1 + torch.erf(ref / 2 ** 0.5))
+        if epi == 4:
+            ref = torch.relu(ref) ** 2  # tranception/activations.py:79-84
     if epi == 3:
         T = 37
         cos, sin = torch.rand(T, 32, device="cuda", generator=g), torch.rand(T, 32, device="cuda", generator=g)
