@@ -154,6 +154,18 @@ def main_msa_transformer(args, df, mutant_col):
     if args.scoring_strategy == "pseudo-ppl":
         raise NotImplementedError("pseudo-ppl with the MSA Transformer (compute_fitness.py:406-418) is not part of the B200 path")
     seeds = [args.seeds] if isinstance(args.seeds, int) else list(args.seeds)
+    # under torchrun (WORLD_SIZE > 1) the masked positions of every seed are split over the ranks (one NCCL all-gather per seed)
+    from proteingym_b200 import sharding
+    rank, world = sharding.rank_world()
+    shard = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        args.device = int(os.environ.get("LOCAL_RANK", args.device))
+        torch.cuda.set_device(args.device)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", args.device))
+        shard = (rank, world)
     offset_idx = args.MSA_start
     name = None
     for model_location in args.model_location:
@@ -184,7 +196,11 @@ def main_msa_transformer(args, df, mutant_col):
                     scorer.close()
                 scorer = msa_engine.MsaScorer(config, state, precision=precision, device=args.device, max_rows=need)
                 print("Scoring with {} and model {} (operand precision {})".format(args.scoring_strategy, name, precision))
-            df[col] = scorer.score_assay(rows, args.sequence, list(df[mutant_col]), offset_idx).astype(np.float64)
+            df[col] = scorer.score_assay(rows, args.sequence, list(df[mutant_col]), offset_idx, shard=shard).astype(np.float64)
+            if shard is not None:
+                if rank != 0:
+                    sharding.barrier_if_distributed()  # rank 0 finishes writing the CSV before anyone looks at it again
+                    continue  # every rank holds the scores; rank 0 writes
             if os.path.exists(args.dms_output) and not args.overwrite_prior_scores:  # :419-423
                 prior = pd.read_csv(args.dms_output)
                 assert col not in prior.columns, f"Column {col} already exists in {args.dms_output}"
@@ -193,8 +209,12 @@ def main_msa_transformer(args, df, mutant_col):
                 df = prior
             else:
                 df.to_csv(args.dms_output, index=False)
+            if shard is not None:
+                sharding.barrier_if_distributed()
         if scorer is not None:
             scorer.close()
+    if shard is not None and rank != 0:
+        return
     df[f"{name}_ensemble"] = 0.0
     for seed in seeds:
         df[f"{name}_ensemble"] += df[f"{name}_seed{seed}"]
@@ -205,8 +225,7 @@ def main_msa_transformer(args, df, mutant_col):
 def main(args):
     from proteingym_b200.checkpoint import load_esm_checkpoint
     from proteingym_b200.esm_engine import EsmScorer, choose_precision
-    if not os.path.exists(args.dms_output):
-        os.mkdir(args.dms_output)
+    os.makedirs(args.dms_output, exist_ok=True)  # the reference's exists + mkdir (:283), safe when several ranks start together
     print("Arguments:", args)
     if args.nogpu:
         raise RuntimeError("--nogpu: this scorer is the B200 path and has no CPU fallback (use the reference script)")

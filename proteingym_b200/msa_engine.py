@@ -141,10 +141,20 @@ class MsaScorer:
             pass
 
     # ------------------------------------------------------------------------------------------------------------
-    def masked_marginal_rows(self, tokens: np.ndarray, positions) -> torch.Tensor:
+    def masked_marginal_rows(self, tokens: np.ndarray, positions, shard=None) -> torch.Tensor:
         """The reference loop body (:383-399) for the given columns of row 0: tokens int32 [R, C] (BOS column included) ->
         float32 [len(positions), vocab] on the device, row p = log_softmax(logits[0, 0, positions[p]]) with (0, positions[p]) masked.
-        Alignments wider than 1024 columns use the reference's per-position window (``get_optimal_window`` with L + 2, :389)."""
+        Alignments wider than 1024 columns use the reference's per-position window (``get_optimal_window`` with L + 2, :389).
+        ``shard = (rank, world)`` with an initialised torch.distributed group: the masked positions are independent forwards, so this
+        rank runs a contiguous chunk of them and one all-gather completes the table on every rank."""
+        if shard is not None and shard[1] > 1:
+            from . import sharding
+            positions = np.asarray(positions, dtype=np.int32)
+            lo, hi, chunk = sharding.position_chunk(len(positions), shard[1], shard[0])
+            full = torch.zeros((shard[1] * chunk, self.config.vocab), dtype=torch.float32, device=self.device)
+            if hi > lo:
+                full[lo:hi] = self.masked_marginal_rows(tokens, positions[lo:hi])
+            return sharding.all_gather_rows(full, chunk)[:len(positions)]
         tokens = np.ascontiguousarray(tokens, dtype=np.int32)
         R, Cf = tokens.shape
         if (tokens == ALPHABET.padding_idx).any():
@@ -174,7 +184,7 @@ class MsaScorer:
         self._keep = (dev_tok,)
         return out
 
-    def score_assay(self, rows, sequence: str, mutants, offset_idx: int = 1) -> np.ndarray:
+    def score_assay(self, rows, sequence: str, mutants, offset_idx: int = 1, shard=None) -> np.ndarray:
         """One (checkpoint, seed) column (:377-405): ``rows`` = the sampled alignment [(name, aligned string)], ``sequence`` = the part
         of the target the alignment covers, ``offset_idx`` = MSA_start. Only the columns some mutant reads are forwarded (exact)."""
         tokens = tokenize_alignment(rows)
@@ -185,7 +195,7 @@ class MsaScorer:
         if len(site_row) and (site_row.min() < 0 or site_row.max() >= tokens.shape[1]):
             raise IndexError("mutation position outside the alignment")
         positions = np.unique(site_row).astype(np.int32)
-        table = self.masked_marginal_rows(tokens, positions)
+        table = self.masked_marginal_rows(tokens, positions, shard=shard)
         row_of = np.full(tokens.shape[1], -1, dtype=np.int32)
         row_of[positions] = np.arange(len(positions), dtype=np.int32)
         M = len(offs) - 1

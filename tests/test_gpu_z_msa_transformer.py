@@ -199,3 +199,15 @@ def test_grouped_gemm_matches_fp64(G, rows_a, N, rows_b, K, nseg, epi, cta2):
     err, amax = (got - ref).abs().max().item(), ref.abs().max().item()
     bound = 4e-7 * (K * nseg) ** 0.5 * max(4.0, amax) if (epi == 2 or nseg == 3) else 2.5e-3 * max(1.0, amax / 4)
     assert err < bound, (err, bound)
+
+
+def test_two_gpu_position_partition_is_bit_identical():
+    """MsaScorer.score_assay(shard=(rank, world)) over NCCL on 2 GPUs: every rank ends with the single-GPU scores, bit for bit.
+    Needs 2 devices (skipped on the 1-GPU box; runs under `gpurun --gpus 2`)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29673", os.path.join(ROOT, "scripts", "check_msa_partition.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "bit_identical=True" in r.stdout
