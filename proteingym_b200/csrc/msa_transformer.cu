@@ -116,7 +116,7 @@ __global__ void tied_transpose_v_kernel(const __half* __restrict__ qkv, long lon
   __syncthreads();
   {
     const int dd = t & 63, j0 = (t >> 6) * 16;  // consecutive lanes read consecutive head-dim columns of the tile: no bank conflicts
-    __half out[16];
+    __align__(16) __half out[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) out[k] = tile[j0 + k][dd];
     __half* dst = tv + (((static_cast<long long>(b) * H + h) * R + r) * 64 + dd) * ldv + static_cast<long long>(pl) * Kp + jt * 64 + j0;
