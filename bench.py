@@ -391,11 +391,11 @@ def other_workloads(a, rank, world, local_rank, dist, sustained, sampler):
                     "mutants_per_s_all_singles": 19 * world * npos / secs, "seconds": secs, "per_rank_ms": per_rank,
                     "algorithmic_tflop_per_position": flop / 1e12, "algorithmic_tflops": world * npos * flop / 1e12 / secs,
                     "frac_of_peak": npos * flop / 1e12 / secs / sustained, "clocks": sampler.window(*tw) if sampler else None})
-    except Exception as e:  # noqa: BLE001  (keep the entries of configs 3-5)
-        if dist is not None:
-            raise
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001  (keep the entries of configs 3-5; the shapes are the same on every rank, so is a failure)
+        import traceback
+        traceback.print_exc(file=sys.stderr)
         out.append({"config": "MSA Transformer", "error": f"{type(e).__name__}: {e}"})
-    torch.cuda.empty_cache()
     return out
 
 
