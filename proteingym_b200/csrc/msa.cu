@@ -82,28 +82,30 @@ __global__ void __launch_bounds__(256) msa_cluster_kernel(const uint8_t* __restr
 // tokens_t [L, N] uint8 (token id < vocab, anything >= vocab = not in vocabulary), weights [N] fp64.
 // out[j, k] = (sum_i w_i [tok_ij == k] + base * W) / (sum_i w_i [tok_ij in vocab] + vocab * base * W),  W = sum_i w_i.
 template <int V>
-__global__ void __launch_bounds__(256) msa_prior_kernel(const uint8_t* __restrict__ tok_t, const double* __restrict__ w, int N,
+__global__ void __launch_bounds__(128) msa_prior_kernel(const uint8_t* __restrict__ tok_t, const double* __restrict__ w, int N,
                                                         double base, double* __restrict__ out) {
-  __shared__ double red[256];
-  const int j = blockIdx.x;
+  // Each thread keeps its V partial sums in its own column of shared memory and adds w_i to ONE of them per sequence (the first
+  // version ran V predicated fp64 adds per sequence and was fp64-ALU bound at a sixth of the HBM roofline). Order of additions per
+  // thread and the reduction tree are fixed: the result does not depend on scheduling.
+  __shared__ double sb[V][128];
+  __shared__ double red[128];
+  const int j = blockIdx.x, tid = threadIdx.x;
   const uint8_t* col = tok_t + static_cast<long long>(j) * N;
-  double bins[V];
 #pragma unroll
-  for (int k = 0; k < V; ++k) bins[k] = 0.0;
+  for (int k = 0; k < V; ++k) sb[k][tid] = 0.0;
   double wsum = 0.0;
-  for (int i = threadIdx.x; i < N; i += 256) {
+  for (int i = tid; i < N; i += 128) {
     const int t = col[i];
     const double wi = w[i];
     wsum += wi;
-#pragma unroll
-    for (int k = 0; k < V; ++k) bins[k] += (t == k) ? wi : 0.0;
+    if (t < V) sb[t][tid] += wi;
   }
   auto block_reduce = [&](double v) {  // fixed-order tree: deterministic
     __syncthreads();
-    red[threadIdx.x] = v;
+    red[tid] = v;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-      if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    for (int s = 64; s > 0; s >>= 1) {
+      if (tid < s) red[tid] += red[tid + s];
       __syncthreads();
     }
     return red[0];
@@ -113,10 +115,10 @@ __global__ void __launch_bounds__(256) msa_prior_kernel(const uint8_t* __restric
   double norm = 0.0;
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-    tot[k] = block_reduce(bins[k]) + base * W;
+    tot[k] = block_reduce(sb[k][tid]) + base * W;
     norm += tot[k];
   }
-  if (threadIdx.x == 0)
+  if (tid == 0)
     for (int k = 0; k < V; ++k) out[static_cast<long long>(j) * V + k] = tot[k] / norm;
 }
 
@@ -143,7 +145,7 @@ int pg_msa_prior(const uint8_t* tokens_t, const double* weights, int32_t N, int3
   if (vocab != 25) return set_error(PG_ERR_UNSUPPORTED, "pg_msa_prior: vocab must be 25 (Tranception tokenizer)");
   if (L == 0) return PG_OK;
   if (!tokens_t || !weights || !out) return set_error(PG_ERR_ARG, "pg_msa_prior: null buffer");
-  msa_prior_kernel<25><<<L, 256, 0, static_cast<cudaStream_t>(stream)>>>(tokens_t, weights, N, base_rate, out);
+  msa_prior_kernel<25><<<L, 128, 0, static_cast<cudaStream_t>(stream)>>>(tokens_t, weights, N, base_rate, out);
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;
 }
