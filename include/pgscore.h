@@ -216,8 +216,7 @@ typedef struct {
   void* out; int64_t ldo; int64_t out_lo_off;
   int32_t B, T, heads, nseg;
   int32_t causal; const float* alibi_slopes; /* NULL = none */
-  int32_t impl; /* 0 = the model's kernel (tcgen05/TMEM, 2 CTAs per SM, 128x64 blocks), 1 = mma.sync cross-check kernel,
-                   2 = round-1 tcgen05 layout (1 CTA per SM, 128x128 blocks) */
+  int32_t impl; /* 0 = the model's kernel (tcgen05/TMEM, 2 CTAs per SM, 128x64 blocks), 1 = mma.sync cross-check kernel */
   int32_t out_fmt; float out_scale; /* as pg_gemm_args (0 = auto); 2 only with impl 0 */
 } pg_attn_args;
 int pg_attention(const pg_attn_args* args, pg_stream stream);

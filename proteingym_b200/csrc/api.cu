@@ -19,8 +19,7 @@ int set_error(int code, const std::string& msg) {
   return code;
 }
 int launch_attention_tc(const AttnLaunch& a, cudaStream_t s) {
-  static const bool old = getenv("PG_ATTN_TC3") != nullptr;
-  return (old && !a.perm_C) ? launch_attention_tc3(a, s) : launch_attention_tc4(a, s);
+  return launch_attention_tc4(a, s);
 }
 
 int num_sms() {  // of the current device (cached per ordinal: one process may hold handles on several GPUs)
@@ -1145,8 +1144,7 @@ int pg_attention(const pg_attn_args* a, pg_stream stream) {
   l.out_fmt = a->out_fmt ? a->out_fmt : -1; l.out_scale = a->out_scale;
   ProfScope ps(CAT_OTHER, static_cast<cudaStream_t>(stream));
   if (a->impl == 0) return launch_attention_tc(l, static_cast<cudaStream_t>(stream));   // the model's kernel (tcgen05)
-  if (a->impl == 2) return launch_attention_tc3(l, static_cast<cudaStream_t>(stream));  // round-1 tcgen05 layout (A/B reference)
-  if (a->impl != 1) return set_error(PG_ERR_ARG, "pg_attention: impl must be 0 (the model's tcgen05 kernel), 1 (mma.sync cross-check) or 2 (round-1 tcgen05 layout)");
+  if (a->impl != 1) return set_error(PG_ERR_ARG, "pg_attention: impl must be 0 (the model's tcgen05 kernel) or 1 (mma.sync cross-check)");
   if (l.out_fmt == 2) return set_error(PG_ERR_UNSUPPORTED, "pg_attention: the mma.sync cross-check kernel writes fp16 planes only");
   return launch_attention(l, static_cast<cudaStream_t>(stream));
 }

@@ -126,8 +126,7 @@ int make_tmap_f16_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
 int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
                  int elem_bytes, int swizzle);
 int launch_attention_tc4(const AttnLaunch& a, cudaStream_t s);  // tcgen05/TMEM attention, 2 CTAs/SM, 128x64 blocks (attention_tc4.cu): the model's kernel
-int launch_attention_tc3(const AttnLaunch& a, cudaStream_t s);  // round-1 layout: 1 CTA/SM, 128x128 blocks, row split over two threads (attention_tc3.cu)
-int launch_attention_tc(const AttnLaunch& a, cudaStream_t s);   // the model's dispatch: tc4 unless PG_ATTN_TC3=1 (A/B switch)
+int launch_attention_tc(const AttnLaunch& a, cudaStream_t s);   // the model's attention (attention_tc4.cu)
 }  // namespace pg
 
 namespace pg {

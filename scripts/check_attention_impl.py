@@ -1,5 +1,5 @@
 """Run the attention parity cases of tests/test_gpu_parity.py (fp64 reference; causal + ALiBi included) and the throughput probe
-for ONE implementation id of pg_attention (0 the model kernel: tcgen05 2 CTAs per SM; 1 mma.sync; 2 round-1 tcgen05 layout). Used to qualify an experimental
+for ONE implementation id of pg_attention (0 the model kernel: tcgen05 2 CTAs per SM; 1 mma.sync cross-check). Used to qualify an experimental
 kernel without putting it in the test suite: run it under `timeout`. Exit code 0 only if every case passes.
     python scripts/check_attention_impl.py 4"""
 import ctypes as C
@@ -37,7 +37,7 @@ def main():
         np_ = 2 if nseg == 3 else 1
         qkv = (torch.randn(B * T, 3 * d * np_, device="cuda") * 0.5).half()
         out = torch.empty(B * T, d * np_, device="cuda", dtype=torch.float16)
-        for im in (2, impl):
+        for im in (1, impl):
             a = _lib.PgAttnArgs()
             a.qkv, a.ld, a.lo_off = qkv.data_ptr(), 3 * d * np_, (3 * d if nseg == 3 else 0)
             a.out, a.ldo, a.out_lo_off = out.data_ptr(), d * np_, (d if nseg == 3 else 0)

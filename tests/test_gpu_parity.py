@@ -244,7 +244,7 @@ def test_layernorm_matches_fp64(rows, d):
 @pytest.mark.parametrize("B,T,H,nseg,causal", [(2, 64, 2, 1, 0), (3, 100, 2, 1, 0), (2, 514, 4, 1, 0), (1, 1024, 2, 1, 0),
                                                (1, 1, 1, 1, 0), (2, 3, 1, 3, 0), (3, 100, 2, 3, 0), (2, 514, 4, 3, 0),
                                                (2, 130, 2, 1, 1), (2, 130, 2, 3, 1), (2, 514, 4, 1, 1), (1, 1024, 2, 3, 1)])
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1])
 def test_attention_matches_fp64(B, T, H, nseg, causal, impl):
     slopes = None
     lib = _lib.load()
@@ -272,7 +272,7 @@ def test_attention_matches_fp64(B, T, H, nseg, causal, impl):
     torch.cuda.synchronize()
     got = out[:, :d].double() + (out[:, d:].double() if nseg == 3 else 0)
     assert (got - ref).abs().max().item() < ((1e-4 if causal else 3e-5) if nseg == 3 else 3e-3)
-    if impl in (0, 2) and nseg == 3:  # same launch writing the out_proj operand with e4m3 planes (common.h fmt 2)
+    if impl == 0 and nseg == 3:  # same launch writing the out_proj operand with e4m3 planes (common.h fmt 2)
         out8 = torch.zeros(B * T, 4 * d, device="cuda", dtype=torch.uint8)
         a.out, a.out_fmt, a.out_scale = out8.data_ptr(), 2, 4.0
         _lib.check(lib.pg_attention(C.byref(a), None))
