@@ -155,7 +155,7 @@ def test_cli_matches_reference_csv(tmp_path):
     assert r.returncode == 0 and "Skipping seed" in r.stdout
 
 
-@pytest.mark.parametrize("G,rows_a,N,rows_b,K,nseg,epi", [(3, 128, 100, 100, 128, 3, 2), (4, 256, 300, 384, 192, 3, 0), (2, 384, 513, 640, 1024, 1, 2),
+@pytest.mark.parametrize("G,rows_a,N,rows_b,K,nseg,epi", [(3, 128, 100, 100, 128, 3, 2), (4, 256, 304, 384, 192, 3, 0), (2, 384, 513, 640, 1024, 1, 2),
                                                           (5, 128, 64, 64, 64, 3, 0), (2, 640, 513, 640, 2560, 3, 2), (3, 256, 3200, 3200, 192, 3, 0)])
 @pytest.mark.parametrize("cta2", [0, 1])
 def test_grouped_gemm_matches_fp64(G, rows_a, N, rows_b, K, nseg, epi, cta2):
