@@ -1087,6 +1087,8 @@ int pg_set_tuning(const char* key, int32_t value) {
   if (std::string(key) == "gemm_kchunk") { set_gemm_kchunk(value); return PG_OK; }
   if (std::string(key) == "gemm_prefetch") { set_gemm_prefetch(value); return PG_OK; }
   if (std::string(key) == "gemm_cta2") { set_gemm_cta2(value); return PG_OK; }
+  if (std::string(key) == "attn_softmax") { set_attn_softmax(value); return PG_OK; }
+  if (std::string(key) == "gemm_epi") { set_gemm_epi(value); return PG_OK; }
   return set_error(PG_ERR_ARG, std::string("pg_set_tuning: unknown key ") + key);
 }
 

@@ -21,6 +21,7 @@
 //   The softmax warps wait for a finished PV only on the rare blocks that rescale O (pv_done), and in the epilogue (o_full).
 //   MMA issue order per work item:  QK0 QK1 QK2 | PV0 QK3 | PV1 QK4 | ...   TMA load order: K0 K1 K2 | V0 K3 | V1 K4 | ...
 //   Work item = (sequence, head, 128-query tile); persistent CTAs, grid = 2 x SMs.
+#include <atomic>
 #include <cstdlib>
 
 #include "common.h"
@@ -70,7 +71,11 @@ __device__ __forceinline__ uint32_t cvt2h(float lo_elem, float hi_elem) {
   return d;
 }
 
-template <int NP>
+// SV = softmax arithmetic version: 1 = one fp32 instruction per element and step (round 2's first form, kept for the same-box A/B
+// behind pg_set_tuning("attn_softmax", 1)); 2 = packed pairs (FFMA2 / FADD2 / FMUL2), 3-input maxima (FMNMX3) and the log2(e) scale
+// folded into the exponent's FFMA2: ~5 instead of ~9 issue slots per score. The softmax warps were the pace-setter of this kernel
+// (profiles/ncu_r02_summary.txt: 49 % issue-slot use with two softmax warps per scheduler, tensor pipe 52 % active).
+template <int NP, int SV>
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tm,
                                                                   const __grid_constant__ CUtensorMap tmP, const Attn4Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -277,9 +282,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
         if (live) {
           // (1) scores to the log2 domain (+ ALiBi, masks) and the block maximum of this row
           float mblk = -INFINITY;
+          float mulc[2] = {1.f, 1.f};  // SV 2: factor that takes r[] of chunk c to the log2 domain inside step (3)'s FFMA2
           auto to_log2 = [&](uint32_t (&r)[32], const int c) {
             if (c * 32 >= ncols) return;
-            if (plain && valid - c * 32 >= 32) {
+            if (SV == 2 && plain && valid - c * 32 >= 32) {
+              // raw scores stay in r[]: max(s) * log2(e) = max(s * log2(e)) (monotone rounding), the scale itself moves to step (3)
+              float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) m4[k] = fmax3(m4[k], __uint_as_float(r[i + 2 * k]), __uint_as_float(r[i + 2 * k + 1]));
+              }
+              mblk = fmaxf(mblk, fmax3(fmaxf(m4[0], m4[1]), m4[2], m4[3]) * LOG2E);
+              mulc[c] = LOG2E;
+            } else if (plain && valid - c * 32 >= 32) {
               float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
@@ -320,6 +336,23 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
           float lsum = 0.f;
           auto to_p = [&](uint32_t (&r)[32], const int c) {
             if (c * 32 >= ncols) return;
+            if (SV == 2) {
+              const uint64_t mul2 = f2_pack(mulc[c], mulc[c]), neg2 = f2_pack(-mref, -mref);
+              uint64_t l2[4] = {0ull, 0ull, 0ull, 0ull};  // {0.f, 0.f}
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                float d0, d1;
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(r[2 * u]), __uint_as_float(r[2 * u + 1])), mul2, neg2), d0, d1);
+                const float e0 = ex2a3(d0), e1 = ex2a3(d1);
+                r[2 * u] = __float_as_uint(e0);
+                r[2 * u + 1] = __float_as_uint(e1);
+                l2[u & 3] = f2_add(l2[u & 3], f2_pack(e0, e1));
+              }
+              float a0, a1;
+              f2_unpack(f2_add(f2_add(l2[0], l2[1]), f2_add(l2[2], l2[3])), a0, a1);
+              lsum += a0 + a1;
+              return;
+            }
             float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -357,7 +390,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
               hi[u] = cvt2h(x0, x1);
               if (NP == 2) {
                 const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
-                lo[u] = cvt2h(x0 - hf.x, x1 - hf.y);
+                if (SV == 2) {
+                  float q0, q1;
+                  f2_unpack(f2_sub(f2_pack(x0, x1), f2_pack(hf.x, hf.y)), q0, q1);
+                  lo[u] = cvt2h(q0, q1);
+                } else {
+                  lo[u] = cvt2h(x0 - hf.x, x1 - hf.y);
+                }
               }
             }
             tmem_st_32x32b_x16(tmem_s + c * 16, hi);
@@ -398,11 +437,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
           uint4* d4 = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            const float x0 = __uint_as_float(o[2 * u]) * rl, x1 = __uint_as_float(o[2 * u + 1]) * rl;
+            float x0, x1;
+            if (SV == 2) f2_unpack(f2_mul(f2_pack(__uint_as_float(o[2 * u]), __uint_as_float(o[2 * u + 1])), f2_pack(rl, rl)), x0, x1);
+            else { x0 = __uint_as_float(o[2 * u]) * rl; x1 = __uint_as_float(o[2 * u + 1]) * rl; }
             hi[u] = cvt2h(x0, x1);
             const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
-            o[2 * u] = __float_as_uint(x0 - hf.x);      // o[] now holds the fp32 remainders
-            o[2 * u + 1] = __float_as_uint(x1 - hf.y);
+            if (SV == 2) {
+              float q0, q1;
+              f2_unpack(f2_sub(f2_pack(x0, x1), f2_pack(hf.x, hf.y)), q0, q1);
+              o[2 * u] = __float_as_uint(q0);           // o[] now holds the fp32 remainders
+              o[2 * u + 1] = __float_as_uint(q1);
+            } else {
+              o[2 * u] = __float_as_uint(x0 - hf.x);
+              o[2 * u + 1] = __float_as_uint(x1 - hf.y);
+            }
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) d4[u] = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
@@ -443,7 +491,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+std::atomic<int> g_attn_softmax{[] {
+  const char* e = std::getenv("PG_ATTN_SOFTMAX");
+  return e ? std::atoi(e) : 2;
+}()};
+
 }  // namespace
+
+void set_attn_softmax(int v) { g_attn_softmax.store(v, std::memory_order_relaxed); }
 
 int launch_attention_tc4(const AttnLaunch& a, cudaStream_t s) {
   if (a.B <= 0 || a.T <= 0) return PG_OK;
@@ -486,12 +541,20 @@ int launch_attention_tc4(const AttnLaunch& a, cudaStream_t s) {
   PG_CUDA_OK(cudaGetDevice(&dev));
   static bool attr_set[64] = {};
   if (dev < 64 && !attr_set[dev]) {
-    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<1>::TOTAL));
-    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<2>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<1>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<2>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<1>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<2>::TOTAL));
     attr_set[dev] = true;
   }
-  if (np == 1) attn_tc4_kernel<1><<<grid, ATT_THREADS, Smem4<1>::TOTAL, s>>>(tmQ, tm, tmP, p);
-  else attn_tc4_kernel<2><<<grid, ATT_THREADS, Smem4<2>::TOTAL, s>>>(tmQ, tm, tmP, p);
+  const bool v2 = g_attn_softmax.load(std::memory_order_relaxed) != 1;
+  if (np == 1) {
+    if (v2) attn_tc4_kernel<1, 2><<<grid, ATT_THREADS, Smem4<1>::TOTAL, s>>>(tmQ, tm, tmP, p);
+    else attn_tc4_kernel<1, 1><<<grid, ATT_THREADS, Smem4<1>::TOTAL, s>>>(tmQ, tm, tmP, p);
+  } else {
+    if (v2) attn_tc4_kernel<2, 2><<<grid, ATT_THREADS, Smem4<2>::TOTAL, s>>>(tmQ, tm, tmP, p);
+    else attn_tc4_kernel<2, 1><<<grid, ATT_THREADS, Smem4<2>::TOTAL, s>>>(tmQ, tm, tmP, p);
+  }
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;
 }

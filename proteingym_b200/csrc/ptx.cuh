@@ -89,6 +89,41 @@ __device__ __forceinline__ uint32_t cvt_e4m3x2(float e0, float e1) {
 __device__ __forceinline__ uint32_t pack4_e4m3(float e0, float e1, float e2, float e3) {
   return cvt_e4m3x2(e0, e1) | (cvt_e4m3x2(e2, e3) << 16);
 }
+// ---- packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 process two fp32 lanes per issue slot) and the 3-input max (FMNMX3).
+// A pair lives in a 64-bit register {lo = .x, hi = .y}; the pack / unpack moves are register aliasing, not instructions, when the
+// two halves are adjacent (tcgen05.ld results are).
+__device__ __forceinline__ uint64_t f2_pack(float x, float y) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(x), "f"(y));
+  return d;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 // Register re-budgeting between warpgroups (all four warps of a warpgroup execute the same instruction).
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
