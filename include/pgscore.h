@@ -234,6 +234,13 @@ int pg_msa_cluster_neighbors(const uint8_t* tokens, int64_t ld, int32_t N, int32
 int pg_msa_prior(const uint8_t* tokens_t, const double* weights, int32_t N, int32_t L, int32_t vocab, double base_rate, double* out,
                  pg_stream stream);
 
+/* EVE log-prior pre-step of TranceptEVE (trancepteve/model_pytorch.py:969-1001 -> EVE/VAE_decoder.py:118-169). The dense layers of
+ * the encoder / Bayesian decoder run through pg_gemm (fp16 hi/lo operand rows from pg_pack_weight fmt 1, nseg 3, fp32 reduce-add
+ * epilogue); this entry is the one op of the batched sampler that is not a GEMM with shared weights: the decoder's 1x1 output
+ * convolution (VAE_decoder.py:139-147) with one weight draw PER SAMPLE,
+ *   y[s, j*C + c] = sum_a x[s, j*A + a] * conv[s, c*A + a]      x [S, J*A], conv [S, C*A], y [S, J*C], all fp32 on the device. */
+int pg_eve_output_conv(const float* x, const float* conv, int32_t S, int32_t J, int32_t A, int32_t C, float* y, pg_stream stream);
+
 /* Launch accounting and per-category device timing (bench.py's roofline leg).
  * pg_launch_count: kernels launched by this library since load. pg_profile_begin/end: CUDA-event pairs are recorded on
  * the launching stream around every kernel; _end (after the caller synchronised) returns summed ms and scope counts
@@ -250,6 +257,11 @@ int pg_profile_end(float* ms, int32_t* counts, int32_t ncat);
  *   "gemm_prefetch" k-blocks of L2 look-ahead the GEMM's TMA producer issues for the streamed A operand (default 0 = off: measured
  *                  neutral-to-negative in the model; PG_GEMM_PREFETCH). */
 int pg_set_tuning(const char* key, int32_t value);
+/*   "attn_softmax" arithmetic of the attention kernel's softmax warps: 3 (default) packed fp32 pairs (FFMA2 / FADD2 / FMNMX3) with the
+ *                  exponent and the fp16 hi / lo packing of a 32-column chunk in one basic block; 2 packed pairs, steps separate;
+ *                  1 scalar (round 2's first form). PG_ATTN_SOFTMAX.
+ *   "gemm_epi"     2 (default): packed fp32 pairs in the GEMM epilogue (GELU, e4m3 / fp16 lo packing); 1: scalar. Bit-identical
+ *                  results either way. PG_GEMM_EPI. */
 
 /* Build/version probe (also what the CPU-only test suite calls to check the library loads). */
 int pg_abi_version(void);

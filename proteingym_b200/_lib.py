@@ -74,6 +74,7 @@ SIGNATURES = {
     "pg_attention": (C.c_int, [C.POINTER(PgAttnArgs), C.c_void_p]),
     "pg_msa_cluster_neighbors": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pg_msa_prior": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
+    "pg_eve_output_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "pg_set_tuning": (C.c_int, [C.c_char_p, C.c_int32]),
     "pg_launch_count": (C.c_longlong, []),
     "pg_profile_begin": (C.c_int, []),

@@ -585,7 +585,7 @@ using namespace pg;
 
 extern "C" {
 
-int pg_abi_version(void) { return 4; }
+int pg_abi_version(void) { return 5; }
 
 long long pg_launch_count(void) {
   std::lock_guard<std::mutex> lk(prof_mu());

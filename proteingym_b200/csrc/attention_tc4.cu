@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
           float mulc[2] = {1.f, 1.f};  // SV 2: factor that takes r[] of chunk c to the log2 domain inside step (3)'s FFMA2
           auto to_log2 = [&](uint32_t (&r)[32], const int c) {
             if (c * 32 >= ncols) return;
-            if (SV == 2 && plain && valid - c * 32 >= 32) {
+            if (SV >= 2 && plain && valid - c * 32 >= 32) {
               // raw scores stay in r[]: max(s) * log2(e) = max(s * log2(e)) (monotone rounding), the scale itself moves to step (3)
               float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
           float lsum = 0.f;
           auto to_p = [&](uint32_t (&r)[32], const int c) {
             if (c * 32 >= ncols) return;
-            if (SV == 2) {
+            if (SV >= 2) {
               const uint64_t mul2 = f2_pack(mulc[c], mulc[c]), neg2 = f2_pack(-mref, -mref);
               uint64_t l2[4] = {0ull, 0ull, 0ull, 0ull};  // {0.f, 0.f}
 #pragma unroll
@@ -362,8 +362,43 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
             }
             lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
           };
-          to_p(r0, 0);
-          to_p(r1, 1);
+          // SV 3: steps (3) and (5) of a 32-column chunk in ONE basic block — exponent FFMA2, ex2, row sum, fp16 hi / lo pairs and the
+          // tcgen05.st — so that the scheduler can issue the packing of earlier pairs between the MUFU.EX2 instructions (a warp-wide
+          // MUFU holds the SFU for 8 cycles; ncu r02 of SV 2: 47 % of the softmax samples were fixed-latency waits behind a block of
+          // 32 back-to-back MUFUs, with the F2FP / HADD2 / FADD2 work of step (5) queued behind it in a later block).
+          auto exp_store = [&](uint32_t (&r)[32], const int c) {
+            if (c * 32 >= ncols) return;
+            const uint64_t mul2 = f2_pack(mulc[c], mulc[c]), neg2 = f2_pack(-mref, -mref);
+            uint64_t l2[4] = {0ull, 0ull, 0ull, 0ull};
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              float d0, d1;
+              f2_unpack(f2_fma(f2_pack(__uint_as_float(r[2 * u]), __uint_as_float(r[2 * u + 1])), mul2, neg2), d0, d1);
+              const float e0 = ex2a3(d0), e1 = ex2a3(d1);
+              const uint64_t e = f2_pack(e0, e1);
+              l2[u & 3] = f2_add(l2[u & 3], e);
+              hi[u] = cvt2h(e0, e1);
+              if (NP == 2) {
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
+                float q0, q1;
+                f2_unpack(f2_sub(e, f2_pack(hf.x, hf.y)), q0, q1);
+                lo[u] = cvt2h(q0, q1);
+              }
+            }
+            float a0, a1;
+            f2_unpack(f2_add(f2_add(l2[0], l2[1]), f2_add(l2[2], l2[3])), a0, a1);
+            lsum += a0 + a1;
+            tmem_st_32x32b_x16(tmem_s + c * 16, hi);
+            if (NP == 2) tmem_st_32x32b_x16(tmem_s + 32 + c * 16, lo);
+          };
+          if (SV == 3) {
+            exp_store(r0, 0);
+            exp_store(r1, 1);
+          } else {
+            to_p(r0, 0);
+            to_p(r1, 1);
+          }
           l = fmaf(l, scale, lsum);
           // (4) rare: the running maximum moved -> bring the O accumulated so far to the new reference. PV(n-1) (and with it every
           //     earlier PV) must have completed; PV(n) cannot start before this warp arrives on p_full below.
@@ -390,7 +425,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
               hi[u] = cvt2h(x0, x1);
               if (NP == 2) {
                 const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
-                if (SV == 2) {
+                if (SV >= 2) {
                   float q0, q1;
                   f2_unpack(f2_sub(f2_pack(x0, x1), f2_pack(hf.x, hf.y)), q0, q1);
                   lo[u] = cvt2h(q0, q1);
@@ -402,8 +437,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
             tmem_st_32x32b_x16(tmem_s + c * 16, hi);
             if (NP == 2) tmem_st_32x32b_x16(tmem_s + 32 + c * 16, lo);
           };
-          store_p(r0, 0);
-          store_p(r1, 1);
+          if (SV != 3) {
+            store_p(r0, 0);
+            store_p(r1, 1);
+          }
           tmem_st_wait();
         }
         tc_fence_before();
@@ -438,11 +475,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             float x0, x1;
-            if (SV == 2) f2_unpack(f2_mul(f2_pack(__uint_as_float(o[2 * u]), __uint_as_float(o[2 * u + 1])), f2_pack(rl, rl)), x0, x1);
+            if (SV >= 2) f2_unpack(f2_mul(f2_pack(__uint_as_float(o[2 * u]), __uint_as_float(o[2 * u + 1])), f2_pack(rl, rl)), x0, x1);
             else { x0 = __uint_as_float(o[2 * u]) * rl; x1 = __uint_as_float(o[2 * u + 1]) * rl; }
             hi[u] = cvt2h(x0, x1);
             const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
-            if (SV == 2) {
+            if (SV >= 2) {
               float q0, q1;
               f2_unpack(f2_sub(f2_pack(x0, x1), f2_pack(hf.x, hf.y)), q0, q1);
               o[2 * u] = __float_as_uint(q0);           // o[] now holds the fp32 remainders
@@ -493,7 +530,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
 
 std::atomic<int> g_attn_softmax{[] {
   const char* e = std::getenv("PG_ATTN_SOFTMAX");
-  return e ? std::atoi(e) : 2;
+  return e ? std::atoi(e) : 3;
 }()};
 
 }  // namespace
@@ -541,20 +578,19 @@ int launch_attention_tc4(const AttnLaunch& a, cudaStream_t s) {
   PG_CUDA_OK(cudaGetDevice(&dev));
   static bool attr_set[64] = {};
   if (dev < 64 && !attr_set[dev]) {
-    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<1>::TOTAL));
-    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<2>::TOTAL));
-    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<1>::TOTAL));
-    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<2>::TOTAL));
+#define PG_ATT_SMEM(NPV, SVV) PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<NPV, SVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<NPV>::TOTAL))
+    PG_ATT_SMEM(1, 1); PG_ATT_SMEM(2, 1); PG_ATT_SMEM(1, 2); PG_ATT_SMEM(2, 2); PG_ATT_SMEM(1, 3); PG_ATT_SMEM(2, 3);
+#undef PG_ATT_SMEM
     attr_set[dev] = true;
   }
-  const bool v2 = g_attn_softmax.load(std::memory_order_relaxed) != 1;
+  const int sv = g_attn_softmax.load(std::memory_order_relaxed);
+#define PG_ATT_LAUNCH(NPV, SVV) attn_tc4_kernel<NPV, SVV><<<grid, ATT_THREADS, Smem4<NPV>::TOTAL, s>>>(tmQ, tm, tmP, p)
   if (np == 1) {
-    if (v2) attn_tc4_kernel<1, 2><<<grid, ATT_THREADS, Smem4<1>::TOTAL, s>>>(tmQ, tm, tmP, p);
-    else attn_tc4_kernel<1, 1><<<grid, ATT_THREADS, Smem4<1>::TOTAL, s>>>(tmQ, tm, tmP, p);
+    if (sv == 1) PG_ATT_LAUNCH(1, 1); else if (sv == 2) PG_ATT_LAUNCH(1, 2); else PG_ATT_LAUNCH(1, 3);
   } else {
-    if (v2) attn_tc4_kernel<2, 2><<<grid, ATT_THREADS, Smem4<2>::TOTAL, s>>>(tmQ, tm, tmP, p);
-    else attn_tc4_kernel<2, 1><<<grid, ATT_THREADS, Smem4<2>::TOTAL, s>>>(tmQ, tm, tmP, p);
+    if (sv == 1) PG_ATT_LAUNCH(2, 1); else if (sv == 2) PG_ATT_LAUNCH(2, 2); else PG_ATT_LAUNCH(2, 3);
   }
+#undef PG_ATT_LAUNCH
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;
 }

@@ -122,12 +122,44 @@ __global__ void __launch_bounds__(128) msa_prior_kernel(const uint8_t* __restric
     for (int k = 0; k < V; ++k) out[static_cast<long long>(j) * V + k] = tot[k] / norm;
 }
 
+// EVE Bayesian decoder, output 1x1 convolution with PER-SAMPLE weights (batched local-reparameterisation sampler, eve_prior.py;
+// reference arithmetic: trancepteve/EVE/VAE_decoder.py:139-147 applied to sample s's own draw of the convolution weights):
+//   y[s, j*C + c] = sum_a x[s, j*A + a] * conv[s, c*A + a]        x [S, J*A], conv [S, C*A], y [S, J*C]
+// One block per sample: its x row and its C*A weights are staged in shared memory once, then every thread owns (j, c) outputs.
+__global__ void __launch_bounds__(256) eve_conv_kernel(const float* __restrict__ x, const float* __restrict__ conv, int J, int A, int C,
+                                                        float* __restrict__ y) {
+  extern __shared__ float sm[];
+  float* sx = sm;            // [J*A]
+  float* sc = sm + J * A;    // [C*A]
+  const long long s = blockIdx.x;
+  for (int i = threadIdx.x; i < J * A; i += blockDim.x) sx[i] = x[s * J * A + i];
+  for (int i = threadIdx.x; i < C * A; i += blockDim.x) sc[i] = conv[s * C * A + i];
+  __syncthreads();
+  for (int o = threadIdx.x; o < J * C; o += blockDim.x) {
+    const int j = o / C, c = o - j * C;
+    float acc = 0.f;
+    for (int a = 0; a < A; ++a) acc = fmaf(sx[j * A + a], sc[c * A + a], acc);  // fixed order: deterministic
+    y[s * J * C + o] = acc;
+  }
+}
+
 }  // namespace
 }  // namespace pg
 
 using namespace pg;
 
 extern "C" {
+
+int pg_eve_output_conv(const float* x, const float* conv, int32_t S, int32_t J, int32_t A, int32_t C, float* y, pg_stream stream) {
+  if (S < 0 || J <= 0 || A <= 0 || C <= 0) return set_error(PG_ERR_ARG, "pg_eve_output_conv: bad sizes");
+  if (S == 0) return PG_OK;
+  if (!x || !conv || !y) return set_error(PG_ERR_ARG, "pg_eve_output_conv: null buffer");
+  const size_t smem = (static_cast<size_t>(J) * A + static_cast<size_t>(C) * A) * sizeof(float);
+  if (smem > 48 * 1024) return set_error(PG_ERR_UNSUPPORTED, "pg_eve_output_conv: (J + C) * A floats must fit 48 KB of shared memory");
+  eve_conv_kernel<<<S, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, conv, J, A, C, y);
+  PG_CUDA_OK(cudaGetLastError());
+  return PG_OK;
+}
 
 int pg_msa_cluster_neighbors(const uint8_t* tokens, int64_t ld, int32_t N, int32_t L, const int32_t* min_matches,
                              int32_t* out_neighbors, pg_stream stream) {

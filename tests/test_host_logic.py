@@ -99,7 +99,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pg_abi_version() == 4
+    assert lib.pg_abi_version() == 5
 
 
 def test_product_path_never_imports_the_oracle():
