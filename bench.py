@@ -594,7 +594,7 @@ def main():
         except Exception:
             pass
         res["roofline"] = {
-            "bound": "tensor", "kernel": "gemm_tc_kernel (CTA pairs: tcgen05.mma cta_group::2 kind::f16 + kind::f8f6f4, 256x256 tile per pair, "
+            "bound": "tensor", "kernel": "gemm_tc_kernel (CTA pairs: tcgen05.mma cta_group::2 kind::f16 + kind::f8f6f4, 256x256 tile per pair, packed-fp32 epilogue, "
                                          "TMA 6-stage ring, chunked RN accumulation, TMA-store epilogue)",
             "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": (achieved / sustained) if achieved else None,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how}); burst {burst}",

@@ -864,6 +864,18 @@ int pg_load_weights(pg_handle h, const pg_tensor* tensors, int32_t n) {
   return PG_OK;
 }
 
+// Sequences per pass: as many as the workspace holds, then evened out over the passes that needs — 512 copies of a 514-token window
+// against the default 131 072-row workspace are 171 + 171 + 170, not 255 + 255 + 2 (a 2-sequence pass pays all 33 layers' launch
+// latencies and partial waves for 0.4 % of the rows). Results do not depend on the split (rows are independent; tested).
+static long long balanced_per(long long total, long long cap) {
+  static const int off = [] { const char* e = getenv("PG_BALANCED_PASSES"); return e && atoi(e) == 0; }();  // same-box A/B only
+  if (cap < 1) cap = 1;
+  if (off) return cap;
+  if (total <= cap) return total > 0 ? total : 1;
+  const long long passes = (total + cap - 1) / cap;
+  return (total + passes - 1) / passes;
+}
+
 int pg_masked_marginals(pg_handle h, const int32_t* tokens, int32_t n_tokens, const int32_t* positions, const int32_t* win_start,
                         const int32_t* out_row, int32_t P, int32_t T, float* out_logprobs, pg_stream stream) {
   if (!h) return set_error(PG_ERR_ARG, "pg_masked_marginals: null handle");
@@ -880,6 +892,7 @@ int pg_masked_marginals(pg_handle h, const int32_t* tokens, int32_t n_tokens, co
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   long long per = h->max_rows / T;
   if (per > h->head_cap) per = h->head_cap;
+  per = balanced_per(P, per);
   for (int p0 = 0; p0 < P; p0 += static_cast<int>(per)) {
     const int Bc = (P - p0) < per ? (P - p0) : static_cast<int>(per);
     row_select_kernel<<<(Bc + 255) / 256, 256, 0, s>>>(positions, win_start, out_row, p0, Bc, h->row_sel);
@@ -911,6 +924,7 @@ int pg_msa_masked_marginals(pg_handle h, const int32_t* tokens, int32_t R, int32
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   long long per = h->max_rows / per_msa;
   if (per > h->head_cap) per = h->head_cap;
+  per = balanced_per(P, per);
   for (int p0 = 0; p0 < P; p0 += static_cast<int>(per)) {
     const int Bc = (P - p0) < per ? (P - p0) : static_cast<int>(per);
     row_select_kernel<<<(Bc + 255) / 256, 256, 0, s>>>(positions, win_start, nullptr, p0, Bc, h->row_sel);
@@ -980,7 +994,7 @@ int pg_ar_loglik_fused(pg_handle h, const int32_t* ids, const int32_t* lens, int
   if (T > h->max_rows) return fail(h, PG_ERR_ARG, "pg_ar_loglik: sequence longer than workspace");
   PG_CUDA_OK(cudaSetDevice(h->desc.device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const long long per = h->max_rows / T;
+  const long long per = balanced_per(B, h->max_rows / T);
   for (int b0 = 0; b0 < B; b0 += static_cast<int>(per)) {
     const int Bc = (B - b0) < per ? (B - b0) : static_cast<int>(per);
     const long long off = static_cast<long long>(b0) * T;
@@ -1048,7 +1062,7 @@ int pg_ar_loglik_prefix(pg_handle h, const int32_t* ids, const int32_t* lens, in
   if (rc) return rc;
   PG_CUDA_OK(cudaSetDevice(h->desc.device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const long long per = h->max_rows / T;
+  const long long per = balanced_per(B, h->max_rows / T);
   for (int b0 = 0; b0 < B; b0 += static_cast<int>(per)) {
     const int Bc = (B - b0) < per ? (B - b0) : static_cast<int>(per);
     const long long off = static_cast<long long>(b0) * T;

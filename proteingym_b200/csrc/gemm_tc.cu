@@ -83,6 +83,7 @@ struct GemmKParams {
   const float* rot_cos; const float* rot_sin; int rot_T; int rot_dim;
   int tiles_m, tiles_n;
   int prefetch;           // k-blocks of L2 look-ahead for the A operand (0 = off)
+  int fenced_release;     // 1: the peer CTA's accumulator release uses the .release.cluster arrive (round 2's first form; PG_GEMM_FENCED_RELEASE=1)
   int grp_rows_a, grp_rows_b;  // grouped (block-diagonal) mode: A rows [g*grp_rows_a, (g+1)*grp_rows_a) pair with W rows g*grp_rows_b + n
 };
 
@@ -554,7 +555,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (CTA2 && rank != 0) mbar_arrive_cluster(&tempty[buf], 0);  // the leader's MMA thread waits on its own barrier
+          if (CTA2 && rank != 0) {  // the leader's MMA thread waits on its own barrier
+            if (p.fenced_release) mbar_arrive_cluster_release(&tempty[buf], 0); else mbar_arrive_cluster(&tempty[buf], 0);
+          }
           else mbar_arrive(&tempty[buf]);
         }
       }
@@ -779,6 +782,8 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   p.tiles_n = (g.N + BN - 1) / BN;
   p.prefetch = grouped ? 0 : gemm_prefetch();
   p.grp_rows_a = g.grp_rows_a; p.grp_rows_b = g.grp_rows_b;
+  static const int fenced = [] { const char* e = getenv("PG_GEMM_FENCED_RELEASE"); return e ? atoi(e) : 0; }();
+  p.fenced_release = fenced;
   const int ntiles = p.tiles_m * p.tiles_n;
   if (!cta2) {
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
