@@ -35,7 +35,9 @@ def main():
     d = H * 64
     for nseg in (1, 3):
         np_ = 2 if nseg == 3 else 1
-        qkv = (torch.randn(B * T, 3 * d * np_, device="cuda") * 0.5).half()
+        x32 = torch.randn(B * T, 3 * d, device="cuda") * 0.5
+        hi16 = x32.half()
+        qkv = torch.cat([hi16, (x32 - hi16.float()).half()], 1).contiguous() if np_ == 2 else hi16  # lo plane = fp16 remainder, as in the model
         out = torch.empty(B * T, d * np_, device="cuda", dtype=torch.float16)
         for im in (1, impl):
             a = _lib.PgAttnArgs()
