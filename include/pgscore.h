@@ -257,11 +257,7 @@ int pg_profile_end(float* ms, int32_t* counts, int32_t ncat);
  *   "gemm_prefetch" k-blocks of L2 look-ahead the GEMM's TMA producer issues for the streamed A operand (default 0 = off: measured
  *                  neutral-to-negative in the model; PG_GEMM_PREFETCH). */
 int pg_set_tuning(const char* key, int32_t value);
-/*   "attn_softmax" arithmetic of the attention kernel's softmax warps: 3 (default) packed fp32 pairs (FFMA2 / FADD2 / FMNMX3) with the
- *                  exponent and the fp16 hi / lo packing of a 32-column chunk in one basic block; 2 packed pairs, steps separate;
- *                  1 scalar (round 2's first form). PG_ATTN_SOFTMAX.
- *   "gemm_epi"     2 (default): packed fp32 pairs in the GEMM epilogue (GELU, e4m3 / fp16 lo packing); 1: scalar. Bit-identical
- *                  results either way. PG_GEMM_EPI. */
+
 
 /* Build/version probe (also what the CPU-only test suite calls to check the library loads). */
 int pg_abi_version(void);

@@ -868,9 +868,7 @@ int pg_load_weights(pg_handle h, const pg_tensor* tensors, int32_t n) {
 // against the default 131 072-row workspace are 171 + 171 + 170, not 255 + 255 + 2 (a 2-sequence pass pays all 33 layers' launch
 // latencies and partial waves for 0.4 % of the rows). Results do not depend on the split (rows are independent; tested).
 static long long balanced_per(long long total, long long cap) {
-  static const int off = [] { const char* e = getenv("PG_BALANCED_PASSES"); return e && atoi(e) == 0; }();  // same-box A/B only
   if (cap < 1) cap = 1;
-  if (off) return cap;
   if (total <= cap) return total > 0 ? total : 1;
   const long long passes = (total + cap - 1) / cap;
   return (total + passes - 1) / passes;
@@ -1101,8 +1099,6 @@ int pg_set_tuning(const char* key, int32_t value) {
   if (std::string(key) == "gemm_kchunk") { set_gemm_kchunk(value); return PG_OK; }
   if (std::string(key) == "gemm_prefetch") { set_gemm_prefetch(value); return PG_OK; }
   if (std::string(key) == "gemm_cta2") { set_gemm_cta2(value); return PG_OK; }
-  if (std::string(key) == "attn_softmax") { set_attn_softmax(value); return PG_OK; }
-  if (std::string(key) == "gemm_epi") { set_gemm_epi(value); return PG_OK; }
   return set_error(PG_ERR_ARG, std::string("pg_set_tuning: unknown key ") + key);
 }
 

@@ -21,7 +21,6 @@
 //   The softmax warps wait for a finished PV only on the rare blocks that rescale O (pv_done), and in the epilogue (o_full).
 //   MMA issue order per work item:  QK0 QK1 QK2 | PV0 QK3 | PV1 QK4 | ...   TMA load order: K0 K1 K2 | V0 K3 | V1 K4 | ...
 //   Work item = (sequence, head, 128-query tile); persistent CTAs, grid = 2 x SMs.
-#include <atomic>
 #include <cstdlib>
 
 #include "common.h"
@@ -71,11 +70,11 @@ __device__ __forceinline__ uint32_t cvt2h(float lo_elem, float hi_elem) {
   return d;
 }
 
-// SV = softmax arithmetic version: 1 = one fp32 instruction per element and step (round 2's first form, kept for the same-box A/B
-// behind pg_set_tuning("attn_softmax", 1)); 2 = packed pairs (FFMA2 / FADD2 / FMUL2), 3-input maxima (FMNMX3) and the log2(e) scale
-// folded into the exponent's FFMA2: ~5 instead of ~9 issue slots per score. The softmax warps were the pace-setter of this kernel
-// (profiles/ncu_r02_summary.txt: 49 % issue-slot use with two softmax warps per scheduler, tensor pipe 52 % active).
-template <int NP, int SV>
+// Softmax arithmetic: packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2), 3-input maxima (FMNMX3), the log2(e) scale folded into the
+// exponent's FFMA2, and exponent + row sum + fp16 hi / lo packing of a 32-column chunk in ONE basic block so that the packing of
+// earlier pairs issues between the MUFU.EX2 instructions: ~5 instead of ~9 issue slots per score. Same-box A/B against the scalar
+// form (profiles/ab_r02_m_*.txt, profiles/ncu_r02_attn_sv3_summary.txt): 268 vs 254 TFLOP/s hi/lo, 443 vs 400 single pass.
+template <int NP>
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tm,
                                                                   const __grid_constant__ CUtensorMap tmP, const Attn4Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -282,10 +281,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
         if (live) {
           // (1) scores to the log2 domain (+ ALiBi, masks) and the block maximum of this row
           float mblk = -INFINITY;
-          float mulc[2] = {1.f, 1.f};  // SV 2: factor that takes r[] of chunk c to the log2 domain inside step (3)'s FFMA2
+          float mulc[2] = {1.f, 1.f};  // factor that takes r[] of chunk c to the log2 domain inside step (3)'s FFMA2
           auto to_log2 = [&](uint32_t (&r)[32], const int c) {
             if (c * 32 >= ncols) return;
-            if (SV >= 2 && plain && valid - c * 32 >= 32) {
+            if (plain && valid - c * 32 >= 32) {
               // raw scores stay in r[]: max(s) * log2(e) = max(s * log2(e)) (monotone rounding), the scale itself moves to step (3)
               float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -295,15 +294,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
               }
               mblk = fmaxf(mblk, fmax3(fmaxf(m4[0], m4[1]), m4[2], m4[3]) * LOG2E);
               mulc[c] = LOG2E;
-            } else if (plain && valid - c * 32 >= 32) {
-              float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float t = __uint_as_float(r[i]) * LOG2E;
-                r[i] = __float_as_uint(t);
-                m4[i & 3] = fmaxf(m4[i & 3], t);
-              }
-              mblk = fmaxf(mblk, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
             } else if (vrow - c * 32 >= 32) {  // every column of this chunk visible to this row: no masks
               float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -334,38 +324,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
           const float mref = (m_run == -INFINITY) ? 0.f : m_run;  // a row that has seen no key yet: every t is -inf -> P = 0
           // (3) P = 2^(t - m_run), row sum
           float lsum = 0.f;
-          auto to_p = [&](uint32_t (&r)[32], const int c) {
-            if (c * 32 >= ncols) return;
-            if (SV >= 2) {
-              const uint64_t mul2 = f2_pack(mulc[c], mulc[c]), neg2 = f2_pack(-mref, -mref);
-              uint64_t l2[4] = {0ull, 0ull, 0ull, 0ull};  // {0.f, 0.f}
-#pragma unroll
-              for (int u = 0; u < 16; ++u) {
-                float d0, d1;
-                f2_unpack(f2_fma(f2_pack(__uint_as_float(r[2 * u]), __uint_as_float(r[2 * u + 1])), mul2, neg2), d0, d1);
-                const float e0 = ex2a3(d0), e1 = ex2a3(d1);
-                r[2 * u] = __float_as_uint(e0);
-                r[2 * u + 1] = __float_as_uint(e1);
-                l2[u & 3] = f2_add(l2[u & 3], f2_pack(e0, e1));
-              }
-              float a0, a1;
-              f2_unpack(f2_add(f2_add(l2[0], l2[1]), f2_add(l2[2], l2[3])), a0, a1);
-              lsum += a0 + a1;
-              return;
-            }
-            float l4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float e = ex2a3(__uint_as_float(r[i]) - mref);
-              l4[i & 3] += e;
-              r[i] = __float_as_uint(e);
-            }
-            lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-          };
-          // SV 3: steps (3) and (5) of a 32-column chunk in ONE basic block — exponent FFMA2, ex2, row sum, fp16 hi / lo pairs and the
+          // steps (3) and (5) of a 32-column chunk in ONE basic block — exponent FFMA2, ex2, row sum, fp16 hi / lo pairs and the
           // tcgen05.st — so that the scheduler can issue the packing of earlier pairs between the MUFU.EX2 instructions (a warp-wide
-          // MUFU holds the SFU for 8 cycles; ncu r02 of SV 2: 47 % of the softmax samples were fixed-latency waits behind a block of
-          // 32 back-to-back MUFUs, with the F2FP / HADD2 / FADD2 work of step (5) queued behind it in a later block).
+          // MUFU holds the SFU for 8 cycles; with the two steps in separate blocks 47 % of the softmax samples were fixed-latency
+          // waits behind 32 back-to-back MUFUs, the F2FP / HADD2 / FADD2 work of step (5) queued behind them).
           auto exp_store = [&](uint32_t (&r)[32], const int c) {
             if (c * 32 >= ncols) return;
             const uint64_t mul2 = f2_pack(mulc[c], mulc[c]), neg2 = f2_pack(-mref, -mref);
@@ -392,13 +354,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
             tmem_st_32x32b_x16(tmem_s + c * 16, hi);
             if (NP == 2) tmem_st_32x32b_x16(tmem_s + 32 + c * 16, lo);
           };
-          if (SV == 3) {
-            exp_store(r0, 0);
-            exp_store(r1, 1);
-          } else {
-            to_p(r0, 0);
-            to_p(r1, 1);
-          }
+          exp_store(r0, 0);
+          exp_store(r1, 1);
           l = fmaf(l, scale, lsum);
           // (4) rare: the running maximum moved -> bring the O accumulated so far to the new reference. PV(n-1) (and with it every
           //     earlier PV) must have completed; PV(n) cannot start before this warp arrives on p_full below.
@@ -415,32 +372,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
               tmem_st_32x32b_x32(tmem_base + lane_addr + O_COL + c * 32, o);
             }
           }
-          // (5) P -> fp16 pairs, in place over the S slot: hi pairs in columns [0,32), lo pairs in [32,64)
-          auto store_p = [&](const uint32_t (&r)[32], const int c) {
-            if (c * 32 >= ncols) return;
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const float x0 = __uint_as_float(r[2 * u]), x1 = __uint_as_float(r[2 * u + 1]);
-              hi[u] = cvt2h(x0, x1);
-              if (NP == 2) {
-                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
-                if (SV >= 2) {
-                  float q0, q1;
-                  f2_unpack(f2_sub(f2_pack(x0, x1), f2_pack(hf.x, hf.y)), q0, q1);
-                  lo[u] = cvt2h(q0, q1);
-                } else {
-                  lo[u] = cvt2h(x0 - hf.x, x1 - hf.y);
-                }
-              }
-            }
-            tmem_st_32x32b_x16(tmem_s + c * 16, hi);
-            if (NP == 2) tmem_st_32x32b_x16(tmem_s + 32 + c * 16, lo);
-          };
-          if (SV != 3) {
-            store_p(r0, 0);
-            store_p(r1, 1);
-          }
+          // (5) the P stores were issued by exp_store; PV(n) may read them once they have landed
           tmem_st_wait();
         }
         tc_fence_before();
@@ -475,19 +407,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             float x0, x1;
-            if (SV >= 2) f2_unpack(f2_mul(f2_pack(__uint_as_float(o[2 * u]), __uint_as_float(o[2 * u + 1])), f2_pack(rl, rl)), x0, x1);
-            else { x0 = __uint_as_float(o[2 * u]) * rl; x1 = __uint_as_float(o[2 * u + 1]) * rl; }
+            f2_unpack(f2_mul(f2_pack(__uint_as_float(o[2 * u]), __uint_as_float(o[2 * u + 1])), f2_pack(rl, rl)), x0, x1);
             hi[u] = cvt2h(x0, x1);
             const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
-            if (SV >= 2) {
-              float q0, q1;
-              f2_unpack(f2_sub(f2_pack(x0, x1), f2_pack(hf.x, hf.y)), q0, q1);
-              o[2 * u] = __float_as_uint(q0);           // o[] now holds the fp32 remainders
-              o[2 * u + 1] = __float_as_uint(q1);
-            } else {
-              o[2 * u] = __float_as_uint(x0 - hf.x);
-              o[2 * u + 1] = __float_as_uint(x1 - hf.y);
-            }
+            float q0, q1;
+            f2_unpack(f2_sub(f2_pack(x0, x1), f2_pack(hf.x, hf.y)), q0, q1);
+            o[2 * u] = __float_as_uint(q0);           // o[] now holds the fp32 remainders
+            o[2 * u + 1] = __float_as_uint(q1);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) d4[u] = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
@@ -528,14 +454,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-std::atomic<int> g_attn_softmax{[] {
-  const char* e = std::getenv("PG_ATTN_SOFTMAX");
-  return e ? std::atoi(e) : 3;
-}()};
-
 }  // namespace
-
-void set_attn_softmax(int v) { g_attn_softmax.store(v, std::memory_order_relaxed); }
 
 int launch_attention_tc4(const AttnLaunch& a, cudaStream_t s) {
   if (a.B <= 0 || a.T <= 0) return PG_OK;
@@ -578,19 +497,12 @@ int launch_attention_tc4(const AttnLaunch& a, cudaStream_t s) {
   PG_CUDA_OK(cudaGetDevice(&dev));
   static bool attr_set[64] = {};
   if (dev < 64 && !attr_set[dev]) {
-#define PG_ATT_SMEM(NPV, SVV) PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<NPV, SVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<NPV>::TOTAL))
-    PG_ATT_SMEM(1, 1); PG_ATT_SMEM(2, 1); PG_ATT_SMEM(1, 2); PG_ATT_SMEM(2, 2); PG_ATT_SMEM(1, 3); PG_ATT_SMEM(2, 3);
-#undef PG_ATT_SMEM
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<1>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<2>::TOTAL));
     attr_set[dev] = true;
   }
-  const int sv = g_attn_softmax.load(std::memory_order_relaxed);
-#define PG_ATT_LAUNCH(NPV, SVV) attn_tc4_kernel<NPV, SVV><<<grid, ATT_THREADS, Smem4<NPV>::TOTAL, s>>>(tmQ, tm, tmP, p)
-  if (np == 1) {
-    if (sv == 1) PG_ATT_LAUNCH(1, 1); else if (sv == 2) PG_ATT_LAUNCH(1, 2); else PG_ATT_LAUNCH(1, 3);
-  } else {
-    if (sv == 1) PG_ATT_LAUNCH(2, 1); else if (sv == 2) PG_ATT_LAUNCH(2, 2); else PG_ATT_LAUNCH(2, 3);
-  }
-#undef PG_ATT_LAUNCH
+  if (np == 1) attn_tc4_kernel<1><<<grid, ATT_THREADS, Smem4<1>::TOTAL, s>>>(tmQ, tm, tmP, p);
+  else attn_tc4_kernel<2><<<grid, ATT_THREADS, Smem4<2>::TOTAL, s>>>(tmQ, tm, tmP, p);
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;
 }

@@ -60,8 +60,6 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s);
 void set_gemm_kchunk(int v);    // tuning: see gemm_tc.cu
 void set_gemm_prefetch(int v);
 void set_gemm_cta2(int v);      // 1: CTA-pair (cta_group::2) GEMM kernel
-void set_attn_softmax(int v);   // attention_tc4.cu softmax arithmetic: 2 (default) packed FFMA2/FADD2/FMNMX3, 1 scalar
-void set_gemm_epi(int v);       // gemm_tc.cu epilogue arithmetic: 2 (default) packed pairs, 1 scalar
 
 // fmt / scale as above (fmt 0 when lo_off == 0).
 int launch_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int rows, int d, __half* out,

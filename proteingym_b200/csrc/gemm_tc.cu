@@ -83,31 +83,14 @@ struct GemmKParams {
   const float* rot_cos; const float* rot_sin; int rot_T; int rot_dim;
   int tiles_m, tiles_n;
   int prefetch;           // k-blocks of L2 look-ahead for the A operand (0 = off)
-  int fenced_release;     // 1: the peer CTA's accumulator release uses the .release.cluster arrive (round 2's first form; PG_GEMM_FENCED_RELEASE=1)
   int grp_rows_a, grp_rows_b;  // grouped (block-diagonal) mode: A rows [g*grp_rows_a, (g+1)*grp_rows_a) pair with W rows g*grp_rows_b + n
 };
 
 // Exact-erf GELU (esm/modules.py:17-24): 0.5*x*(1+erf(x/sqrt2)) = 0.5*x + 0.5*|x|*erf(|x|/sqrt2).
 // erf via Abramowitz & Stegun 7.1.26 (abs error <= 1.5e-7; measured |gelu error| <= 4.7e-7, below torch's own fp32 gelu),
-// branch-free: MUFU.RCP + MUFU.EX2 + ~11 FMA-pipe ops instead of erff()'s two divergent code paths.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float ax = fabsf(x);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, ax, 1.0f)));  // 1/(1 + 0.3275911*|x|/sqrt2)
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));  // exp(-x^2/2)
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  return fmaf(0.5f * ax, erf_abs, 0.5f * x);
-}
-
-// The same arithmetic on two values per instruction (FFMA2 / FMUL2: one issue slot for both lanes; every operation and rounding is
-// the scalar form's, with the polynomial carried negated so that 1 - poly*e is a single FFMA2): bit-identical results, ~9 instead
-// of ~15 issue slots per element. EV = 2 (default) selects the packed epilogue arithmetic, EV = 1 the scalar one (A/B switch).
+// branch-free: MUFU.RCP + MUFU.EX2 + FMA-pipe ops instead of erff()'s two divergent code paths, evaluated on TWO values per
+// instruction (sm_100 FFMA2 / FMUL2: one issue slot for both lanes; the polynomial is carried negated so that 1 - poly*e is a single
+// FFMA2): ~9 issue slots per element.
 #define PG_F2C(v) f2_pack((v), (v))
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   const uint64_t x = f2_pack(x0, x1), ax = f2_pack(fabsf(x0), fabsf(x1));
@@ -133,7 +116,7 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
 // are bank-conflict free and the global write is one coalesced bulk tensor store (or reduce-add) per block, clipped at M and N.
 //   fp16 / fp32: 32 rows x 128 B, SWIZZLE_128B (16-byte chunk c of row r lives at chunk c ^ (r & 7))
 //   e4m3       : two tiles of 32 rows x 64 B (lo8 at +0, hi8 at +2048), SWIZZLE_64B (chunk c of row r at c ^ ((r >> 1) & 3))
-template <int OFF, int EV>
+template <int OFF>
 __device__ __forceinline__ void stage_row_f16(uint8_t* stg, int lane, const float (&acc)[128], bool lo_plane) {
   uint8_t* row = stg + lane * 128;
   const int sw = lane & 7;
@@ -146,13 +129,9 @@ __device__ __forceinline__ void stage_row_f16(uint8_t* stg, int lane, const floa
       const uint32_t hi = cvt_f16x2_rn(x0, x1);
       if (lo_plane) {
         const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-        if (EV == 2) {
-          float q0, q1;
-          f2_unpack(f2_sub(f2_pack(x0, x1), f2_pack(hf.x, hf.y)), q0, q1);
-          w[u] = cvt_f16x2_rn(q0, q1);
-        } else {
-          w[u] = cvt_f16x2_rn(x0 - hf.x, x1 - hf.y);
-        }
+        float q0, q1;
+        f2_unpack(f2_sub(f2_pack(x0, x1), f2_pack(hf.x, hf.y)), q0, q1);
+        w[u] = cvt_f16x2_rn(q0, q1);
       } else {
         w[u] = hi;
       }
@@ -162,7 +141,7 @@ __device__ __forceinline__ void stage_row_f16(uint8_t* stg, int lane, const floa
 }
 // e4m3 planes of 64 accumulated columns as packed words (16 x lo8, 16 x hi8): pure register math, so it can run while the TMA
 // store of the fp16 hi tile is still reading the staging buffer.
-template <int OFF, int EV>
+template <int OFF>
 __device__ __forceinline__ void pack_row_f8(const float (&acc)[128], float s_hi, float s_lo, uint32_t (&wl)[16], uint32_t (&wh)[16]) {
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
@@ -170,19 +149,14 @@ __device__ __forceinline__ void pack_row_f8(const float (&acc)[128], float s_hi,
     const uint32_t h01 = cvt_f16x2_rn(x0, x1), h23 = cvt_f16x2_rn(x2, x3);
     const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
     const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
-    if (EV == 2) {
-      const uint64_t p01 = f2_pack(f01.x, f01.y), p23 = f2_pack(f23.x, f23.y), sh2 = f2_pack(s_hi, s_hi), sl2 = f2_pack(s_lo, s_lo);
-      float a0, a1, a2, a3, b0, b1, b2, b3;
-      f2_unpack(f2_mul(p01, sh2), a0, a1);
-      f2_unpack(f2_mul(p23, sh2), a2, a3);
-      f2_unpack(f2_mul(f2_sub(f2_pack(x0, x1), p01), sl2), b0, b1);
-      f2_unpack(f2_mul(f2_sub(f2_pack(x2, x3), p23), sl2), b2, b3);
-      wh[u] = pack4_e4m3(a0, a1, a2, a3);
-      wl[u] = pack4_e4m3(b0, b1, b2, b3);
-      continue;
-    }
-    wh[u] = pack4_e4m3(f01.x * s_hi, f01.y * s_hi, f23.x * s_hi, f23.y * s_hi);
-    wl[u] = pack4_e4m3((x0 - f01.x) * s_lo, (x1 - f01.y) * s_lo, (x2 - f23.x) * s_lo, (x3 - f23.y) * s_lo);
+    const uint64_t p01 = f2_pack(f01.x, f01.y), p23 = f2_pack(f23.x, f23.y), sh2 = f2_pack(s_hi, s_hi), sl2 = f2_pack(s_lo, s_lo);
+    float a0, a1, a2, a3, b0, b1, b2, b3;
+    f2_unpack(f2_mul(p01, sh2), a0, a1);
+    f2_unpack(f2_mul(p23, sh2), a2, a3);
+    f2_unpack(f2_mul(f2_sub(f2_pack(x0, x1), p01), sl2), b0, b1);
+    f2_unpack(f2_mul(f2_sub(f2_pack(x2, x3), p23), sl2), b2, b3);
+    wh[u] = pack4_e4m3(a0, a1, a2, a3);
+    wl[u] = pack4_e4m3(b0, b1, b2, b3);
   }
 }
 __device__ __forceinline__ void stage_row_f8(uint8_t* stg, int lane, const uint32_t (&wl)[16], const uint32_t (&wh)[16]) {
@@ -213,7 +187,7 @@ struct EpiCtx {
 };
 
 // Bias, activation and store of one 64-column group (G = 0, 1) of this thread's 128 accumulated columns.
-template <int EPI, int G, int EV>
+template <int EPI, int G>
 __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKParams& p, const EpiCtx& c) {
   constexpr int O = G * 64;
   const int gcol = c.gcol + O;
@@ -224,12 +198,8 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float4 x = __ldg(b4 + j);
-        if (EV == 2) {
-          f2_unpack(f2_add(f2_pack(acc[O + 4 * j], acc[O + 4 * j + 1]), f2_pack(x.x, x.y)), acc[O + 4 * j], acc[O + 4 * j + 1]);
-          f2_unpack(f2_add(f2_pack(acc[O + 4 * j + 2], acc[O + 4 * j + 3]), f2_pack(x.z, x.w)), acc[O + 4 * j + 2], acc[O + 4 * j + 3]);
-        } else {
-          acc[O + 4 * j] += x.x; acc[O + 4 * j + 1] += x.y; acc[O + 4 * j + 2] += x.z; acc[O + 4 * j + 3] += x.w;
-        }
+        f2_unpack(f2_add(f2_pack(acc[O + 4 * j], acc[O + 4 * j + 1]), f2_pack(x.x, x.y)), acc[O + 4 * j], acc[O + 4 * j + 1]);
+        f2_unpack(f2_add(f2_pack(acc[O + 4 * j + 2], acc[O + 4 * j + 3]), f2_pack(x.z, x.w)), acc[O + 4 * j + 2], acc[O + 4 * j + 3]);
       }
     } else {
 #pragma unroll
@@ -237,24 +207,14 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
     }
   }
   if (EPI == 1) {
-    if (EV == 2) {
 #pragma unroll
-      for (int j = 0; j < 64; j += 2) gelu_erf2(acc[O + j], acc[O + j + 1]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 64; ++j) acc[O + j] = gelu_erf(acc[O + j]);
-    }
+    for (int j = 0; j < 64; j += 2) gelu_erf2(acc[O + j], acc[O + j + 1]);
   } else if (EPI == 4) {  // squared ReLU (Tranception MLP, tranception/activations.py:79-84)
 #pragma unroll
     for (int j = 0; j < 64; j += 2) {
       const float a = fmaxf(acc[O + j], 0.f), b = fmaxf(acc[O + j + 1], 0.f);
-      if (EV == 2) {
-        const uint64_t ab = f2_pack(a, b);
-        f2_unpack(f2_mul(ab, ab), acc[O + j], acc[O + j + 1]);
-      } else {
-        acc[O + j] = a * a;
-        acc[O + j + 1] = b * b;
-      }
+      const uint64_t ab = f2_pack(a, b);
+      f2_unpack(f2_mul(ab, ab), acc[O + j], acc[O + j + 1]);
     }
   } else if (EPI == 3 && gcol < 2 * p.rot_dim) {
     // rotary: x*cos + rotate_half(x)*sin over one 64-wide head; cos/sin[t, j] for j in [0,32) (both halves equal)
@@ -288,7 +248,7 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
   } else {
     if (lane == 0) bulk_wait_read0();
     __syncwarp();
-    stage_row_f16<O, EV>(stg, lane, acc, false);
+    stage_row_f16<O>(stg, lane, acc, false);
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -298,7 +258,7 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
     if (p.out_fmt == 1) {
       if (lane == 0) bulk_wait_read0();
       __syncwarp();
-      stage_row_f16<O, EV>(stg, lane, acc, true);
+      stage_row_f16<O>(stg, lane, acc, true);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -307,7 +267,7 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
       }
     } else if (p.out_fmt == 2) {
       uint32_t wl[16], wh[16];
-      pack_row_f8<O, EV>(acc, p.out_scale, p.out_scale * 2048.f, wl, wh);  // overlaps the hi store's read of the staging tile
+      pack_row_f8<O>(acc, p.out_scale, p.out_scale * 2048.f, wl, wh);  // overlaps the hi store's read of the staging tile
       if (lane == 0) bulk_wait_read0();
       __syncwarp();
       stage_row_f8(stg, lane, wl, wh);
@@ -322,7 +282,7 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
   }
 }
 
-template <int EPI, int CTA2, int EV>
+template <int EPI, int CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8,
@@ -507,18 +467,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 32; ++j) acc[i * 32 + j] = __uint_as_float(r[i][j]);
           } else if (p.w_uniform) {  // e4m3 cross terms, one scale per weight matrix: a single factor for the whole tile
             const float f = p.a_inv * __ldg(p.w_inv);
-            const uint64_t f2 = f2_pack(f, f);
+            // scalar on purpose (as the chunk adds below): with 128 accumulators + 128 freshly loaded values live, the 64-bit
+            // register pairing of the packed forms made ptxas spill
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                if (EV == 3) {  // packed form: with 128 accumulators + 128 freshly loaded values live the register pairing spills
-                  f2_unpack(f2_mul(f2_pack(__uint_as_float(r[i][j]), __uint_as_float(r[i][j + 1])), f2), acc[i * 32 + j], acc[i * 32 + j + 1]);
-                } else {
-                  acc[i * 32 + j] = __uint_as_float(r[i][j]) * f;
-                  acc[i * 32 + j + 1] = __uint_as_float(r[i][j + 1]) * f;
-                }
-              }
+              for (int j = 0; j < 32; ++j) acc[i * 32 + j] = __uint_as_float(r[i][j]) * f;
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -536,33 +490,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld_32x32b_x32(taddr + hp * 64 + 32, r1);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              if (EV == 3) {
-                f2_unpack(f2_add(f2_pack(acc[hp * 64 + j], acc[hp * 64 + j + 1]), f2_pack(__uint_as_float(r0[j]), __uint_as_float(r0[j + 1]))),
-                          acc[hp * 64 + j], acc[hp * 64 + j + 1]);
-                f2_unpack(f2_add(f2_pack(acc[hp * 64 + 32 + j], acc[hp * 64 + 32 + j + 1]),
-                                 f2_pack(__uint_as_float(r1[j]), __uint_as_float(r1[j + 1]))),
-                          acc[hp * 64 + 32 + j], acc[hp * 64 + 32 + j + 1]);
-              } else {
-                acc[hp * 64 + j] += __uint_as_float(r0[j]);
-                acc[hp * 64 + j + 1] += __uint_as_float(r0[j + 1]);
-                acc[hp * 64 + 32 + j] += __uint_as_float(r1[j]);
-                acc[hp * 64 + 32 + j + 1] += __uint_as_float(r1[j + 1]);
-              }
+            for (int j = 0; j < 32; ++j) {
+              acc[hp * 64 + j] += __uint_as_float(r0[j]);
+              acc[hp * 64 + 32 + j] += __uint_as_float(r1[j]);
             }
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (CTA2 && rank != 0) {  // the leader's MMA thread waits on its own barrier
-            if (p.fenced_release) mbar_arrive_cluster_release(&tempty[buf], 0); else mbar_arrive_cluster(&tempty[buf], 0);
-          }
+          if (CTA2 && rank != 0) mbar_arrive_cluster(&tempty[buf], 0);  // the leader's MMA thread waits on its own barrier
           else mbar_arrive(&tempty[buf]);
         }
       }
-      finalize_group<EPI, 0, EV>(acc, p, c);
-      finalize_group<EPI, 1, EV>(acc, p, c);
+      finalize_group<EPI, 0>(acc, p, c);
+      finalize_group<EPI, 1>(acc, p, c);
     }
     if (lane == 0) bulk_wait0();  // all bulk stores of this warp have landed
   }
@@ -657,16 +599,6 @@ int gemm_cta2() {
   return g_cta2;
 }
 void set_gemm_cta2(int v) { g_cta2 = v ? 1 : 0; }
-// Epilogue arithmetic of the CTA-pair kernel: 2 = packed fp32 pairs (default), 1 = scalar (bit-identical results; same-box A/B only).
-static int g_epi_v = -1;
-int gemm_epi() {
-  if (g_epi_v < 0) {
-    const char* e = getenv("PG_GEMM_EPI");
-    g_epi_v = e ? atoi(e) : 2;
-  }
-  return g_epi_v;
-}
-void set_gemm_epi(int v) { g_epi_v = v == 1 ? 1 : 2; }
 int gemm_kchunk() {
   if (g_kchunk < 0) {
     const char* e = getenv("PG_GEMM_KCHUNK");
@@ -700,10 +632,9 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   PG_CUDA_OK(cudaGetDevice(&dev));
   static bool attr_set[64] = {};
   if (dev < 64 && !attr_set[dev]) {
-#define PG_SET_SMEM(E)                                                                                                 \
-  PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<E, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)); \
-  PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<E, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)); \
-  PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<E, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM))
+#define PG_SET_SMEM(E)                                                                                              \
+  PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<E, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)); \
+  PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM))
     PG_SET_SMEM(0); PG_SET_SMEM(1); PG_SET_SMEM(2); PG_SET_SMEM(3); PG_SET_SMEM(4);
 #undef PG_SET_SMEM
     attr_set[dev] = true;
@@ -782,17 +713,15 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   p.tiles_n = (g.N + BN - 1) / BN;
   p.prefetch = grouped ? 0 : gemm_prefetch();
   p.grp_rows_a = g.grp_rows_a; p.grp_rows_b = g.grp_rows_b;
-  static const int fenced = [] { const char* e = getenv("PG_GEMM_FENCED_RELEASE"); return e ? atoi(e) : 0; }();
-  p.fenced_release = fenced;
   const int ntiles = p.tiles_m * p.tiles_n;
   if (!cta2) {
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
     switch (g.epi) {
-      case 0: gemm_tc_kernel<0, 0, 2><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-      case 1: gemm_tc_kernel<1, 0, 2><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-      case 2: gemm_tc_kernel<2, 0, 2><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-      case 3: gemm_tc_kernel<3, 0, 2><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-      default: gemm_tc_kernel<4, 0, 2><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      case 0: gemm_tc_kernel<0, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      case 1: gemm_tc_kernel<1, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      case 2: gemm_tc_kernel<2, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      case 3: gemm_tc_kernel<3, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      default: gemm_tc_kernel<4, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
     }
     PG_CUDA_OK(cudaGetLastError());
     return PG_OK;
@@ -810,17 +739,13 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e;
-#define PG_LAUNCH2(E)                                                                                             \
-  e = (gemm_epi() != 1) ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<E, 1, 2>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p) \
-                        : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<E, 1, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p)
   switch (g.epi) {
-    case 0: PG_LAUNCH2(0); break;
-    case 1: PG_LAUNCH2(1); break;
-    case 2: PG_LAUNCH2(2); break;
-    case 3: PG_LAUNCH2(3); break;
-    default: PG_LAUNCH2(4); break;
+    case 0: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<0, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    case 1: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    case 2: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    case 3: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<3, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    default: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<4, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
   }
-#undef PG_LAUNCH2
   PG_CUDA_OK(e);
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;

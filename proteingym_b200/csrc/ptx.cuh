@@ -238,16 +238,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 // MEMBAR.ALL.GPU + ERRBAR in front of every remote arrive — 3 % of all warp samples of the fc1 GEMM sat in that fence
 // (profiles/prof_r02_gemm_fc1_f16f8_cta2.ncu-rep), each one holding back the release of an accumulator buffer to the leader's MMA
 // thread until the epilogue's outstanding global stores had drained.
-__device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t rank) {  // the fenced form, for the A/B only
-  asm volatile(
-      "{\n\t"
-      ".reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(rank)
-      : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t"
