@@ -38,9 +38,13 @@ enum pg_arch {
  *  PG_PREC_F16F8: linear layers = one kind::f16 pass hi*hi + one kind::f8f6f4 pass holding BOTH cross terms as e4m3
  *                 ([lo8 | hi8] x [hi8 | lo8] along K, 2x the fp16 rate) = 2 units; attention keeps the x3 scheme. ~16-bit
  *                 operands; meets the 1e-3 abs per-mutant parity target. Default of the host code.
+ *  PG_PREC_F16D : delta operands (ESM-1b / ESM-1v masked-marginals on one shared window): every linear layer = the shared unmasked
+ *                 row at F16X3 precision, computed once per window, + ONE fp16 pass on the per-copy difference to it; the row that
+ *                 holds the mask takes an exact (F16X3) compact path. 1 tensor-pipe unit per algorithmic FLOP; every other entry
+ *                 point of such a handle behaves as F16X3.
  *  PG_PREC_F16  : single fp16 pass; fastest, |error| ~1e-2 on scores of std ~6 (Spearman > 0.999) — not a parity mode.
  * In all modes the hi*hi accumulation is cut into K chunks that the epilogue adds in round-to-nearest fp32 (gemm_tc.cu). */
-enum pg_precision { PG_PREC_F16 = 0, PG_PREC_F16X3 = 1, PG_PREC_F16F8 = 2 };
+enum pg_precision { PG_PREC_F16 = 0, PG_PREC_F16X3 = 1, PG_PREC_F16F8 = 2, PG_PREC_F16D = 3 };
 
 typedef struct {
   int32_t arch;            /* pg_arch */
@@ -196,6 +200,10 @@ typedef struct {
    * of 128 per group) meet rows [g*grp_rows_b, g*grp_rows_b + N) of w; outputs keep a's row index. The tied row attention of the MSA
    * Transformer runs its two products this way (esm/axial_attention.py:140,176). 0 = plain GEMM. */
   int32_t grp_rows_a, grp_rows_b;
+  /* delta-operand form (PG_PREC_F16D): `a` holds differences to shared base rows t = row % base_T (M a multiple of base_T, N % 64 == 0);
+   * base_pre [base_T, N] fp32 is added to the accumulator before the activation, base_post [base_T, N] (or NULL) subtracted after
+   * it, and with epi 2 the rows (row / base_T) * base_T + mask_pos[row / base_T] receive no update (mask_pos device int32, or NULL). */
+  const float* base_pre; const float* base_post; int32_t base_T; const int32_t* mask_pos;
 } pg_gemm_args;
 int pg_gemm(const pg_gemm_args* args, pg_stream stream);
 
@@ -218,6 +226,9 @@ typedef struct {
   int32_t causal; const float* alibi_slopes; /* NULL = none */
   int32_t impl; /* 0 = the model's kernel (tcgen05/TMEM, 2 CTAs per SM, 128x64 blocks), 1 = mma.sync cross-check kernel */
   int32_t out_fmt; float out_scale; /* as pg_gemm_args (0 = auto); 2 only with impl 0 */
+  /* delta-operand form (impl 0): out = attention - base_o[t] (base_o fp32 [T, heads*64], or NULL); the full-precision value of row
+   * mask_pos[b] of every sequence b goes to row b of cout as an fp16 hi / lo pair (pitch ldc, lo plane at +c_lo_off), or NULL. */
+  const float* base_o; const int32_t* mask_pos; void* cout; int64_t ldc; int64_t c_lo_off;
 } pg_attn_args;
 int pg_attention(const pg_attn_args* args, pg_stream stream);
 

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpgscore.so")
 
 PG_ARCH_ESM1B, PG_ARCH_ESM2, PG_ARCH_TRANCEPTION, PG_ARCH_MSA = 0, 1, 2, 3
-PG_PREC_F16, PG_PREC_F16X3, PG_PREC_F16F8 = 0, 1, 2
+PG_PREC_F16, PG_PREC_F16X3, PG_PREC_F16F8, PG_PREC_F16D = 0, 1, 2, 3
 
 
 class PgModelDesc(C.Structure):
@@ -28,7 +28,8 @@ class PgGemmArgs(C.Structure):
                 ("resid", C.c_void_p), ("ldr", C.c_int64),
                 ("rot_cos", C.c_void_p), ("rot_sin", C.c_void_p), ("rot_T", C.c_int32), ("rot_dim", C.c_int32),
                 ("a_scale", C.c_float), ("w_inv", C.c_void_p), ("out_fmt", C.c_int32), ("out_scale", C.c_float),
-                ("grp_rows_a", C.c_int32), ("grp_rows_b", C.c_int32)]
+                ("grp_rows_a", C.c_int32), ("grp_rows_b", C.c_int32),
+                ("base_pre", C.c_void_p), ("base_post", C.c_void_p), ("base_T", C.c_int32), ("mask_pos", C.c_void_p)]
 
 
 class PgAttnArgs(C.Structure):
@@ -36,7 +37,8 @@ class PgAttnArgs(C.Structure):
                 ("out", C.c_void_p), ("ldo", C.c_int64), ("out_lo_off", C.c_int64),
                 ("B", C.c_int32), ("T", C.c_int32), ("heads", C.c_int32), ("nseg", C.c_int32),
                 ("causal", C.c_int32), ("alibi_slopes", C.c_void_p), ("impl", C.c_int32),
-                ("out_fmt", C.c_int32), ("out_scale", C.c_float)]
+                ("out_fmt", C.c_int32), ("out_scale", C.c_float),
+                ("base_o", C.c_void_p), ("mask_pos", C.c_void_p), ("cout", C.c_void_p), ("ldc", C.c_int64), ("c_lo_off", C.c_int64)]
 
 
 class PgArFusion(C.Structure):

@@ -212,6 +212,13 @@ struct pg_handle_s {
   // compact buffers for the pruned last layer (one row per sequence)
   float* xc = nullptr;
   __half *cabuf = nullptr, *cfbuf = nullptr;
+  // delta-operand mode (PG_PREC_F16D): per-layer base rows of the unmasked window (one allocation, regrown on demand, not in
+  // `allocs`) and the compact exact q/k/v rows of the masked positions
+  bool delta = false;
+  float* base = nullptr;
+  size_t base_floats = 0;
+  int base_T = 0;
+  __half* cq = nullptr;
 };
 
 namespace pg {
@@ -338,6 +345,204 @@ int forward_rows(pg_handle h, const int32_t* tokens, int n_tokens, const int32_t
     f2.resid = h->x;
     rc = run_lin(h, CAT_GEMM_FC2, f2, s);
     if (rc) return rc;
+  }
+  return PG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Delta-operand mode (PG_PREC_F16D) of the masked-marginal pass. The P masked copies of a window differ from the unmasked window
+// by a perturbation: every GEMM input is a = a0[t] + D with the base row a0[t] shared by all copies. The linear layers then are
+//   W a + b = (W a0[t] + b)  +  W D
+// with the first term computed ONCE per window at the fp16 hi/lo x3 precision (forward_base: T rows) and the second per copy in a
+// SINGLE fp16 pass on D = rn16(a - a0[t]) — the products' error scales with |D|, which is 6-10 % of |a| on the rows that do not
+// hold the mask (scripts/precision_delta.py, true ESM-1v 650M size: max score error 5.7e-4 at L = 96 against 1.5e-2 for a plain
+// single pass). The row that holds the mask (|D| ~ |a|) takes the compact exact path: P rows per layer through the x3 GEMMs, like
+// the pruned last layer. One tensor-pipe unit per algorithmic FLOP instead of two (fp16 + e4m3 cross terms) or three.
+//   base rows per layer (fp32 [T, n]): a0 = LN1 output, bqkv = Wqkv a0 + b, o0 = attention output, bout = Wo o0 + b, b0 = LN2 output,
+//   bfc1 = W1 b0 + b (pre-GELU), f0 = GELU output, bfc2 = W2 f0 + b.
+struct BaseRows { const float *a0, *bqkv, *o0, *bout, *b0, *bfc1, *f0, *bfc2; };
+BaseRows base_rows(pg_handle h, int l) {
+  const long long T = h->base_T, d = h->desc.embed_dim, f = h->desc.ffn_dim;
+  const float* p = h->base + static_cast<long long>(l) * T * (8 * d + 2 * f);
+  BaseRows b;
+  b.a0 = p; b.bqkv = p + T * d; b.o0 = p + T * 4 * d; b.bout = p + T * 5 * d; b.b0 = p + T * 6 * d; b.bfc1 = p + T * 7 * d;
+  b.f0 = p + T * (7 * d + f); b.bfc2 = p + T * (7 * d + 2 * f);
+  return b;
+}
+
+// The unmasked window (with the token-dropout scale of a copy that holds one mask) through the model at x3 precision, recording
+// the base rows of every layer. Uses the pass workspace (T rows of it) before the passes start.
+int forward_base(pg_handle h, const int32_t* tokens, int n_tokens, int T, cudaStream_t s) {
+  const pg_model_desc& D = h->desc;
+  const int d = D.embed_dim, f = D.ffn_dim, np = h->np;
+  const int64_t ldd = static_cast<int64_t>(d) * np, ldf = static_cast<int64_t>(f) * np, ldq = static_cast<int64_t>(3 * d) * np;
+  const size_t need = static_cast<size_t>(D.layers) * T * (8 * static_cast<size_t>(d) + 2 * static_cast<size_t>(f));
+  if (need > h->base_floats) {
+    if (h->base) cudaFree(h->base);
+    h->base = nullptr; h->base_floats = 0;
+    cudaError_t e = cudaMalloc(&h->base, need * sizeof(float));
+    if (e != cudaSuccess) return set_error(PG_ERR_CUDA, std::string("forward_base: cudaMalloc: ") + cudaGetErrorString(e));
+    h->base_floats = need;
+  }
+  h->base_T = T;
+  PG_CUDA_OK(cudaMemsetAsync(h->base, 0, need * sizeof(float), s));  // the tap GEMMs reduce-add into zero
+  EmbedLaunch e{};
+  e.tokens = tokens; e.n_tokens = n_tokens; e.positions = nullptr; e.win_start = nullptr;
+  e.P = 1; e.T = T; e.d = d; e.embed = h->embed; e.pos_table = h->pos;
+  e.lnb_gamma = D.emb_ln_before ? h->lnbg : nullptr; e.lnb_beta = D.emb_ln_before ? h->lnbb : nullptr;
+  e.token_dropout = D.token_dropout; e.mask_idx = 32; e.p_offset = 0; e.x = h->x; e.force_mask_scale = 1;
+  int rc;
+  { ProfScope ps(CAT_EMBED, s); rc = launch_embed(e, s); }
+  if (rc) return rc;
+  auto ln = [&](const float* g, const float* b) {
+    ProfScope ps(CAT_LN, s);
+    return launch_layernorm_f16(h->x, d, g, b, T, d, h->abuf, ldd, d, s, 1, 0.f);
+  };
+  auto tap = [&](int cat, const __half* a, int64_t lda, const __half* w, const float* bias, int N, int K, const float* dst) {
+    Lin t{a, lda, 0.f, w, nullptr, bias, T, N, K, 2};
+    t.resid = const_cast<float*>(dst);
+    return run_lin(h, cat, t, s);
+  };
+  auto unpack = [&](const __half* in, int64_t ld, int n, const float* dst) {
+    ProfScope ps(CAT_OTHER, s);
+    return launch_unpack_hilo(in, ld, n, T, n, const_cast<float*>(dst), s);
+  };
+  for (int l = 0; l < D.layers; ++l) {
+    const Layer& L = h->layers[l];
+    const BaseRows B = base_rows(h, l);
+    if ((rc = ln(L.ln1g, L.ln1b))) return rc;
+    if ((rc = unpack(h->abuf, ldd, d, B.a0))) return rc;
+    Lin q{h->abuf, ldd, 0.f, L.wqkv, nullptr, L.bqkv, T, 3 * d, d, 0};
+    q.out = h->qkv; q.out_fmt = 1;
+    if ((rc = run_lin(h, CAT_GEMM_QKV, q, s))) return rc;
+    if ((rc = tap(CAT_GEMM_QKV, h->abuf, ldd, L.wqkv, L.bqkv, 3 * d, d, B.bqkv))) return rc;
+    AttnLaunch a{};
+    a.qkv = h->qkv; a.ld = ldq; a.lo_off = 3 * d;
+    a.out = h->abuf; a.ldo = ldd; a.out_lo_off = d; a.out_fmt = 1;
+    a.B = 1; a.T = T; a.heads = D.heads; a.nseg = 3; a.causal = 0; a.alibi_slopes = nullptr;
+    { ProfScope ps(CAT_ATTN, s); rc = launch_attention_tc(a, s); }
+    if (rc) return rc;
+    if ((rc = unpack(h->abuf, ldd, d, B.o0))) return rc;
+    Lin o{h->abuf, ldd, 0.f, L.wo, nullptr, L.bo, T, d, d, 2};
+    o.resid = h->x;
+    if ((rc = run_lin(h, CAT_GEMM_OUT, o, s))) return rc;
+    if ((rc = tap(CAT_GEMM_OUT, h->abuf, ldd, L.wo, L.bo, d, d, B.bout))) return rc;
+    if ((rc = ln(L.ln2g, L.ln2b))) return rc;
+    if ((rc = unpack(h->abuf, ldd, d, B.b0))) return rc;
+    Lin f1{h->abuf, ldd, 0.f, L.w1, nullptr, L.b1, T, f, d, 1};
+    f1.out = h->fbuf; f1.out_fmt = 1;
+    if ((rc = run_lin(h, CAT_GEMM_FC1, f1, s))) return rc;
+    if ((rc = tap(CAT_GEMM_FC1, h->abuf, ldd, L.w1, L.b1, f, d, B.bfc1))) return rc;
+    if ((rc = unpack(h->fbuf, ldf, f, B.f0))) return rc;
+    Lin f2{h->fbuf, ldf, 0.f, L.w2, nullptr, L.b2, T, d, f, 2};
+    f2.resid = h->x;
+    if ((rc = run_lin(h, CAT_GEMM_FC2, f2, s))) return rc;
+    if ((rc = tap(CAT_GEMM_FC2, h->fbuf, ldf, L.w2, L.b2, d, f, B.bfc2))) return rc;
+  }
+  return PG_OK;
+}
+
+// One single-pass GEMM on difference rows: C = epi(base_pre[t] + A_delta * W_hi^T) [- base_post[t]].
+int run_lin_delta(pg_handle h, int cat, const __half* a, int64_t lda, const __half* w, int M, int N, int K, int epi, const float* base_pre,
+                  const float* base_post, int T, const int32_t* mask_pos, __half* out, int64_t ldo, int out_fmt, float* resid,
+                  cudaStream_t s) {
+  GemmLaunch g{};
+  g.a = a; g.lda = lda; g.w = w; g.ldw = static_cast<int64_t>(K) * h->np; g.bias = nullptr;  // W: the hi plane of the hi/lo rows
+  g.M = M; g.N = N; g.K = K; g.nseg = 1; g.epi = epi;
+  g.base_pre = base_pre; g.base_post = base_post; g.base_T = T; g.mask_pos = mask_pos;
+  if (epi == 2) {
+    g.resid = resid; g.ldr = N;
+  } else {
+    g.out = out; g.ldo = ldo; g.out_fmt = out_fmt; g.out_lo_off = out_fmt ? N : 0;
+  }
+  ProfScope ps(cat, s);
+  return launch_gemm(g, s);
+}
+
+// forward_rows in delta-operand mode (single window: every copy sees tokens [0, T); emit_rows[b] = the masked token of copy b).
+int forward_rows_delta(pg_handle h, const int32_t* tokens, int n_tokens, const int32_t* positions, const int32_t* win_start,
+                       int p_offset, int Bc, int T, cudaStream_t s, const int32_t* emit_rows) {
+  const pg_model_desc& D = h->desc;
+  const int d = D.embed_dim, f = D.ffn_dim, np = h->np;
+  const int64_t ldd = static_cast<int64_t>(d) * np, ldf = static_cast<int64_t>(f) * np, ldq = static_cast<int64_t>(3 * d) * np;
+  const int rows = Bc * T;
+  EmbedLaunch e{};
+  e.tokens = tokens; e.n_tokens = n_tokens; e.positions = positions; e.win_start = win_start;
+  e.P = Bc; e.T = T; e.d = d; e.embed = h->embed; e.pos_table = h->pos;
+  e.lnb_gamma = D.emb_ln_before ? h->lnbg : nullptr; e.lnb_beta = D.emb_ln_before ? h->lnbb : nullptr;
+  e.token_dropout = D.token_dropout; e.mask_idx = 32; e.p_offset = p_offset; e.x = h->x;
+  int rc;
+  { ProfScope ps(CAT_EMBED, s); rc = launch_embed(e, s); }
+  if (rc) return rc;
+  { ProfScope ps(CAT_OTHER, s); rc = launch_gather_rows(h->x, emit_rows, Bc, T, d, h->xc, s); }  // xc = the masked rows, kept exact
+  if (rc) return rc;
+  auto ln_delta = [&](const float* g, const float* b, const float* base) {   // all rows: LN(x) - base[t] -> abuf (fp16, pitch ldd)
+    ProfScope ps(CAT_LN, s);
+    return launch_layernorm_f16(h->x, d, g, b, rows, d, h->abuf, ldd, 0, s, 0, 0.f, 0, 0, base, T);
+  };
+  auto ln_compact = [&](const float* g, const float* b) {                     // masked rows: LN(xc) -> cabuf (hi | lo)
+    ProfScope ps(CAT_LN, s);
+    return launch_layernorm_f16(h->xc, d, g, b, Bc, d, h->cabuf, ldd, d, s, 1, 0.f);
+  };
+  auto put_back = [&]() {                                                    // x[masked rows] <- xc
+    ProfScope ps(CAT_OTHER, s);
+    return launch_scatter_rows(h->xc, static_cast<int64_t>(d) * 4, h->x, static_cast<int64_t>(d) * 4, emit_rows, Bc, T, d * 4, s);
+  };
+  for (int l = 0; l < D.layers; ++l) {
+    const Layer& L = h->layers[l];
+    const BaseRows B = base_rows(h, l);
+    // q/k/v: all rows from the difference, the masked rows exactly
+    if ((rc = ln_delta(L.ln1g, L.ln1b, B.a0))) return rc;
+    if ((rc = run_lin_delta(h, CAT_GEMM_QKV, h->abuf, ldd, L.wqkv, rows, 3 * d, d, 0, B.bqkv, nullptr, T, nullptr, h->qkv, ldq, 1, nullptr, s)))
+      return rc;
+    if ((rc = ln_compact(L.ln1g, L.ln1b))) return rc;
+    Lin cq{h->cabuf, ldd, 0.f, L.wqkv, nullptr, L.bqkv, Bc, 3 * d, d, 0};
+    cq.out = h->cq; cq.out_fmt = 1;
+    if ((rc = run_lin(h, CAT_GEMM_QKV, cq, s))) return rc;
+    { ProfScope ps(CAT_OTHER, s);
+      rc = launch_scatter_rows(h->cq, ldq * 2, h->qkv, ldq * 2, emit_rows, Bc, T, static_cast<int>(ldq * 2), s); }
+    if (rc) return rc;
+    if (l == D.layers - 1) {
+      // exact pruning of the final layer, as in forward_rows: one query row per copy from here on, x3 GEMMs on full values
+      { ProfScope ps(CAT_ATTN, s, 2);
+        rc = launch_attn_single_query(h->qkv, ldq, 3 * d, emit_rows, Bc, T, D.heads, h->cabuf, ldd, d, s, 1, 0.f); }
+      if (rc) return rc;
+      Lin o{h->cabuf, ldd, 0.f, L.wo, nullptr, L.bo, Bc, d, d, 2};
+      o.resid = h->xc;
+      if ((rc = run_lin(h, CAT_GEMM_OUT, o, s))) return rc;
+      if ((rc = ln_compact(L.ln2g, L.ln2b))) return rc;
+      Lin f1{h->cabuf, ldd, 0.f, L.w1, nullptr, L.b1, Bc, f, d, 1};
+      f1.out = h->cfbuf; f1.out_fmt = 1;
+      if ((rc = run_lin(h, CAT_GEMM_FC1, f1, s))) return rc;
+      Lin f2{h->cfbuf, ldf, 0.f, L.w2, nullptr, L.b2, Bc, d, f, 2};
+      f2.resid = h->xc;
+      return run_lin(h, CAT_GEMM_FC2, f2, s);
+    }
+    // attention on full-value q/k/v; output as difference rows, the masked rows' exact output to cabuf
+    AttnLaunch a{};
+    a.qkv = h->qkv; a.ld = ldq; a.lo_off = 3 * d;
+    a.out = h->abuf; a.ldo = ldd; a.out_lo_off = 0; a.out_fmt = 0;
+    a.B = Bc; a.T = T; a.heads = D.heads; a.nseg = 3; a.causal = 0; a.alibi_slopes = nullptr;
+    a.base_o = B.o0; a.mask_pos = emit_rows; a.cout = h->cabuf; a.ldc = ldd; a.c_lo_off = d;
+    { ProfScope ps(CAT_ATTN, s); rc = launch_attention_tc(a, s); }
+    if (rc) return rc;
+    if ((rc = run_lin_delta(h, CAT_GEMM_OUT, h->abuf, ldd, L.wo, rows, d, d, 2, B.bout, nullptr, T, emit_rows, nullptr, 0, 0, h->x, s))) return rc;
+    Lin o{h->cabuf, ldd, 0.f, L.wo, nullptr, L.bo, Bc, d, d, 2};
+    o.resid = h->xc;
+    if ((rc = run_lin(h, CAT_GEMM_OUT, o, s))) return rc;
+    if ((rc = put_back())) return rc;
+    // MLP
+    if ((rc = ln_delta(L.ln2g, L.ln2b, B.b0))) return rc;
+    if ((rc = run_lin_delta(h, CAT_GEMM_FC1, h->abuf, ldd, L.w1, rows, f, d, 1, B.bfc1, B.f0, T, nullptr, h->fbuf, ldf, 0, nullptr, s))) return rc;
+    if ((rc = ln_compact(L.ln2g, L.ln2b))) return rc;
+    Lin f1{h->cabuf, ldd, 0.f, L.w1, nullptr, L.b1, Bc, f, d, 1};
+    f1.out = h->cfbuf; f1.out_fmt = 1;
+    if ((rc = run_lin(h, CAT_GEMM_FC1, f1, s))) return rc;
+    if ((rc = run_lin_delta(h, CAT_GEMM_FC2, h->fbuf, ldf, L.w2, rows, d, f, 2, B.bfc2, nullptr, T, emit_rows, nullptr, 0, 0, h->x, s))) return rc;
+    Lin f2{h->cfbuf, ldf, 0.f, L.w2, nullptr, L.b2, Bc, d, f, 2};
+    f2.resid = h->xc;
+    if ((rc = run_lin(h, CAT_GEMM_FC2, f2, s))) return rc;
+    if ((rc = put_back())) return rc;
   }
   return PG_OK;
 }
@@ -633,8 +838,10 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
   if (D.arch != PG_ARCH_ESM1B && D.arch != PG_ARCH_ESM2 && D.arch != PG_ARCH_TRANCEPTION && D.arch != PG_ARCH_MSA)
     return set_error(PG_ERR_UNSUPPORTED, "pg_create: unknown arch");
   if (D.arch == PG_ARCH_TRANCEPTION && D.heads % 4) return set_error(PG_ERR_UNSUPPORTED, "pg_create: Tranception needs heads % 4 == 0 (model_pytorch.py:129-131)");
-  if (D.precision != PG_PREC_F16 && D.precision != PG_PREC_F16X3 && D.precision != PG_PREC_F16F8)
+  if (D.precision != PG_PREC_F16 && D.precision != PG_PREC_F16X3 && D.precision != PG_PREC_F16F8 && D.precision != PG_PREC_F16D)
     return set_error(PG_ERR_ARG, "pg_create: unknown precision");
+  if (D.precision == PG_PREC_F16D && D.arch != PG_ARCH_ESM1B)
+    return set_error(PG_ERR_UNSUPPORTED, "pg_create: PG_PREC_F16D (delta operands) is built for the ESM-1b / ESM-1v masked-marginal path");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return set_error(PG_ERR_CUDA, "pg_create: no CUDA device (the B200 path has no CPU fallback)");
   if (D.device < 0 || D.device >= ndev) return set_error(PG_ERR_ARG, "pg_create: bad device ordinal");
@@ -645,7 +852,8 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
   pg_handle h = new pg_handle_s();
   h->desc = D;
   h->np = (D.precision == PG_PREC_F16) ? 1 : 2;
-  h->nseg = (D.precision == PG_PREC_F16) ? 1 : (D.precision == PG_PREC_F16X3 ? 3 : 2);
+  h->nseg = (D.precision == PG_PREC_F16) ? 1 : (D.precision == PG_PREC_F16F8 ? 2 : 3);  // F16D: the fp16 hi/lo x3 plumbing + delta GEMMs
+  h->delta = (D.precision == PG_PREC_F16D);
   h->max_rows = D.max_rows > 0 ? D.max_rows : 131072;
   h->head_cap = 8192;
   const int d = D.embed_dim, f = D.ffn_dim, np = h->np;
@@ -689,6 +897,7 @@ int pg_create(const pg_model_desc* desc, pg_handle* out) {
   A(&h->xc, static_cast<size_t>(h->head_cap) * d);
   A(&h->cabuf, static_cast<size_t>(h->head_cap) * d * np);
   A(&h->cfbuf, static_cast<size_t>(h->head_cap) * f * np);
+  if (h->delta) A(&h->cq, static_cast<size_t>(h->head_cap) * 3 * d * np);
   if (rc) {
     std::string m = h->err;
     pg_destroy(h);
@@ -704,6 +913,7 @@ int pg_destroy(pg_handle h) {
   cudaSetDevice(h->desc.device);
   for (void* p : h->allocs) cudaFree(p);
   if (h->tied_ws) cudaFree(h->tied_ws);
+  if (h->base) cudaFree(h->base);
   delete h;
   return PG_OK;
 }
@@ -891,10 +1101,17 @@ int pg_masked_marginals(pg_handle h, const int32_t* tokens, int32_t n_tokens, co
   long long per = h->max_rows / T;
   if (per > h->head_cap) per = h->head_cap;
   per = balanced_per(P, per);
+  // delta-operand mode needs one shared window (every copy sees all n_tokens tokens) and the masked row as the emitted row
+  const bool delta = h->delta && T == n_tokens && out_row == nullptr && P > 0;
+  if (delta) {
+    int rc = forward_base(h, tokens, n_tokens, T, s);
+    if (rc) return fail(h, rc, tls_error());
+  }
   for (int p0 = 0; p0 < P; p0 += static_cast<int>(per)) {
     const int Bc = (P - p0) < per ? (P - p0) : static_cast<int>(per);
     row_select_kernel<<<(Bc + 255) / 256, 256, 0, s>>>(positions, win_start, out_row, p0, Bc, h->row_sel);
-    int rc = forward_rows(h, tokens, n_tokens, positions, win_start, p0, Bc, T, s, h->row_sel);
+    int rc = delta ? forward_rows_delta(h, tokens, n_tokens, positions, win_start, p0, Bc, T, s, h->row_sel)
+                   : forward_rows(h, tokens, n_tokens, positions, win_start, p0, Bc, T, s, h->row_sel);
     if (rc) return fail(h, rc, tls_error());
     ProfScope ps(CAT_HEAD, s, 4);
     HeadLaunch hl = head_args(h, T);
@@ -1113,6 +1330,7 @@ int pg_gemm(const pg_gemm_args* a, pg_stream stream) {
   g.a_scale = a->a_scale; g.w_inv = a->w_inv; g.out_scale = a->out_scale;
   g.out_fmt = a->out_fmt ? a->out_fmt : (a->out_lo_off > 0 ? 1 : 0);
   g.grp_rows_a = a->grp_rows_a; g.grp_rows_b = a->grp_rows_b;
+  g.base_pre = a->base_pre; g.base_post = a->base_post; g.base_T = a->base_T; g.mask_pos = a->mask_pos;
   ProfScope ps(CAT_OTHER, static_cast<cudaStream_t>(stream));
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
@@ -1154,6 +1372,8 @@ int pg_attention(const pg_attn_args* a, pg_stream stream) {
   l.out = static_cast<__half*>(a->out); l.ldo = a->ldo; l.out_lo_off = a->out_lo_off;
   l.B = a->B; l.T = a->T; l.heads = a->heads; l.nseg = a->nseg; l.causal = a->causal; l.alibi_slopes = a->alibi_slopes;
   l.out_fmt = a->out_fmt ? a->out_fmt : -1; l.out_scale = a->out_scale;
+  l.base_o = a->base_o; l.mask_pos = a->mask_pos; l.cout = static_cast<__half*>(a->cout); l.ldc = a->ldc; l.c_lo_off = a->c_lo_off;
+  if ((l.base_o || l.mask_pos) && a->impl != 0) return set_error(PG_ERR_UNSUPPORTED, "pg_attention: the delta-operand form needs impl 0");
   ProfScope ps(CAT_OTHER, static_cast<cudaStream_t>(stream));
   if (a->impl == 0) return launch_attention_tc(l, static_cast<cudaStream_t>(stream));   // the model's kernel (tcgen05)
   if (a->impl != 1) return set_error(PG_ERR_ARG, "pg_attention: impl must be 0 (the model's tcgen05 kernel) or 1 (mma.sync cross-check)");

@@ -57,6 +57,8 @@ struct Attn4Params {
   const float* alibi_slopes;
   int out_fmt; float out_scale;  // common.h operand formats: 1 = fp16 lo plane, 2 = e4m3 [lo8 | hi8] planes for the out_proj GEMM
   int perm_C;                    // > 0: sequence b is column (b / perm_C, b % perm_C) of an alignment; output rows go to (., r, c) order
+  // delta-operand mode (common.h AttnLaunch): out = attention - base_o[row]; full-precision hi / lo copy of row mask_pos[b] to cout[b]
+  const float* base_o; const int* mask_pos; __half* cout; long long ldc; long long c_lo_off;
 };
 
 __device__ __forceinline__ float ex2a3(float x) {
@@ -389,6 +391,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
       __half* orow = p.out + orow_idx * p.ldo + h * 64;
       uint8_t* f8 = reinterpret_cast<uint8_t*>(p.out + orow_idx * p.ldo + p.out_lo_off) + h * 64;
       const float sh = p.out_scale, sl = p.out_scale * 2048.f;
+      const bool crow = wr && p.mask_pos != nullptr && qidx == __ldg(p.mask_pos + b);  // this row's exact value also goes to cout[b]
+      const float* brow = p.base_o != nullptr ? p.base_o + static_cast<long long>(qidx) * p.d + h * 64 : nullptr;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {  // 32 head-dim columns at a time (register budget: 128 per thread at two CTAs per SM)
         uint32_t o[32];
@@ -408,6 +412,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
           for (int u = 0; u < 16; ++u) {
             float x0, x1;
             f2_unpack(f2_mul(f2_pack(__uint_as_float(o[2 * u]), __uint_as_float(o[2 * u + 1])), f2_pack(rl, rl)), x0, x1);
+            if (crow) {  // rare (one row per sequence and head): fp16 hi / lo pair of the full value
+              __half* cr = p.cout + static_cast<long long>(b) * p.ldc + h * 64 + c * 32 + 2 * u;
+              const uint32_t ch = cvt2h(x0, x1);
+              const float2 cf = __half22float2(*reinterpret_cast<const __half2*>(&ch));
+              *reinterpret_cast<uint32_t*>(cr) = ch;
+              *reinterpret_cast<uint32_t*>(cr + p.c_lo_off) = cvt2h(x0 - cf.x, x1 - cf.y);
+            }
+            if (brow != nullptr) {
+              const float2 bq = __ldg(reinterpret_cast<const float2*>(brow + c * 32 + 2 * u));
+              x0 -= bq.x;
+              x1 -= bq.y;
+            }
             hi[u] = cvt2h(x0, x1);
             const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi[u]));
             float q0, q1;
@@ -474,6 +490,9 @@ int launch_attention_tc4(const AttnLaunch& a, cudaStream_t s) {
   p.out_fmt = a.out_fmt < 0 ? (a.out_lo_off > 0 ? 1 : 0) : a.out_fmt;
   p.out_scale = a.out_scale;
   p.perm_C = a.perm_C;
+  p.base_o = a.base_o; p.mask_pos = a.mask_pos; p.cout = a.cout; p.ldc = a.ldc; p.c_lo_off = a.c_lo_off;
+  if ((a.base_o || a.mask_pos) && (a.prefix || a.perm_C || (a.mask_pos && (!a.cout || a.ldc % 2 || a.c_lo_off % 2 || a.c_lo_off <= 0))))
+    return set_error(PG_ERR_ARG, "attention_tc4: delta-operand mode needs plain sequences and, with mask_pos, a compact hi/lo output");
   if (a.perm_C < 0 || (a.perm_C > 0 && (a.prefix || a.B % a.perm_C))) return set_error(PG_ERR_ARG, "attention_tc4: bad column-attention arguments");
   if (p.out_fmt > 2 || (p.out_fmt >= 1 && a.out_lo_off <= 0) || (p.out_fmt == 2 && !(a.out_scale > 0.f)))
     return set_error(PG_ERR_ARG, "attention_tc4: bad output format");

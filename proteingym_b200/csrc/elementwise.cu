@@ -40,7 +40,8 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 template <int MAXV>  // float4 vectors per lane; d <= MAXV*128
 __global__ void layernorm_f16_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, int rows, int d, __half* __restrict__ out,
-                                     long long ldo, long long lo_off, int fmt, float scale, int perm_R, int perm_C) {
+                                     long long ldo, long long lo_off, int fmt, float scale, int perm_R, int perm_C,
+                                     const float* __restrict__ base, int base_T) {
   const int warps_per_block = blockDim.x >> 5;
   const long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -84,6 +85,10 @@ __global__ void layernorm_f16_kernel(const float* __restrict__ x, long long ldx,
       const float4 b = reinterpret_cast<const float4*>(beta)[idx];
       float y[4] = {(v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
                     (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w};
+      if (base) {  // delta-operand mode: the difference to the shared base row, formed in fp32 before the fp16 rounding
+        const float4 q = reinterpret_cast<const float4*>(base + (row % base_T) * static_cast<long long>(d))[idx];
+        y[0] -= q.x; y[1] -= q.y; y[2] -= q.z; y[3] -= q.w;
+      }
       __half h[4], l[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) split_hi_lo(y[j], h[j], l[j]);
@@ -117,7 +122,7 @@ __global__ void embed_kernel(EmbedLaunch e) {
   const bool masked = (gi == mpos);
   const int tok = masked ? e.mask_idx : e.tokens[gi < e.n_tokens ? gi : e.n_tokens - 1];
   // mask_ratio_observed = (#mask tokens)/T ; WT sequences never contain <mask> themselves
-  const bool has_mask = (mpos >= ws && mpos < ws + e.T);
+  const bool has_mask = (mpos >= ws && mpos < ws + e.T) || e.force_mask_scale;
   float scale = 1.f;
   if (e.token_dropout) {
     const float ratio = has_mask ? 1.0f / static_cast<float>(e.T) : 0.f;
@@ -367,19 +372,59 @@ int launch_gather_rows(const float* x, const int32_t* row_sel, int B, int T, int
   return PG_OK;
 }
 
+static __global__ void unpack_hilo_kernel(const __half* __restrict__ in, long long ld, long long lo_off, long long total, int n,
+                                   float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long r = i / n;
+  const int c = static_cast<int>(i - r * n);
+  const __half* row = in + r * ld;
+  out[i] = __half2float(row[c]) + (lo_off > 0 ? __half2float(row[lo_off + c]) : 0.f);
+}
+
+static __global__ void scatter_rows_kernel(const uint8_t* __restrict__ src, long long src_pitch, uint8_t* __restrict__ dst, long long dst_pitch,
+                                    const int32_t* __restrict__ row_sel, int T, int row_bytes) {
+  const int b = blockIdx.x;
+  const uint4* s = reinterpret_cast<const uint4*>(src + b * src_pitch);
+  uint4* d = reinterpret_cast<uint4*>(dst + (static_cast<long long>(b) * T + row_sel[b]) * dst_pitch);
+  for (int i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) d[i] = s[i];
+}
+
+int launch_unpack_hilo(const __half* in, int64_t ld, int64_t lo_off, int rows, int n, float* out, cudaStream_t s) {
+  const long long total = static_cast<long long>(rows) * n;
+  if (total <= 0) return PG_OK;
+  unpack_hilo_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, ld, lo_off, total, n, out);
+  PG_CUDA_OK(cudaGetLastError());
+  return PG_OK;
+}
+
+int launch_scatter_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes, const int32_t* row_sel, int B, int T,
+                        int row_bytes, cudaStream_t s) {
+  if (B <= 0) return PG_OK;
+  if (row_bytes % 16 || src_pitch_bytes % 16 || dst_pitch_bytes % 16 || (reinterpret_cast<uintptr_t>(src) & 15) ||
+      (reinterpret_cast<uintptr_t>(dst) & 15))
+    return set_error(PG_ERR_ARG, "scatter_rows: rows must be 16-byte aligned multiples of 16 bytes");
+  scatter_rows_kernel<<<B, 256, 0, s>>>(static_cast<const uint8_t*>(src), src_pitch_bytes, static_cast<uint8_t*>(dst), dst_pitch_bytes,
+                                        row_sel, T, row_bytes);
+  PG_CUDA_OK(cudaGetLastError());
+  return PG_OK;
+}
+
 int launch_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int rows, int d, __half* out,
-                         int64_t ldo, int64_t lo_off, cudaStream_t s, int fmt, float scale, int perm_R, int perm_C) {
+                         int64_t ldo, int64_t lo_off, cudaStream_t s, int fmt, float scale, int perm_R, int perm_C, const float* base,
+                         int base_T) {
   if (rows <= 0) return PG_OK;
+  if (base && (base_T <= 0 || perm_C > 0)) return set_error(PG_ERR_ARG, "layernorm: a base needs base_T > 0 and no row permutation");
   if (perm_C > 0 && (perm_R <= 0 || rows % (perm_R * perm_C))) return set_error(PG_ERR_ARG, "layernorm: rows must be whole [R, C] alignments");
   if (d % 4 || ldx % 4 || ldo % 4 || lo_off % 4) return set_error(PG_ERR_ARG, "layernorm: d and pitches must be multiples of 4");
   if (fmt < 0) fmt = lo_off > 0 ? 1 : 0;
   if (fmt > 2 || (fmt >= 1 && lo_off <= 0) || (fmt == 2 && !(scale > 0.f))) return set_error(PG_ERR_ARG, "layernorm: bad output format");
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
-  if (d <= 128 * 4) layernorm_f16_kernel<4><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale, perm_R, perm_C);
-  else if (d <= 128 * 10) layernorm_f16_kernel<10><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale, perm_R, perm_C);
-  else if (d <= 128 * 20) layernorm_f16_kernel<20><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale, perm_R, perm_C);
-  else if (d <= 128 * 40) layernorm_f16_kernel<40><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale, perm_R, perm_C);
+  if (d <= 128 * 4) layernorm_f16_kernel<4><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale, perm_R, perm_C, base, base_T);
+  else if (d <= 128 * 10) layernorm_f16_kernel<10><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale, perm_R, perm_C, base, base_T);
+  else if (d <= 128 * 20) layernorm_f16_kernel<20><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale, perm_R, perm_C, base, base_T);
+  else if (d <= 128 * 40) layernorm_f16_kernel<40><<<grid, wpb * 32, 0, s>>>(x, ldx, gamma, beta, rows, d, out, ldo, lo_off, fmt, scale, perm_R, perm_C, base, base_T);
   else return set_error(PG_ERR_UNSUPPORTED, "layernorm: d > 5120");
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;

@@ -83,6 +83,8 @@ struct GemmKParams {
   const float* rot_cos; const float* rot_sin; int rot_T; int rot_dim;
   int tiles_m, tiles_n;
   int prefetch;           // k-blocks of L2 look-ahead for the A operand (0 = off)
+  // delta-operand mode (common.h GemmLaunch): shared base rows added before / subtracted after the activation, masked rows skipped
+  const float* base_pre; const float* base_post; int base_T; const int* mask_pos;
   int grp_rows_a, grp_rows_b;  // grouped (block-diagonal) mode: A rows [g*grp_rows_a, (g+1)*grp_rows_a) pair with W rows g*grp_rows_b + n
 };
 
@@ -206,6 +208,18 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
       for (int j = 0; j < 64; ++j) acc[O + j] += (gcol + j < p.N) ? __ldg(p.bias + gcol + j) : 0.f;
     }
   }
+  const float* brow = nullptr;  // delta-operand mode: this row's shared base row (row % base_T), columns [gcol, gcol + 64)
+  if (p.base_pre != nullptr) {
+    const long long boff = (c.row % p.base_T) * static_cast<long long>(p.N) + gcol;
+    brow = p.base_post != nullptr ? p.base_post + boff : nullptr;
+    const float4* b4 = reinterpret_cast<const float4*>(p.base_pre + boff);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 x = __ldg(b4 + j);
+      f2_unpack(f2_add(f2_pack(acc[O + 4 * j], acc[O + 4 * j + 1]), f2_pack(x.x, x.y)), acc[O + 4 * j], acc[O + 4 * j + 1]);
+      f2_unpack(f2_add(f2_pack(acc[O + 4 * j + 2], acc[O + 4 * j + 3]), f2_pack(x.z, x.w)), acc[O + 4 * j + 2], acc[O + 4 * j + 3]);
+    }
+  }
   if (EPI == 1) {
 #pragma unroll
     for (int j = 0; j < 64; j += 2) gelu_erf2(acc[O + j], acc[O + j + 1]);
@@ -227,6 +241,22 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
       const float a = acc[O + j], b = acc[O + 32 + j];
       acc[O + j] = a * co - b * s;
       acc[O + 32 + j] = b * co + a * s;
+    }
+  }
+  if (brow != nullptr) {  // the output is again a difference to the base row's activated value
+    const float4* b4 = reinterpret_cast<const float4*>(brow);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 x = __ldg(b4 + j);
+      f2_unpack(f2_sub(f2_pack(acc[O + 4 * j], acc[O + 4 * j + 1]), f2_pack(x.x, x.y)), acc[O + 4 * j], acc[O + 4 * j + 1]);
+      f2_unpack(f2_sub(f2_pack(acc[O + 4 * j + 2], acc[O + 4 * j + 3]), f2_pack(x.z, x.w)), acc[O + 4 * j + 2], acc[O + 4 * j + 3]);
+    }
+  }
+  if (EPI == 2 && p.mask_pos != nullptr && c.row_ok) {  // the masked row of each copy is updated by the compact exact path instead
+    const long long copy = c.row / p.base_T;
+    if (c.row - copy * p.base_T == __ldg(p.mask_pos + copy)) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) acc[O + j] = 0.f;
     }
   }
   uint8_t* stg = c.stg;
@@ -625,6 +655,9 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   if (g.epi == 3 && (!g.rot_cos || !g.rot_sin || g.rot_T <= 0 || g.rot_dim % 64)) return set_error(PG_ERR_ARG, "gemm: bad rotary args");
   if (g.nseg == 2 && (!g.w_inv || !(g.a_scale > 0.f))) return set_error(PG_ERR_ARG, "gemm: nseg 2 needs w_inv[N] and a_scale > 0");
   if (g.out_fmt < 0 || g.out_fmt > 2) return set_error(PG_ERR_ARG, "gemm: bad out_fmt");
+  if ((g.base_pre || g.base_post || g.mask_pos) && (!g.base_pre || g.base_T <= 0 || g.N % 64 || g.M % g.base_T || g.grp_rows_a ||
+                                                       (g.mask_pos && g.epi != 2) || (g.base_post && g.epi == 2)))
+    return set_error(PG_ERR_ARG, "gemm: delta-operand mode needs base_pre, base_T > 0 dividing M, N % 64 == 0, no groups; mask_pos only with the residual epilogue");
   if (g.epi != 2 && g.out_fmt == 2 && (g.N % 64 || !(g.out_scale > 0.f)))
     return set_error(PG_ERR_ARG, "gemm: out_fmt 2 needs N % 64 == 0 and out_scale > 0");
   if (g.epi != 2 && g.out_fmt >= 1 && g.out_lo_off <= 0) return set_error(PG_ERR_ARG, "gemm: out_fmt 1/2 need out_lo_off > 0");
@@ -713,6 +746,7 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   p.tiles_n = (g.N + BN - 1) / BN;
   p.prefetch = grouped ? 0 : gemm_prefetch();
   p.grp_rows_a = g.grp_rows_a; p.grp_rows_b = g.grp_rows_b;
+  p.base_pre = g.base_pre; p.base_post = g.base_post; p.base_T = g.base_T; p.mask_pos = g.mask_pos;
   const int ntiles = p.tiles_m * p.tiles_n;
   if (!cta2) {
     const int grid = ntiles < num_sms() ? ntiles : num_sms();

@@ -19,7 +19,7 @@ from .checkpoint import EsmConfig, rotary_tables
 from .mutants import parse_mutants
 from .windows import optimal_window_starts
 
-PRECISIONS = {"f16": _lib.PG_PREC_F16, "f16x3": _lib.PG_PREC_F16X3, "f16f8": _lib.PG_PREC_F16F8}
+PRECISIONS = {"f16": _lib.PG_PREC_F16, "f16x3": _lib.PG_PREC_F16X3, "f16f8": _lib.PG_PREC_F16F8, "f16d": _lib.PG_PREC_F16D}
 
 
 def choose_precision(config: EsmConfig, mutants=None, strategy: str = "masked-marginals") -> str:
