@@ -76,7 +76,7 @@ __device__ __forceinline__ uint32_t cvt2h(float lo_elem, float hi_elem) {
 // exponent's FFMA2, and exponent + row sum + fp16 hi / lo packing of a 32-column chunk in ONE basic block so that the packing of
 // earlier pairs issues between the MUFU.EX2 instructions: ~5 instead of ~9 issue slots per score. Same-box A/B against the scalar
 // form (profiles/ab_r02_m_*.txt, profiles/ncu_r02_attn_sv3_summary.txt): 268 vs 254 TFLOP/s hi/lo, 443 vs 400 single pass.
-template <int NP>
+template <int NP, int DELTA>
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tm,
                                                                   const __grid_constant__ CUtensorMap tmP, const Attn4Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -391,8 +391,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
       __half* orow = p.out + orow_idx * p.ldo + h * 64;
       uint8_t* f8 = reinterpret_cast<uint8_t*>(p.out + orow_idx * p.ldo + p.out_lo_off) + h * 64;
       const float sh = p.out_scale, sl = p.out_scale * 2048.f;
-      const bool crow = wr && p.mask_pos != nullptr && qidx == __ldg(p.mask_pos + b);  // this row's exact value also goes to cout[b]
-      const float* brow = p.base_o != nullptr ? p.base_o + static_cast<long long>(qidx) * p.d + h * 64 : nullptr;
+      // delta-operand mode (DELTA): this row's exact value also goes to cout[b] when it is the masked row; base row to subtract
+      const bool crow = DELTA && wr && p.mask_pos != nullptr && qidx == __ldg(p.mask_pos + b);
+      const float* brow = (DELTA && p.base_o != nullptr) ? p.base_o + static_cast<long long>(qidx) * p.d + h * 64 : nullptr;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {  // 32 head-dim columns at a time (register budget: 128 per thread at two CTAs per SM)
         uint32_t o[32];
@@ -412,14 +413,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
           for (int u = 0; u < 16; ++u) {
             float x0, x1;
             f2_unpack(f2_mul(f2_pack(__uint_as_float(o[2 * u]), __uint_as_float(o[2 * u + 1])), f2_pack(rl, rl)), x0, x1);
-            if (crow) {  // rare (one row per sequence and head): fp16 hi / lo pair of the full value
+            if (DELTA && crow) {  // rare (one row per sequence and head): fp16 hi / lo pair of the full value
               __half* cr = p.cout + static_cast<long long>(b) * p.ldc + h * 64 + c * 32 + 2 * u;
               const uint32_t ch = cvt2h(x0, x1);
               const float2 cf = __half22float2(*reinterpret_cast<const __half2*>(&ch));
               *reinterpret_cast<uint32_t*>(cr) = ch;
               *reinterpret_cast<uint32_t*>(cr + p.c_lo_off) = cvt2h(x0 - cf.x, x1 - cf.y);
             }
-            if (brow != nullptr) {
+            if (DELTA && brow != nullptr) {
               const float2 bq = __ldg(reinterpret_cast<const float2*>(brow + c * 32 + 2 * u));
               x0 -= bq.x;
               x1 -= bq.y;
@@ -516,12 +517,16 @@ int launch_attention_tc4(const AttnLaunch& a, cudaStream_t s) {
   PG_CUDA_OK(cudaGetDevice(&dev));
   static bool attr_set[64] = {};
   if (dev < 64 && !attr_set[dev]) {
-    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<1>::TOTAL));
-    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<2>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<1>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<2>::TOTAL));
+    PG_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem4<2>::TOTAL));
     attr_set[dev] = true;
   }
-  if (np == 1) attn_tc4_kernel<1><<<grid, ATT_THREADS, Smem4<1>::TOTAL, s>>>(tmQ, tm, tmP, p);
-  else attn_tc4_kernel<2><<<grid, ATT_THREADS, Smem4<2>::TOTAL, s>>>(tmQ, tm, tmP, p);
+  const bool delta = a.base_o != nullptr || a.mask_pos != nullptr;
+  if (delta && np != 2) return set_error(PG_ERR_UNSUPPORTED, "attention_tc4: the delta-operand form runs on fp16 hi/lo operands (nseg 3)");
+  if (delta) attn_tc4_kernel<2, 1><<<grid, ATT_THREADS, Smem4<2>::TOTAL, s>>>(tmQ, tm, tmP, p);
+  else if (np == 1) attn_tc4_kernel<1, 0><<<grid, ATT_THREADS, Smem4<1>::TOTAL, s>>>(tmQ, tm, tmP, p);
+  else attn_tc4_kernel<2, 0><<<grid, ATT_THREADS, Smem4<2>::TOTAL, s>>>(tmQ, tm, tmP, p);
   PG_CUDA_OK(cudaGetLastError());
   return PG_OK;
 }

@@ -49,12 +49,15 @@ __global__ void layernorm_f16_kernel(const float* __restrict__ x, long long ldx,
   const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
   const int nv = d >> 2;
   float4 v[MAXV];
+  float4 q[MAXV];  // delta-operand mode: the shared base row, requested together with x so that its latency hides behind the reductions
+  const float4* qr = base ? reinterpret_cast<const float4*>(base + (row % base_T) * static_cast<long long>(d)) : nullptr;
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + i * 32;
     if (idx < nv) {
       v[i] = xr[idx];
+      if (qr) q[i] = __ldg(qr + idx);
       s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
   }
@@ -85,9 +88,8 @@ __global__ void layernorm_f16_kernel(const float* __restrict__ x, long long ldx,
       const float4 b = reinterpret_cast<const float4*>(beta)[idx];
       float y[4] = {(v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
                     (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w};
-      if (base) {  // delta-operand mode: the difference to the shared base row, formed in fp32 before the fp16 rounding
-        const float4 q = reinterpret_cast<const float4*>(base + (row % base_T) * static_cast<long long>(d))[idx];
-        y[0] -= q.x; y[1] -= q.y; y[2] -= q.z; y[3] -= q.w;
+      if (qr) {  // delta-operand mode: the difference to the shared base row, formed in fp32 before the fp16 rounding
+        y[0] -= q[i].x; y[1] -= q[i].y; y[2] -= q[i].z; y[3] -= q[i].w;
       }
       __half h[4], l[4];
 #pragma unroll

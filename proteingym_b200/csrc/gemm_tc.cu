@@ -189,7 +189,7 @@ struct EpiCtx {
 };
 
 // Bias, activation and store of one 64-column group (G = 0, 1) of this thread's 128 accumulated columns.
-template <int EPI, int G>
+template <int EPI, int G, int DELTA>
 __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKParams& p, const EpiCtx& c) {
   constexpr int O = G * 64;
   const int gcol = c.gcol + O;
@@ -208,19 +208,26 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
       for (int j = 0; j < 64; ++j) acc[O + j] += (gcol + j < p.N) ? __ldg(p.bias + gcol + j) : 0.f;
     }
   }
-  const float* brow = nullptr;  // delta-operand mode: this row's shared base row (row % base_T), columns [gcol, gcol + 64)
-  if (p.base_pre != nullptr) {
-    const long long boff = (c.row % p.base_T) * static_cast<long long>(p.N) + gcol;
-    brow = p.base_post != nullptr ? p.base_post + boff : nullptr;
-    const float4* b4 = reinterpret_cast<const float4*>(p.base_pre + boff);
+  if (EPI == 1 && DELTA && p.base_post != nullptr) {
+    // delta-operand mode: base_pre is already in the accumulators (loaded at the start of the tile); the output is again a difference,
+    // GELU(acc) - base_post[t]. 32 columns at a time: the base row's values are requested before the GELU arithmetic of those
+    // columns and consumed after it (8 float4 in flight: the register budget of this warp allows no more)
+    const float4* b4 = reinterpret_cast<const float4*>(p.base_post + (c.row % p.base_T) * static_cast<long long>(p.N) + gcol);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float4 x = __ldg(b4 + j);
-      f2_unpack(f2_add(f2_pack(acc[O + 4 * j], acc[O + 4 * j + 1]), f2_pack(x.x, x.y)), acc[O + 4 * j], acc[O + 4 * j + 1]);
-      f2_unpack(f2_add(f2_pack(acc[O + 4 * j + 2], acc[O + 4 * j + 3]), f2_pack(x.z, x.w)), acc[O + 4 * j + 2], acc[O + 4 * j + 3]);
+    for (int hh = 0; hh < 2; ++hh) {
+      float4 post[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) post[j] = __ldg(b4 + hh * 8 + j);
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) gelu_erf2(acc[O + hh * 32 + j], acc[O + hh * 32 + j + 1]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int e = O + hh * 32 + 4 * j;
+        f2_unpack(f2_sub(f2_pack(acc[e], acc[e + 1]), f2_pack(post[j].x, post[j].y)), acc[e], acc[e + 1]);
+        f2_unpack(f2_sub(f2_pack(acc[e + 2], acc[e + 3]), f2_pack(post[j].z, post[j].w)), acc[e + 2], acc[e + 3]);
+      }
     }
-  }
-  if (EPI == 1) {
+  } else if (EPI == 1) {
 #pragma unroll
     for (int j = 0; j < 64; j += 2) gelu_erf2(acc[O + j], acc[O + j + 1]);
   } else if (EPI == 4) {  // squared ReLU (Tranception MLP, tranception/activations.py:79-84)
@@ -243,16 +250,7 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
       acc[O + 32 + j] = b * co + a * s;
     }
   }
-  if (brow != nullptr) {  // the output is again a difference to the base row's activated value
-    const float4* b4 = reinterpret_cast<const float4*>(brow);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float4 x = __ldg(b4 + j);
-      f2_unpack(f2_sub(f2_pack(acc[O + 4 * j], acc[O + 4 * j + 1]), f2_pack(x.x, x.y)), acc[O + 4 * j], acc[O + 4 * j + 1]);
-      f2_unpack(f2_sub(f2_pack(acc[O + 4 * j + 2], acc[O + 4 * j + 3]), f2_pack(x.z, x.w)), acc[O + 4 * j + 2], acc[O + 4 * j + 3]);
-    }
-  }
-  if (EPI == 2 && p.mask_pos != nullptr && c.row_ok) {  // the masked row of each copy is updated by the compact exact path instead
+  if (EPI == 2 && DELTA && p.mask_pos != nullptr && c.row_ok) {  // the masked row of each copy is updated by the compact exact path instead
     const long long copy = c.row / p.base_T;
     if (c.row - copy * p.base_T == __ldg(p.mask_pos + copy)) {
 #pragma unroll
@@ -312,7 +310,7 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
   }
 }
 
-template <int EPI, int CTA2>
+template <int EPI, int CTA2, int DELTA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8,
@@ -479,12 +477,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       c.row = static_cast<long long>(c.grow0) + lane;
       c.row_ok = c.row < p.M;
       float acc[128];
+      const bool based = DELTA && p.base_pre != nullptr;  // delta-operand mode: the accumulators start from the shared base row, requested
+      if (based) {                                // now so that the loads complete while the tile's MMAs are still running
+        const float* brow = p.base_pre + (c.row % p.base_T) * static_cast<long long>(p.N) + c.gcol;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float4 x = (c.gcol + 4 * j < p.N) ? __ldg(reinterpret_cast<const float4*>(brow) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          acc[4 * j] = x.x; acc[4 * j + 1] = x.y; acc[4 * j + 2] = x.z; acc[4 * j + 3] = x.w;
+        }
+      }
       for (int ch = 0; ch < p.nchunks; ++ch, ++g) {
         const uint32_t buf = g & 1;
         mbar_wait(&tfull[buf], (g >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + half_id * 128;
-        if (ch == 0) {
+        if (ch == 0 && !based) {
           // first chunk: nothing accumulated yet, so all four 32-column loads go out together straight into the accumulators
           uint32_t r[4][32];
 #pragma unroll
@@ -533,8 +540,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           else mbar_arrive(&tempty[buf]);
         }
       }
-      finalize_group<EPI, 0>(acc, p, c);
-      finalize_group<EPI, 1>(acc, p, c);
+      finalize_group<EPI, 0, DELTA>(acc, p, c);
+      finalize_group<EPI, 1, DELTA>(acc, p, c);
     }
     if (lane == 0) bulk_wait0();  // all bulk stores of this warp have landed
   }
@@ -666,10 +673,13 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   static bool attr_set[64] = {};
   if (dev < 64 && !attr_set[dev]) {
 #define PG_SET_SMEM(E)                                                                                              \
-  PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<E, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)); \
-  PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<E, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM))
+  PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<E, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)); \
+  PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<E, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM))
     PG_SET_SMEM(0); PG_SET_SMEM(1); PG_SET_SMEM(2); PG_SET_SMEM(3); PG_SET_SMEM(4);
 #undef PG_SET_SMEM
+    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    PG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     attr_set[dev] = true;
   }
   const uint64_t K = static_cast<uint64_t>(g.K);
@@ -748,14 +758,16 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   p.grp_rows_a = g.grp_rows_a; p.grp_rows_b = g.grp_rows_b;
   p.base_pre = g.base_pre; p.base_post = g.base_post; p.base_T = g.base_T; p.mask_pos = g.mask_pos;
   const int ntiles = p.tiles_m * p.tiles_n;
+  const bool delta = g.base_pre != nullptr;
+  if (delta && (!cta2 || g.epi > 2)) return set_error(PG_ERR_UNSUPPORTED, "gemm: the delta-operand form runs on the CTA-pair kernel with epilogues 0, 1, 2");
   if (!cta2) {
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
     switch (g.epi) {
-      case 0: gemm_tc_kernel<0, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-      case 1: gemm_tc_kernel<1, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-      case 2: gemm_tc_kernel<2, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-      case 3: gemm_tc_kernel<3, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-      default: gemm_tc_kernel<4, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      case 0: gemm_tc_kernel<0, 0, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      case 1: gemm_tc_kernel<1, 0, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      case 2: gemm_tc_kernel<2, 0, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      case 3: gemm_tc_kernel<3, 0, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      default: gemm_tc_kernel<4, 0, 0><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
     }
     PG_CUDA_OK(cudaGetLastError());
     return PG_OK;
@@ -773,12 +785,22 @@ int launch_gemm(const GemmLaunch& g, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e;
+  if (delta) {
+    switch (g.epi) {
+      case 0: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<0, 1, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      case 1: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1, 1, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+      default: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, 1, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    }
+    PG_CUDA_OK(e);
+    PG_CUDA_OK(cudaGetLastError());
+    return PG_OK;
+  }
   switch (g.epi) {
-    case 0: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<0, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-    case 1: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-    case 2: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-    case 3: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<3, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
-    default: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<4, 1>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    case 0: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<0, 1, 0>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    case 1: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1, 1, 0>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    case 2: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2, 1, 0>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    case 3: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<3, 1, 0>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
+    default: e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<4, 1, 0>, tmA, tmB, tmA8, tmB8, tmHi, tmLo, tmRes, p); break;
   }
   PG_CUDA_OK(e);
   PG_CUDA_OK(cudaGetLastError());

@@ -645,7 +645,7 @@ def test_multi_site_error_growth_650m_vs_oracle():
     table = O.masked_marginal_table(O.load_state(st, "esm1v"), seq, "esm1v", arch.layers, arch.heads, batch=16)
     cfg = checkpoint.config_from_synth(arch)
     worst = {}
-    for prec in ("f16f8", "f16x3"):
+    for prec in ("f16f8", "f16x3", "f16d"):
         sc = scorer(arch, st, precision=prec, max_rows=65536)
         for k, lst in muts.items():
             got = sc.score_assay(seq, lst).astype(np.float64)
@@ -655,6 +655,7 @@ def test_multi_site_error_growth_650m_vs_oracle():
     for k, lst in muts.items():
         assert worst[(choose_precision(cfg, lst), k)] < TOL
     assert worst[("f16f8", 1)] < TOL and worst[("f16f8", 2)] < TOL
+    assert worst[("f16d", 1)] < TOL and worst[("f16d", 2)] < TOL  # delta operands: same rule as f16f8
 
 
 @pytest.mark.parametrize("L", [1, 2, 1022, 1023])
