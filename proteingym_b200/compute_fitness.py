@@ -61,10 +61,11 @@ def create_parser():
     for flags, kw in _FLAGS:
         p.add_argument(*flags, **kw)
     # additive (not in the reference)
-    p.add_argument("--precision", default="auto", choices=["auto", "f16f8", "f16x3", "f16"],
-                   help="tensor-core operand precision: auto (default) picks f16f8 (fp16 + e4m3 cross terms, 2 tensor-pipe units) or f16x3 (3 units) "
-                        "by model width and mutation depth (esm_engine.choose_precision); both meet the "
-                        "1e-3 parity bar; f16 (1 unit) is the fastest and does not")
+    p.add_argument("--precision", default="auto", choices=["auto", "f16d", "f16f8", "f16x3", "f16"],
+                   help="tensor-core operand precision: auto (default) picks f16d (delta operands, 1 tensor-pipe unit; ESM-1b / ESM-1v "
+                        "masked-marginals on one window), f16f8 (fp16 + e4m3 cross terms, 2 units) or f16x3 (3 units) by architecture, "
+                        "model width and mutation depth (esm_engine.choose_precision); all three meet the 1e-3 parity bar; f16 (1 unit, "
+                        "plain single pass) is fast and does not")
     p.add_argument("--device", type=int, default=0, help="CUDA device ordinal")
     return p
 
@@ -238,7 +239,8 @@ def main(args):
         if config.arch != "esm2" and len(args.sequence) + 2 > 1024 and args.scoring_strategy == "wt-marginals" \
                 and args.scoring_window != "overlapping":
             raise ValueError(f"Sequence length {len(args.sequence) + 2} above maximum  sequence length of 1024")  # modules.py:256-260
-        precision = choose_precision(config, df[mutant_col], args.scoring_strategy) if args.precision == "auto" else args.precision
+        precision = (choose_precision(config, df[mutant_col], args.scoring_strategy, seq_len=len(args.sequence))
+                     if args.precision == "auto" else args.precision)
         scorer = EsmScorer(config, state, precision=precision, device=args.device)
         print("Scoring with {} and model {} (operand precision {})".format(args.scoring_strategy, name, precision))
         df[name] = score_model(scorer, args, df, mutant_col, offset_idx)

@@ -22,14 +22,19 @@ from .windows import optimal_window_starts
 PRECISIONS = {"f16": _lib.PG_PREC_F16, "f16x3": _lib.PG_PREC_F16X3, "f16f8": _lib.PG_PREC_F16F8, "f16d": _lib.PG_PREC_F16D}
 
 
-def choose_precision(config: EsmConfig, mutants=None, strategy: str = "masked-marginals") -> str:
+def choose_precision(config: EsmConfig, mutants=None, strategy: str = "masked-marginals", seq_len: int = None) -> str:
     """``--precision auto``: the cheapest operand scheme whose MEASURED error meets the 1e-3 abs per-mutant bar for this job.
 
     f16f8 (2 tensor-pipe units) carries ~16-bit operands: per masked site its score error is 1.2e-4 mean / 4.5e-4 max at ESM-1v 650M
     (BLAT golden, 4997 mutants) and 6.1e-4 max at ESM2 3B; errors of independently masked sites add, so 5-site mutants reach 1.0e-3 at
     3B (tests/test_gpu_parity.py::test_golden_true_size_esm2_3b_multi_mutants). f16x3 (3 units, ~22-bit operands) stays at 8e-5 / 3.3e-4
-    in the same tests. Rule: f16f8 for models up to 1280 wide when no mutant has more than two sites (and for every strategy that reads
-    one row per site); f16x3 otherwise."""
+    in the same tests. f16d (delta operands, 1 unit: shared base rows at x3 precision + one fp16 pass on the per-copy difference; built
+    for the ESM-1b / ESM-1v masked-marginal pass over ONE shared window) measures 6.8e-5 mean / 3.9e-4 max on the same BLAT golden
+    (286 residues). Its error scales with the size of the perturbation one mask causes, i.e. ~1/L: on a 96-residue protein it is
+    7.6e-4 / 8.8e-4 / 1.5e-3 for 1 / 2 / 3 sites (f16f8: 3.4e-4 / 5.6e-4 / 6.0e-4; test_multi_site_error_growth_650m_vs_oracle), so
+    short proteins stay on f16f8.
+    Rule: for models up to 1280 wide when no mutant has more than two sites — f16d if the architecture and the strategy allow it and
+    192 <= ``seq_len`` (residues; + 2 tokens must fit the 1024-token window), else f16f8; f16x3 otherwise."""
     if config.embed_dim > 1280:
         return "f16x3"
     if strategy == "pseudo-ppl":  # sums L rows per sequence
@@ -42,6 +47,8 @@ def choose_precision(config: EsmConfig, mutants=None, strategy: str = "masked-ma
                 k = c
                 if k > 2:
                     return "f16x3"
+    if config.arch == "esm1b" and strategy == "masked-marginals" and seq_len is not None and 192 <= seq_len <= config.max_positions - 2:
+        return "f16d"
     return "f16f8"
 
 

@@ -38,7 +38,7 @@ def main(argv=None):
     ap.add_argument("--dms-input", required=True)
     ap.add_argument("--dms-output", required=True)
     ap.add_argument("--mutation-col", default="mutant")
-    ap.add_argument("--precision", default="auto", choices=["auto", "f16f8", "f16x3", "f16"],
+    ap.add_argument("--precision", default="auto", choices=["auto", "f16d", "f16f8", "f16x3", "f16"],
                     help="auto: per assay, the cheapest operand scheme that meets 1e-3 (esm_engine.choose_precision)")
     ap.add_argument("--indices", type=int, nargs="*", default=None, help="subset of dms_index values (default: all rows)")
     ap.add_argument("--partition", default="auto", choices=["auto", "assays", "positions"],
@@ -92,7 +92,7 @@ def main(argv=None):
                 frames[i] = pd.read_csv(os.path.join(a.dms_input, row["DMS_filename"]))
             t0 = time.time()
             muts = list(frames[i][col])
-            scorer = scorer_for(choose_precision(conf, muts) if a.precision == "auto" else a.precision)
+            scorer = scorer_for(choose_precision(conf, muts, seq_len=len(seq)) if a.precision == "auto" else a.precision)
             frames[i][name] = scorer.score_assay(seq, muts, off, shard=(rank, world) if by_pos else None).astype(np.float64)
             if not by_pos or rank == 0:
                 summary[(i, name)] = (time.time() - t0, len(frames[i]))
