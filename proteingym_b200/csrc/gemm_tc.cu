@@ -208,10 +208,21 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
       for (int j = 0; j < 64; ++j) acc[O + j] += (gcol + j < p.N) ? __ldg(p.bias + gcol + j) : 0.f;
     }
   }
+  if (DELTA && p.base_pre != nullptr) {
+    // delta-operand mode: the shared base row (W a0[t] + b) joins the accumulator before the activation. Read here, 64 columns at a
+    // time; starting the accumulators from it at the top of the tile (loads in flight while the MMAs run) measured slower for fc1
+    // (193 vs 157 ms/step: it forces the two-step accumulator read-out) and neutral for the other three GEMMs
+    const float4* b4 = reinterpret_cast<const float4*>(p.base_pre + (c.row % p.base_T) * static_cast<long long>(p.N) + gcol);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 x = __ldg(b4 + j);
+      f2_unpack(f2_add(f2_pack(acc[O + 4 * j], acc[O + 4 * j + 1]), f2_pack(x.x, x.y)), acc[O + 4 * j], acc[O + 4 * j + 1]);
+      f2_unpack(f2_add(f2_pack(acc[O + 4 * j + 2], acc[O + 4 * j + 3]), f2_pack(x.z, x.w)), acc[O + 4 * j + 2], acc[O + 4 * j + 3]);
+    }
+  }
   if (EPI == 1 && DELTA && p.base_post != nullptr) {
-    // delta-operand mode: base_pre is already in the accumulators (loaded at the start of the tile); the output is again a difference,
-    // GELU(acc) - base_post[t]: the base row's activated values are read after the GELU arithmetic, when its temporaries are dead
-    // (requesting them before it, 32 columns at a time, measured slower: 168 vs 157 ms/step for fc1)
+    // the output is again a difference, GELU(acc) - base_post[t]: the base row's activated values are read after the GELU arithmetic,
+    // when its temporaries are dead (requesting them before it, 32 columns at a time, measured slower: 168 vs 157 ms/step for fc1)
 #pragma unroll
     for (int j = 0; j < 64; j += 2) gelu_erf2(acc[O + j], acc[O + j + 1]);
     const float4* b4 = reinterpret_cast<const float4*>(p.base_post + (c.row % p.base_T) * static_cast<long long>(p.N) + gcol);
@@ -471,21 +482,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       c.row = static_cast<long long>(c.grow0) + lane;
       c.row_ok = c.row < p.M;
       float acc[128];
-      const bool based = DELTA && p.base_pre != nullptr;  // delta-operand mode: the accumulators start from the shared base row, requested
-      if (based) {                                // now so that the loads complete while the tile's MMAs are still running
-        const float* brow = p.base_pre + (c.row % p.base_T) * static_cast<long long>(p.N) + c.gcol;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float4 x = (c.gcol + 4 * j < p.N) ? __ldg(reinterpret_cast<const float4*>(brow) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          acc[4 * j] = x.x; acc[4 * j + 1] = x.y; acc[4 * j + 2] = x.z; acc[4 * j + 3] = x.w;
-        }
-      }
       for (int ch = 0; ch < p.nchunks; ++ch, ++g) {
         const uint32_t buf = g & 1;
         mbar_wait(&tfull[buf], (g >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + half_id * 128;
-        if (ch == 0 && !based) {
+        if (ch == 0) {
           // first chunk: nothing accumulated yet, so all four 32-column loads go out together straight into the accumulators
           uint32_t r[4][32];
 #pragma unroll
