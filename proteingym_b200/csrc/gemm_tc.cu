@@ -222,7 +222,8 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
   }
   if (EPI == 1 && DELTA && p.base_post != nullptr) {
     // the output is again a difference, GELU(acc) - base_post[t]: the base row's activated values are read after the GELU arithmetic,
-    // when its temporaries are dead (requesting them before it, 32 columns at a time, measured slower: 168 vs 157 ms/step for fc1)
+    // when its temporaries are dead (requesting them before it, 32 columns at a time, measured slower twice: 166 vs 158 ms/step for
+    // fc1, profiles/ab_r02_t_fc1_post_before_gelu.txt)
 #pragma unroll
     for (int j = 0; j < 64; j += 2) gelu_erf2(acc[O + j], acc[O + j + 1]);
     const float4* b4 = reinterpret_cast<const float4*>(p.base_post + (c.row % p.base_T) * static_cast<long long>(p.N) + gcol);
