@@ -90,7 +90,7 @@ def secondary(cats, arch, T, P, steps, precision, hbm):
     """Rooflines of the non-dominant kernels from the same event timings: LayerNorm against measured HBM bandwidth
     (algorithmic bytes: read 4d, write 2d per operand plane, per row), attention as algorithmic TFLOP/s (4*T^2*d per layer)."""
     out = {}
-    npl = 1 if precision == "f16" else 2
+    npl = 1 if precision in ("f16", "f16d") else 2  # f16d: LayerNorm writes ONE fp16 plane of differences (the base row it reads is L2-resident)
     rows = P * T
     if "layernorm" in cats and cats["layernorm"]["ms"] > 0:
         byts = 2 * arch.layers * rows * (4 * arch.embed_dim + 2 * arch.embed_dim * npl) * steps
