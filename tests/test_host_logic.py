@@ -241,3 +241,21 @@ def test_tranception_tokenize_batch_equals_per_sequence_tokenize():
         assert lens[r] == len(t) and ids[r, :len(t)].tolist() == t and (ids[r, len(t):] == PAD).all()
     e, l0 = tokenize_batch([], 4)
     assert e.shape == (0, 4) and l0.shape == (0,)
+
+
+def test_auto_precision_rule():
+    """esm_engine.choose_precision: f16d (delta operands) only where it was measured inside the 1e-3 bar — ESM-1b / ESM-1v
+    masked-marginals, 192..1022 residues (one shared window), at most two sites per mutant."""
+    from proteingym_b200.checkpoint import EsmConfig
+    from proteingym_b200.esm_engine import PRECISIONS, choose_precision
+    e1 = EsmConfig("esm1b", 33, 1280, 20, 5120, True, False)
+    e2 = EsmConfig("esm2", 33, 1280, 20, 5120, True, False)
+    e3b = EsmConfig("esm2", 36, 2560, 40, 10240, True, False)
+    single, double, triple = ["A5G", "C9D"], ["A5G:C9D", "E3F"], ["A5G:C9D:E3F"]
+    assert choose_precision(e1, single, seq_len=512) == "f16d" and choose_precision(e1, double, seq_len=192) == "f16d"
+    assert choose_precision(e1, single, seq_len=1022) == "f16d" and choose_precision(e1, single, seq_len=1023) == "f16f8"  # windows
+    assert choose_precision(e1, single, seq_len=191) == "f16f8" and choose_precision(e1, single) == "f16f8"  # short / unknown length
+    assert choose_precision(e1, triple, seq_len=512) == "f16x3"
+    assert choose_precision(e1, single, "wt-marginals", seq_len=512) == "f16f8" and choose_precision(e1, single, "pseudo-ppl", seq_len=512) == "f16x3"
+    assert choose_precision(e2, single, seq_len=512) == "f16f8" and choose_precision(e3b, single, seq_len=512) == "f16x3"
+    assert set(PRECISIONS) == {"f16", "f16x3", "f16f8", "f16d"}
