@@ -201,9 +201,9 @@ typedef struct {
    * Transformer runs its two products this way (esm/axial_attention.py:140,176). 0 = plain GEMM. */
   int32_t grp_rows_a, grp_rows_b;
   /* delta-operand form (PG_PREC_F16D): `a` holds differences to shared base rows t = row % base_T (M a multiple of base_T, N % 64 == 0);
-   * base_pre [base_T, N] fp32 is added to the accumulator before the activation, base_post [base_T, N] (or NULL) subtracted after
+   * base_pre [base_T, N] fp32 is added to the accumulator before the activation, base_post [base_T, N] fp16 (or NULL) subtracted after
    * it, and with epi 2 the rows (row / base_T) * base_T + mask_pos[row / base_T] receive no update (mask_pos device int32, or NULL). */
-  const float* base_pre; const float* base_post; int32_t base_T; const int32_t* mask_pos;
+  const float* base_pre; const void* base_post; int32_t base_T; const int32_t* mask_pos;
 } pg_gemm_args;
 int pg_gemm(const pg_gemm_args* args, pg_stream stream);
 
@@ -226,9 +226,9 @@ typedef struct {
   int32_t causal; const float* alibi_slopes; /* NULL = none */
   int32_t impl; /* 0 = the model's kernel (tcgen05/TMEM, 2 CTAs per SM, 128x64 blocks), 1 = mma.sync cross-check kernel */
   int32_t out_fmt; float out_scale; /* as pg_gemm_args (0 = auto); 2 only with impl 0 */
-  /* delta-operand form (impl 0): out = attention - base_o[t] (base_o fp32 [T, heads*64], or NULL); the full-precision value of row
+  /* delta-operand form (impl 0): out = attention - base_o[t] (base_o fp16 [T, heads*64], or NULL); the full-precision value of row
    * mask_pos[b] of every sequence b goes to row b of cout as an fp16 hi / lo pair (pitch ldc, lo plane at +c_lo_off), or NULL. */
-  const float* base_o; const int32_t* mask_pos; void* cout; int64_t ldc; int64_t c_lo_off;
+  const void* base_o; const int32_t* mask_pos; void* cout; int64_t ldc; int64_t c_lo_off;
 } pg_attn_args;
 int pg_attention(const pg_attn_args* args, pg_stream stream);
 

@@ -216,7 +216,7 @@ struct pg_handle_s {
   // `allocs`) and the compact exact q/k/v rows of the masked positions
   bool delta = false;
   float* base = nullptr;
-  size_t base_floats = 0;
+  size_t base_floats = 0;  // bytes allocated for `base`
   int base_T = 0;
   __half* cq = nullptr;
 };
@@ -358,15 +358,22 @@ int forward_rows(pg_handle h, const int32_t* tokens, int n_tokens, const int32_t
 // hold the mask (scripts/precision_delta.py, true ESM-1v 650M size: max score error 5.7e-4 at L = 96 against 1.5e-2 for a plain
 // single pass). The row that holds the mask (|D| ~ |a|) takes the compact exact path: P rows per layer through the x3 GEMMs, like
 // the pruned last layer. One tensor-pipe unit per algorithmic FLOP instead of two (fp16 + e4m3 cross terms) or three.
-//   base rows per layer (fp32 [T, n]): a0 = LN1 output, bqkv = Wqkv a0 + b, o0 = attention output, bout = Wo o0 + b, b0 = LN2 output,
-//   bfc1 = W1 b0 + b (pre-GELU), f0 = GELU output, bfc2 = W2 f0 + b.
-struct BaseRows { const float *a0, *bqkv, *o0, *bout, *b0, *bfc1, *f0, *bfc2; };
+//   base rows per layer, T rows each. Inputs of the four GEMMs, as ONE fp16 plane (any fixed reference works as long as the matching
+//   output rows were computed from exactly these values): a0 = rn16(LN1 output), o0 = rn16(attention output), b0 = rn16(LN2 output),
+//   f0 = rn16(GELU output). Their images, fp32: bqkv = Wqkv a0 + b, bout = Wo o0 + b, bfc1 = W1 b0 + b (pre-GELU), bfc2 = W2 f0 + b.
+struct BaseRows { const float *bqkv, *bout, *bfc1, *bfc2; const __half *a0, *o0, *b0, *f0; };
+size_t base_bytes(const pg_model_desc& D, int T) {
+  const size_t d = D.embed_dim, f = D.ffn_dim;
+  return static_cast<size_t>(D.layers) * T * (4 * (5 * d + f) + 2 * (3 * d + f));
+}
 BaseRows base_rows(pg_handle h, int l) {
   const long long T = h->base_T, d = h->desc.embed_dim, f = h->desc.ffn_dim;
-  const float* p = h->base + static_cast<long long>(l) * T * (8 * d + 2 * f);
+  const float* p = h->base + static_cast<long long>(l) * T * (5 * d + f);
+  const __half* q = reinterpret_cast<const __half*>(h->base + static_cast<long long>(h->desc.layers) * T * (5 * d + f)) +
+                    static_cast<long long>(l) * T * (3 * d + f);
   BaseRows b;
-  b.a0 = p; b.bqkv = p + T * d; b.o0 = p + T * 4 * d; b.bout = p + T * 5 * d; b.b0 = p + T * 6 * d; b.bfc1 = p + T * 7 * d;
-  b.f0 = p + T * (7 * d + f); b.bfc2 = p + T * (7 * d + 2 * f);
+  b.bqkv = p; b.bout = p + T * 3 * d; b.bfc1 = p + T * 4 * d; b.bfc2 = p + T * (4 * d + f);
+  b.a0 = q; b.o0 = q + T * d; b.b0 = q + T * 2 * d; b.f0 = q + T * 3 * d;
   return b;
 }
 
@@ -376,16 +383,16 @@ int forward_base(pg_handle h, const int32_t* tokens, int n_tokens, int T, cudaSt
   const pg_model_desc& D = h->desc;
   const int d = D.embed_dim, f = D.ffn_dim, np = h->np;
   const int64_t ldd = static_cast<int64_t>(d) * np, ldf = static_cast<int64_t>(f) * np, ldq = static_cast<int64_t>(3 * d) * np;
-  const size_t need = static_cast<size_t>(D.layers) * T * (8 * static_cast<size_t>(d) + 2 * static_cast<size_t>(f));
-  if (need > h->base_floats) {
+  const size_t need = base_bytes(D, T);
+  if (need > h->base_floats) {  // (base_floats counts bytes)
     if (h->base) cudaFree(h->base);
     h->base = nullptr; h->base_floats = 0;
-    cudaError_t e = cudaMalloc(&h->base, need * sizeof(float));
+    cudaError_t e = cudaMalloc(&h->base, need);
     if (e != cudaSuccess) return set_error(PG_ERR_CUDA, std::string("forward_base: cudaMalloc: ") + cudaGetErrorString(e));
     h->base_floats = need;
   }
   h->base_T = T;
-  PG_CUDA_OK(cudaMemsetAsync(h->base, 0, need * sizeof(float), s));  // the tap GEMMs reduce-add into zero
+  PG_CUDA_OK(cudaMemsetAsync(h->base, 0, need, s));  // the tap GEMMs reduce-add into zero
   EmbedLaunch e{};
   e.tokens = tokens; e.n_tokens = n_tokens; e.positions = nullptr; e.win_start = nullptr;
   e.P = 1; e.T = T; e.d = d; e.embed = h->embed; e.pos_table = h->pos;
@@ -403,18 +410,23 @@ int forward_base(pg_handle h, const int32_t* tokens, int n_tokens, int T, cudaSt
     t.resid = const_cast<float*>(dst);
     return run_lin(h, cat, t, s);
   };
-  auto unpack = [&](const __half* in, int64_t ld, int n, const float* dst) {
+  // The base row of a GEMM input is its fp16 hi plane: zero the lo plane of the T rows (the tap GEMM then multiplies exactly that
+  // plane by the full hi/lo weights) and keep a copy of the hi plane.
+  auto fix_base = [&](__half* buf, int64_t ld, int n, const __half* dst) -> int {
     ProfScope ps(CAT_OTHER, s);
-    return launch_unpack_hilo(in, ld, n, T, n, const_cast<float*>(dst), s);
+    PG_CUDA_OK(cudaMemset2DAsync(buf + n, ld * 2, 0, static_cast<size_t>(n) * 2, T, s));
+    PG_CUDA_OK(cudaMemcpy2DAsync(const_cast<__half*>(dst), static_cast<size_t>(n) * 2, buf, ld * 2, static_cast<size_t>(n) * 2, T,
+                                 cudaMemcpyDeviceToDevice, s));
+    return PG_OK;
   };
   for (int l = 0; l < D.layers; ++l) {
     const Layer& L = h->layers[l];
     const BaseRows B = base_rows(h, l);
     if ((rc = ln(L.ln1g, L.ln1b))) return rc;
-    if ((rc = unpack(h->abuf, ldd, d, B.a0))) return rc;
     Lin q{h->abuf, ldd, 0.f, L.wqkv, nullptr, L.bqkv, T, 3 * d, d, 0};
     q.out = h->qkv; q.out_fmt = 1;
     if ((rc = run_lin(h, CAT_GEMM_QKV, q, s))) return rc;
+    if ((rc = fix_base(h->abuf, ldd, d, B.a0))) return rc;
     if ((rc = tap(CAT_GEMM_QKV, h->abuf, ldd, L.wqkv, L.bqkv, 3 * d, d, B.bqkv))) return rc;
     AttnLaunch a{};
     a.qkv = h->qkv; a.ld = ldq; a.lo_off = 3 * d;
@@ -422,21 +434,21 @@ int forward_base(pg_handle h, const int32_t* tokens, int n_tokens, int T, cudaSt
     a.B = 1; a.T = T; a.heads = D.heads; a.nseg = 3; a.causal = 0; a.alibi_slopes = nullptr;
     { ProfScope ps(CAT_ATTN, s); rc = launch_attention_tc(a, s); }
     if (rc) return rc;
-    if ((rc = unpack(h->abuf, ldd, d, B.o0))) return rc;
     Lin o{h->abuf, ldd, 0.f, L.wo, nullptr, L.bo, T, d, d, 2};
     o.resid = h->x;
     if ((rc = run_lin(h, CAT_GEMM_OUT, o, s))) return rc;
+    if ((rc = fix_base(h->abuf, ldd, d, B.o0))) return rc;
     if ((rc = tap(CAT_GEMM_OUT, h->abuf, ldd, L.wo, L.bo, d, d, B.bout))) return rc;
     if ((rc = ln(L.ln2g, L.ln2b))) return rc;
-    if ((rc = unpack(h->abuf, ldd, d, B.b0))) return rc;
     Lin f1{h->abuf, ldd, 0.f, L.w1, nullptr, L.b1, T, f, d, 1};
     f1.out = h->fbuf; f1.out_fmt = 1;
     if ((rc = run_lin(h, CAT_GEMM_FC1, f1, s))) return rc;
+    if ((rc = fix_base(h->abuf, ldd, d, B.b0))) return rc;
     if ((rc = tap(CAT_GEMM_FC1, h->abuf, ldd, L.w1, L.b1, f, d, B.bfc1))) return rc;
-    if ((rc = unpack(h->fbuf, ldf, f, B.f0))) return rc;
     Lin f2{h->fbuf, ldf, 0.f, L.w2, nullptr, L.b2, T, d, f, 2};
     f2.resid = h->x;
     if ((rc = run_lin(h, CAT_GEMM_FC2, f2, s))) return rc;
+    if ((rc = fix_base(h->fbuf, ldf, f, B.f0))) return rc;
     if ((rc = tap(CAT_GEMM_FC2, h->fbuf, ldf, L.w2, L.b2, d, f, B.bfc2))) return rc;
   }
   return PG_OK;
@@ -444,7 +456,7 @@ int forward_base(pg_handle h, const int32_t* tokens, int n_tokens, int T, cudaSt
 
 // One single-pass GEMM on difference rows: C = epi(base_pre[t] + A_delta * W_hi^T) [- base_post[t]].
 int run_lin_delta(pg_handle h, int cat, const __half* a, int64_t lda, const __half* w, int M, int N, int K, int epi, const float* base_pre,
-                  const float* base_post, int T, const int32_t* mask_pos, __half* out, int64_t ldo, int out_fmt, float* resid,
+                  const __half* base_post, int T, const int32_t* mask_pos, __half* out, int64_t ldo, int out_fmt, float* resid,
                   cudaStream_t s) {
   GemmLaunch g{};
   g.a = a; g.lda = lda; g.w = w; g.ldw = static_cast<int64_t>(K) * h->np; g.bias = nullptr;  // W: the hi plane of the hi/lo rows
@@ -476,7 +488,7 @@ int forward_rows_delta(pg_handle h, const int32_t* tokens, int n_tokens, const i
   if (rc) return rc;
   { ProfScope ps(CAT_OTHER, s); rc = launch_gather_rows(h->x, emit_rows, Bc, T, d, h->xc, s); }  // xc = the masked rows, kept exact
   if (rc) return rc;
-  auto ln_delta = [&](const float* g, const float* b, const float* base) {   // all rows: LN(x) - base[t] -> abuf (fp16, pitch ldd)
+  auto ln_delta = [&](const float* g, const float* b, const __half* base) {   // all rows: LN(x) - base[t] -> abuf (fp16, pitch ldd)
     ProfScope ps(CAT_LN, s);
     return launch_layernorm_f16(h->x, d, g, b, rows, d, h->abuf, ldd, 0, s, 0, 0.f, 0, 0, base, T);
   };
@@ -1330,7 +1342,7 @@ int pg_gemm(const pg_gemm_args* a, pg_stream stream) {
   g.a_scale = a->a_scale; g.w_inv = a->w_inv; g.out_scale = a->out_scale;
   g.out_fmt = a->out_fmt ? a->out_fmt : (a->out_lo_off > 0 ? 1 : 0);
   g.grp_rows_a = a->grp_rows_a; g.grp_rows_b = a->grp_rows_b;
-  g.base_pre = a->base_pre; g.base_post = a->base_post; g.base_T = a->base_T; g.mask_pos = a->mask_pos;
+  g.base_pre = a->base_pre; g.base_post = static_cast<const __half*>(a->base_post); g.base_T = a->base_T; g.mask_pos = a->mask_pos;
   ProfScope ps(CAT_OTHER, static_cast<cudaStream_t>(stream));
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
@@ -1372,7 +1384,7 @@ int pg_attention(const pg_attn_args* a, pg_stream stream) {
   l.out = static_cast<__half*>(a->out); l.ldo = a->ldo; l.out_lo_off = a->out_lo_off;
   l.B = a->B; l.T = a->T; l.heads = a->heads; l.nseg = a->nseg; l.causal = a->causal; l.alibi_slopes = a->alibi_slopes;
   l.out_fmt = a->out_fmt ? a->out_fmt : -1; l.out_scale = a->out_scale;
-  l.base_o = a->base_o; l.mask_pos = a->mask_pos; l.cout = static_cast<__half*>(a->cout); l.ldc = a->ldc; l.c_lo_off = a->c_lo_off;
+  l.base_o = static_cast<const __half*>(a->base_o); l.mask_pos = a->mask_pos; l.cout = static_cast<__half*>(a->cout); l.ldc = a->ldc; l.c_lo_off = a->c_lo_off;
   if ((l.base_o || l.mask_pos) && a->impl != 0) return set_error(PG_ERR_UNSUPPORTED, "pg_attention: the delta-operand form needs impl 0");
   ProfScope ps(CAT_OTHER, static_cast<cudaStream_t>(stream));
   if (a->impl == 0) return launch_attention_tc(l, static_cast<cudaStream_t>(stream));   // the model's kernel (tcgen05)

@@ -58,7 +58,7 @@ struct Attn4Params {
   int out_fmt; float out_scale;  // common.h operand formats: 1 = fp16 lo plane, 2 = e4m3 [lo8 | hi8] planes for the out_proj GEMM
   int perm_C;                    // > 0: sequence b is column (b / perm_C, b % perm_C) of an alignment; output rows go to (., r, c) order
   // delta-operand mode (common.h AttnLaunch): out = attention - base_o[row]; full-precision hi / lo copy of row mask_pos[b] to cout[b]
-  const float* base_o; const int* mask_pos; __half* cout; long long ldc; long long c_lo_off;
+  const __half* base_o; const int* mask_pos; __half* cout; long long ldc; long long c_lo_off;
 };
 
 __device__ __forceinline__ float ex2a3(float x) {
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
       const float sh = p.out_scale, sl = p.out_scale * 2048.f;
       // delta-operand mode (DELTA): this row's exact value also goes to cout[b] when it is the masked row; base row to subtract
       const bool crow = DELTA && wr && p.mask_pos != nullptr && qidx == __ldg(p.mask_pos + b);
-      const float* brow = (DELTA && p.base_o != nullptr) ? p.base_o + static_cast<long long>(qidx) * p.d + h * 64 : nullptr;
+      const __half* brow = (DELTA && p.base_o != nullptr) ? p.base_o + static_cast<long long>(qidx) * p.d + h * 64 : nullptr;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {  // 32 head-dim columns at a time (register budget: 128 per thread at two CTAs per SM)
         uint32_t o[32];
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_tc4_kernel(const __grid_c
               *reinterpret_cast<uint32_t*>(cr + p.c_lo_off) = cvt2h(x0 - cf.x, x1 - cf.y);
             }
             if (DELTA && brow != nullptr) {
-              const float2 bq = __ldg(reinterpret_cast<const float2*>(brow + c * 32 + 2 * u));
+              const float2 bq = __half22float2(__ldg(reinterpret_cast<const __half2*>(brow + c * 32 + 2 * u)));
               x0 -= bq.x;
               x1 -= bq.y;
             }

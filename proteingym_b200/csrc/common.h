@@ -57,11 +57,12 @@ struct GemmLaunch {
   int grp_rows_a = 0, grp_rows_b = 0;
   // Delta-operand mode (api.cu forward_rows_delta): A holds the difference of each row to a shared base row t = row % base_T.
   //   base_pre  [base_T, N] fp32: added to the accumulator before the activation (W * base row + bias, computed once)
-  //   base_post [base_T, N] fp32: subtracted after the activation (the base row's own activated output), so that `out` is again a
-  //                               difference; null = `out` holds full values
+  //   base_post [base_T, N] fp16: subtracted after the activation (the base row's own activated output, rounded to fp16: any fixed
+  //                               reference works as long as the next layer's base_pre was computed from the same values), so that
+  //                               `out` is again a difference; null = `out` holds full values
   //   mask_pos  [M / base_T] (device): epi 2 only — row (row / base_T) * base_T + mask_pos[row / base_T] receives no update (its
   //                               exact value comes from the compact full-precision path)
-  const float* base_pre = nullptr; const float* base_post = nullptr; int base_T = 0; const int32_t* mask_pos = nullptr;
+  const float* base_pre = nullptr; const __half* base_post = nullptr; int base_T = 0; const int32_t* mask_pos = nullptr;
 };
 int launch_gemm(const GemmLaunch& g, cudaStream_t s);
 void set_gemm_kchunk(int v);    // tuning: see gemm_tc.cu
@@ -69,12 +70,10 @@ void set_gemm_prefetch(int v);
 void set_gemm_cta2(int v);      // 1: CTA-pair (cta_group::2) GEMM kernel
 
 // fmt / scale as above (fmt 0 when lo_off == 0).
-// base (optional, fp32 [base_T, d]): the output is LN(x[row]) - base[row % base_T] (delta-operand mode).
+// base (optional, fp16 [base_T, d]): the output is LN(x[row]) - base[row % base_T] (delta-operand mode).
 int launch_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int rows, int d, __half* out,
                          int64_t ldo, int64_t lo_off, cudaStream_t s, int fmt = -1, float scale = 0.f, int perm_R = 0, int perm_C = 0,
-                         const float* base = nullptr, int base_T = 0);
-// fp32 value of an operand row pair: out[r, c] = float(hi) + float(lo)  (in: [rows, ld] fp16 with the lo plane at lo_off, 0 = none)
-int launch_unpack_hilo(const __half* in, int64_t ld, int64_t lo_off, int rows, int n, float* out, cudaStream_t s);
+                         const __half* base = nullptr, int base_T = 0);
 // dst row (b * T + row_sel[b]) <- src row b, row_bytes each (a multiple of 16): the compact exact rows back into the full buffers
 int launch_scatter_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes, const int32_t* row_sel, int B, int T,
                         int row_bytes, cudaStream_t s);
@@ -94,9 +93,9 @@ struct AttnLaunch {
   // Column attention of an alignment (tcgen05 kernel only): the B sequences are the columns (b, c) of [R = T, C = perm_C] alignments;
   // output row (sequence (b, c), position r) is written to row (b, r, c) of `out`.
   int perm_C = 0;
-  // Delta-operand mode: base_o (fp32 [T, heads*64]) is subtracted from every output row t before rounding (out = attention - base);
+  // Delta-operand mode: base_o (fp16 [T, heads*64]) is subtracted from every output row t before rounding (out = attention - base);
   // the full-precision value of row mask_pos[b] of sequence b is additionally written as an fp16 hi / lo pair to row b of `cout`.
-  const float* base_o = nullptr; const int32_t* mask_pos = nullptr; __half* cout = nullptr; int64_t ldc = 0; int64_t c_lo_off = 0;
+  const __half* base_o = nullptr; const int32_t* mask_pos = nullptr; __half* cout = nullptr; int64_t ldc = 0; int64_t c_lo_off = 0;
 };
 int launch_attention(const AttnLaunch& a, cudaStream_t s);
 

@@ -41,7 +41,7 @@ template <int MAXV>  // float4 vectors per lane; d <= MAXV*128
 __global__ void layernorm_f16_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, int rows, int d, __half* __restrict__ out,
                                      long long ldo, long long lo_off, int fmt, float scale, int perm_R, int perm_C,
-                                     const float* __restrict__ base, int base_T) {
+                                     const __half* __restrict__ base, int base_T) {
   const int warps_per_block = blockDim.x >> 5;
   const long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -51,9 +51,9 @@ __global__ void layernorm_f16_kernel(const float* __restrict__ x, long long ldx,
   float4 v[MAXV];
   // delta-operand mode: the shared base row is read after the two reductions (holding it in registers from here on would halve the
   // occupancy of this latency-bound kernel: measured 74 vs 47 ms/step); an L1 prefetch now hides most of that later latency
-  const float4* qr = base ? reinterpret_cast<const float4*>(base + (row % base_T) * static_cast<long long>(d)) : nullptr;
+  const uint2* qr = base ? reinterpret_cast<const uint2*>(base + (row % base_T) * static_cast<long long>(d)) : nullptr;  // 4 halves per entry
   if (qr) {
-    for (int o = lane * 8; o < nv; o += 256) asm volatile("prefetch.global.L1 [%0];" ::"l"(qr + o));  // one 128-byte line per lane
+    for (int o = lane * 16; o < nv; o += 512) asm volatile("prefetch.global.L1 [%0];" ::"l"(qr + o));  // one 128-byte line per lane
   }
   float s = 0.f;
 #pragma unroll
@@ -92,8 +92,9 @@ __global__ void layernorm_f16_kernel(const float* __restrict__ x, long long ldx,
       float y[4] = {(v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
                     (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w};
       if (qr) {  // delta-operand mode: the difference to the shared base row, formed in fp32 before the fp16 rounding
-        const float4 q = __ldg(qr + idx);
-        y[0] -= q.x; y[1] -= q.y; y[2] -= q.z; y[3] -= q.w;
+        const uint2 q = __ldg(qr + idx);
+        const float2 q01 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), q23 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+        y[0] -= q01.x; y[1] -= q01.y; y[2] -= q23.x; y[3] -= q23.y;
       }
       __half h[4], l[4];
 #pragma unroll
@@ -378,30 +379,12 @@ int launch_gather_rows(const float* x, const int32_t* row_sel, int B, int T, int
   return PG_OK;
 }
 
-static __global__ void unpack_hilo_kernel(const __half* __restrict__ in, long long ld, long long lo_off, long long total, int n,
-                                   float* __restrict__ out) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const long long r = i / n;
-  const int c = static_cast<int>(i - r * n);
-  const __half* row = in + r * ld;
-  out[i] = __half2float(row[c]) + (lo_off > 0 ? __half2float(row[lo_off + c]) : 0.f);
-}
-
 static __global__ void scatter_rows_kernel(const uint8_t* __restrict__ src, long long src_pitch, uint8_t* __restrict__ dst, long long dst_pitch,
                                     const int32_t* __restrict__ row_sel, int T, int row_bytes) {
   const int b = blockIdx.x;
   const uint4* s = reinterpret_cast<const uint4*>(src + b * src_pitch);
   uint4* d = reinterpret_cast<uint4*>(dst + (static_cast<long long>(b) * T + row_sel[b]) * dst_pitch);
   for (int i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) d[i] = s[i];
-}
-
-int launch_unpack_hilo(const __half* in, int64_t ld, int64_t lo_off, int rows, int n, float* out, cudaStream_t s) {
-  const long long total = static_cast<long long>(rows) * n;
-  if (total <= 0) return PG_OK;
-  unpack_hilo_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, ld, lo_off, total, n, out);
-  PG_CUDA_OK(cudaGetLastError());
-  return PG_OK;
 }
 
 int launch_scatter_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes, const int32_t* row_sel, int B, int T,
@@ -417,7 +400,7 @@ int launch_scatter_rows(const void* src, int64_t src_pitch_bytes, void* dst, int
 }
 
 int launch_layernorm_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, int rows, int d, __half* out,
-                         int64_t ldo, int64_t lo_off, cudaStream_t s, int fmt, float scale, int perm_R, int perm_C, const float* base,
+                         int64_t ldo, int64_t lo_off, cudaStream_t s, int fmt, float scale, int perm_R, int perm_C, const __half* base,
                          int base_T) {
   if (rows <= 0) return PG_OK;
   if (base && (base_T <= 0 || perm_C > 0)) return set_error(PG_ERR_ARG, "layernorm: a base needs base_T > 0 and no row permutation");

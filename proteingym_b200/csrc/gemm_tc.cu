@@ -84,7 +84,7 @@ struct GemmKParams {
   int tiles_m, tiles_n;
   int prefetch;           // k-blocks of L2 look-ahead for the A operand (0 = off)
   // delta-operand mode (common.h GemmLaunch): shared base rows added before / subtracted after the activation, masked rows skipped
-  const float* base_pre; const float* base_post; int base_T; const int* mask_pos;
+  const float* base_pre; const __half* base_post; int base_T; const int* mask_pos;
   int grp_rows_a, grp_rows_b;  // grouped (block-diagonal) mode: A rows [g*grp_rows_a, (g+1)*grp_rows_a) pair with W rows g*grp_rows_b + n
 };
 
@@ -221,17 +221,25 @@ __device__ __forceinline__ void finalize_group(float (&acc)[128], const GemmKPar
     }
   }
   if (EPI == 1 && DELTA && p.base_post != nullptr) {
-    // the output is again a difference, GELU(acc) - base_post[t]: the base row's activated values are read after the GELU arithmetic,
-    // when its temporaries are dead (requesting them before it, 32 columns at a time, measured slower twice: 166 vs 158 ms/step for
-    // fc1, profiles/ab_r02_t_fc1_post_before_gelu.txt)
+    // the output is again a difference, GELU(acc) - base_post[t]. base_post is an fp16 plane (any fixed reference works: the next
+    // layer's base_pre was computed from these very values), so the 64 values of this group are 8 vector loads = 32 registers, few
+    // enough to be requested BEFORE the GELU arithmetic and consumed after it: one of the two L2 round trips per group disappears
+    // behind ~600 instructions (with fp32 values, 64 registers, the same reordering had to be split in halves and measured slower)
+    const uint4* b4 = reinterpret_cast<const uint4*>(p.base_post + (c.row % p.base_T) * static_cast<long long>(p.N) + gcol);
+    uint4 post[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) post[j] = __ldg(b4 + j);
 #pragma unroll
     for (int j = 0; j < 64; j += 2) gelu_erf2(acc[O + j], acc[O + j + 1]);
-    const float4* b4 = reinterpret_cast<const float4*>(p.base_post + (c.row % p.base_T) * static_cast<long long>(p.N) + gcol);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float4 x = __ldg(b4 + j);
-      f2_unpack(f2_sub(f2_pack(acc[O + 4 * j], acc[O + 4 * j + 1]), f2_pack(x.x, x.y)), acc[O + 4 * j], acc[O + 4 * j + 1]);
-      f2_unpack(f2_sub(f2_pack(acc[O + 4 * j + 2], acc[O + 4 * j + 3]), f2_pack(x.z, x.w)), acc[O + 4 * j + 2], acc[O + 4 * j + 3]);
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t w[4] = {post[j].x, post[j].y, post[j].z, post[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 q = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+        const int e = O + 8 * j + 2 * k;
+        f2_unpack(f2_sub(f2_pack(acc[e], acc[e + 1]), f2_pack(q.x, q.y)), acc[e], acc[e + 1]);
+      }
     }
   } else if (EPI == 1) {
 #pragma unroll

@@ -25,7 +25,7 @@ def test_gemm_delta_epilogue_matches_fp64(M_copies, T, N, K, epi):
     D = (torch.randn(M, K, device="cuda", generator=g) * 0.1).half().contiguous()
     W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half().contiguous()
     base_pre = torch.randn(T, N, device="cuda", generator=g)
-    base_post = torch.randn(T, N, device="cuda", generator=g)
+    base_post = torch.randn(T, N, device="cuda", generator=g).half()   # the activated base row is an fp16 plane
     mask_pos = torch.randint(0, T, (M_copies,), device="cuda", generator=g, dtype=torch.int32)
     t = torch.arange(M, device="cuda") % T
     acc = D.double() @ W.double().T + base_pre.double()[t]
@@ -69,7 +69,7 @@ def test_attention_delta_outputs_match_fp64(B, T, H):
     eff = q16[:, :3 * d].double() + q16[:, 3 * d:].double()
     q, k, v = [eff[:, i * d:(i + 1) * d].view(B, T, H, 64).transpose(1, 2) for i in range(3)]
     ref = (torch.softmax(q @ k.transpose(-1, -2), -1) @ v).transpose(1, 2).reshape(B * T, d)
-    base = ref.view(B, T, d)[0].float().contiguous() + 0.05 * torch.randn(T, d, device="cuda", generator=g)
+    base = (ref.view(B, T, d)[0].float() + 0.05 * torch.randn(T, d, device="cuda", generator=g)).half().contiguous()  # fp16 base rows
     mask_pos = torch.randint(0, T, (B,), device="cuda", generator=g, dtype=torch.int32)
     out = torch.zeros(B * T, 2 * d, device="cuda", dtype=torch.float16)
     cout = torch.zeros(B, 2 * d, device="cuda", dtype=torch.float16)
