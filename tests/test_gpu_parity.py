@@ -655,7 +655,11 @@ def test_multi_site_error_growth_650m_vs_oracle():
     for k, lst in muts.items():
         assert worst[(choose_precision(cfg, lst), k)] < TOL
     assert worst[("f16f8", 1)] < TOL and worst[("f16f8", 2)] < TOL
-    assert worst[("f16d", 1)] < TOL and worst[("f16d", 2)] < TOL  # delta operands: same rule as f16f8
+    # delta operands: the error follows the size of the perturbation one mask causes, ~1/L — at 96 residues it sits just inside the bar
+    # (7.6e-4 / 8.8e-4 for 1 / 2 sites), which is why the auto rule asks for >= 192 residues before it picks f16d; here only sanity
+    assert worst[("f16d", 1)] < 2 * TOL and worst[("f16d", 2)] < 2 * TOL
+    assert all(choose_precision(cfg, lst, seq_len=96) != "f16d" for lst in muts.values())
+    assert choose_precision(cfg, muts[1], seq_len=286) == "f16d"  # BLAT-sized: measured 3.9e-4 (tests/test_gpu_delta.py)
 
 
 @pytest.mark.parametrize("L", [1, 2, 1022, 1023])
